@@ -1,0 +1,163 @@
+/*
+ * kfb200.h - C ABI of libkfb200.so: B200 (sm_100a) batched Kalman-filter
+ * log-likelihood and reverse-mode gradient.
+ *
+ * This is the drop-in boundary for the ONE hot path of jessegrabowski/pymc_statespace:
+ * what `BaseFilter.build_graph` (reference pymc_statespace/filters/kalman_filter.py:126-193)
+ * computes with `pytensor.scan`, and what PyTensor autodiff of that scan computes for
+ * `pm.Potential("log_likelihood")` (reference pymc_statespace/core/statespace.py:174).
+ * The reference is pure Python (no FFI of its own); the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to float64 (or int32 where stated) unless the
+ *    parameter name starts with `h_`; the caller owns every buffer; the library never
+ *    allocates caller-visible memory and keeps no global state;
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - a "unit" is one independent recursion: unit u = draw * n_series + series;
+ *    parameter matrices are indexed by draw (u / n_series), observations by series
+ *    (u % n_series);
+ *  - matrices are dense row-major with the reference's shapes: a0[m] P0[m,m] T[m,m] Z[p,m]
+ *    R[m,r] H[p,p] Q[r,r] c[m] d[p], y[n,p] (NaN = missing observation);
+ *  - `*_bs` is the stride in ELEMENTS between consecutive draws (series for y); 0 means the
+ *    array is shared by all draws.  `*_ts` is the stride between consecutive time steps for
+ *    a time-varying matrix (reference filters/utilities.py:1-20: 3-D, time-first); 0 = static;
+ *  - errors: integer status (0 = OK), never C++ exceptions; numerical failures are reported
+ *    per unit in `info[u]` (0 ok; t+1 > 0: innovation covariance F_t not positive definite at
+ *    0-based step t; -(t+1) < 0: partially-missing y_t in a filter that only supports
+ *    all-or-nothing rows - reference raises LinAlgError there) and the
+ *    unit's loglik is NaN.
+ */
+#ifndef KFB200_H
+#define KFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFB_VERSION 100
+
+typedef int32_t kfb_status;
+enum {
+  KFB_OK = 0,
+  KFB_ERR_INVALID_ARG = 1,   /* null pointer / non-positive size / bad enum          */
+  KFB_ERR_UNSUPPORTED = 2,   /* valid request this build has no kernel for           */
+  KFB_ERR_WORKSPACE = 3,     /* workspace too small / missing                        */
+  KFB_ERR_CUDA = 4           /* a CUDA runtime call failed (see kfb_last_cuda_error) */
+};
+
+/* FILTER_FACTORY keys, reference pymc_statespace/core/statespace.py:25-31 */
+enum {
+  KFB_STANDARD = 0,     /* StandardFilter         kalman_filter.py:255-284 */
+  KFB_UNIVARIATE = 1,   /* UnivariateFilter       kalman_filter.py:444-505 */
+  KFB_STEADY_STATE = 2, /* SteadyStateFilter      kalman_filter.py:354-441 */
+  KFB_SINGLE = 3,       /* SingleTimeseriesFilter kalman_filter.py:321-351 */
+  KFB_CHOLESKY = 4      /* CholeskyFilter         kalman_filter.py:287-318 */
+};
+
+/* flags */
+#define KFB_FLAG_CORRECTED 1u  /* strict_reference=False: fix SURVEY.md A.2 quirks Q1,Q4,Q5,Q6 */
+#define KFB_FLAG_FORCE_COOP 2u /* testing: use the cooperative (shared-memory) kernels even   */
+                               /* when a thread-per-unit instantiation exists                   */
+
+typedef struct kfb_desc {
+  int32_t filter_kind;
+  uint32_t flags;
+  int64_t n_draws;  /* parameter draws                          */
+  int64_t n_series; /* observation series (>=1); units = n_draws * n_series */
+  int32_t n, m, p, r; /* time steps, k_states, k_endog, k_posdef */
+  /* batch strides (elements); 0 = shared */
+  int64_t y_bs, a0_bs, P0_bs, T_bs, Z_bs, R_bs, H_bs, Q_bs, c_bs, d_bs;
+  /* time strides (elements); 0 = static.  steady_state and univariate take static matrices
+     only (reference kalman_filter.py:421,482 fixed-signature steps)                        */
+  int64_t T_ts, Z_ts, R_ts, H_ts, Q_ts, c_ts, d_ts;
+} kfb_desc;
+
+typedef struct kfb_inputs {
+  const double *y, *a0, *P0, *T, *Z, *R, *H, *Q;
+  const double *c, *d; /* may be NULL = zeros (initialize_intercepts, kalman_filter.py:37-51) */
+} kfb_inputs;
+
+/* Outputs of build_graph (kalman_filter.py:184-191), batched over units (leading dim U).
+ * Any pointer may be NULL = not wanted.  loglik[U]; ll_obs[U,n]; filtered_states[U,n,m];
+ * predicted_states[U,n+1,m] (a0 first); filtered_covs[U,n,m,m]; predicted_covs[U,n+1,m,m]
+ * (P0 first); info[U] int32. */
+typedef struct kfb_outputs {
+  double *loglik, *ll_obs, *filtered_states, *predicted_states, *filtered_covs, *predicted_covs;
+  int32_t *info;
+} kfb_outputs;
+
+/* Cotangents: the differentiated scalar per unit is
+ *   g_loglik[u] * loglik[u] + sum_t g_ll_obs[u,t] * ll_obs[u,t];  NULL g_loglik = 1, NULL g_ll_obs = 0. */
+typedef struct kfb_cotangents {
+  const double *g_loglik, *g_ll_obs;
+} kfb_cotangents;
+
+/* Gradients, one block per UNIT (never reduced over shared inputs): a0[U,m] P0[U,m,m]
+ * T[U,(n,)m,m] Z[U,(n,)p,m] R[U,(n,)m,r] H[U,(n,)p,p] Q[U,(n,)r,r] c[U,(n,)m] d[U,(n,)p] - the (n,)
+ * dimension is present iff that input is time-varying.  NULL = not wanted. */
+typedef struct kfb_grads {
+  double *a0, *P0, *T, *Z, *R, *H, *Q, *c, *d;
+} kfb_grads;
+
+int32_t kfb_version(void);
+const char *kfb_status_string(kfb_status s);
+const char *kfb_last_cuda_error(void);
+
+/* Bytes of device workspace kfb_forward / kfb_backward need.  `save_for_backward` != 0 adds
+ * the forward-pass tape of predicted moments (a_t, P_t) the adjoint kernel reads back. */
+kfb_status kfb_workspace_bytes(const kfb_desc *desc, int32_t save_for_backward, size_t *bytes);
+
+/* Forward recursion: replaces the scan at kalman_filter.py:152-159 (and :388-395, :491-496). */
+kfb_status kfb_forward(const kfb_desc *desc, const kfb_inputs *in, const kfb_outputs *out,
+                       void *workspace, size_t workspace_bytes, int32_t save_for_backward,
+                       void *stream);
+
+/* Reverse-mode adjoint of kfb_forward wrt (a0,P0,T,Z,R,H,Q,c,d): replaces PyTensor's Scan.L_op
+ * of the same graph.  `workspace` must be the buffer a preceding
+ * kfb_forward(..., save_for_backward=1) on the same desc/inputs filled. */
+kfb_status kfb_backward(const kfb_desc *desc, const kfb_inputs *in, const kfb_cotangents *cot,
+                        const kfb_grads *grads, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* Stationary initial covariance: X = A X A^T + C with C = R Q R^T
+ * (reference models/SARIMAX.py:100-107, models/VARMAX.py:143-150:
+ *  solve_discrete_lyapunov(T, R Q R^T, method="bilinear")).  X[B,m,m]; info[B] (0 ok, 1 = no
+ * convergence: spectral radius >= 1).  Backward: given Xbar[B,m,m] accumulates (+=) into
+ * Abar[B,m,m], Rbar[B,m,r], Qbar[B,r,r] (any may be NULL). */
+kfb_status kfb_lyapunov_forward(int64_t B, int32_t m, int32_t r, const double *A, int64_t A_bs,
+                                const double *R, int64_t R_bs, const double *Q, int64_t Q_bs,
+                                double *X, int32_t *info, void *stream);
+kfb_status kfb_lyapunov_backward(int64_t B, int32_t m, int32_t r, const double *A, int64_t A_bs,
+                                 const double *R, int64_t R_bs, const double *Q, int64_t Q_bs,
+                                 const double *X, const double *Xbar, double *Abar, double *Rbar,
+                                 double *Qbar, void *stream);
+
+/* theta -> system matrices ("base + scatter(theta)": every reference model's update() is a
+ * set_subtensor of theta slices into constant matrices, models/SARIMAX.py:59-98,
+ * models/VARMAX.py:95-141, models/local_level.py:28-49).  `dst` is one packed block of
+ * `block` doubles per draw, initialised from base[block]; dst[b, dst_idx[k]] = theta[b, src_idx[k]].
+ * Backward: gtheta[b, src_idx[k]] += gdst[b, dst_idx[k]] (gtheta must be zeroed by the caller). */
+kfb_status kfb_scatter_forward(int64_t B, int32_t n_theta, int32_t block, int32_t n_map,
+                               const double *theta, const double *base, const int32_t *src_idx,
+                               const int32_t *dst_idx, double *dst, void *stream);
+kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32_t n_map,
+                                const double *gdst, const int32_t *src_idx, const int32_t *dst_idx,
+                                double *gtheta, void *stream);
+
+/* FP64 roofline denominator: `iters` dependent-chain DFMA rounds on every SM.  Returns through
+ * h_flops the number of floating-point operations the launch executes (2 per FMA); the caller
+ * times it with CUDA events.  sink[>= 1] receives a checksum so the work cannot be elided. */
+kfb_status kfb_fp64_peak(int32_t iters, int32_t blocks, int32_t threads, double *sink,
+                         double *h_flops, void *stream);
+
+/* How many kernels this library has launched in this process (bench.py "gpu_launches"). */
+int64_t kfb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFB200_H */

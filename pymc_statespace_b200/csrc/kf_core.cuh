@@ -1,0 +1,763 @@
+// kf_core.cuh - the Kalman recursion and its adjoint, written ONCE over an execution-context
+// policy X:
+//   ThreadCtx<M,P>  one unit per thread, compile-time dims, every matrix in registers
+//   CoopCtx         G lanes (a warp or a whole CTA) per unit, run-time dims, matrices in shared memory
+//   (tests/hostsim) the same code compiled for the host so the math can be debugged without a GPU
+//
+// What is computed (reference pymc_statespace/filters/kalman_filter.py):
+//   per step  mask (:196-213) -> update (:255-284 | :287-318 | :333-351 | :399-419 | :460-480)
+//             -> predict (:216-223); outputs assembled as in :166-193.
+//   adjoint   reverse recursion of SURVEY.md appendix B (the reference's gradient is PyTensor
+//             autodiff of the scan; there is no reference source for it).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define KFB_HD __host__ __device__ __forceinline__
+#else
+#define KFB_HD inline
+#endif
+
+namespace kfb {
+
+constexpr double KF_LOG_2PI = 1.8378770664093454835606594728112;  // MVN_CONST kalman_filter.py:16
+constexpr double KF_LN2 = 0.69314718055994530941723212145818;
+
+enum MathKind : int { MK_STD = 0, MK_UNIV = 1, MK_STEADY = 2, MK_CHOLS = 3 };
+enum SizeClass : int { SZ_M = 0, SZ_P = 1, SZ_MM = 2, SZ_MP = 3, SZ_PP = 4 };
+
+struct MatArg {
+  const double* p;
+  long long bs;  // stride between draws (series for y); 0 = shared
+  long long ts;  // stride between time steps; 0 = static
+};
+
+struct KfArgs {
+  long long U, n_series;
+  int n, m, p, math_kind;
+  MatArg y, a0, P0, T, Z, H, C, c, d, Pss, Gss;  // C = R Q R^T (hoisted, predict :219)
+  double ll_const;  // multiple of log(2 pi) per observed step (p-independent quirk Q1)
+  double d_sign;    // v = y - Z a - d_sign * d  (Q5: -1 for "single", Q6: 0 for "steady_state")
+  // forward outputs (any may be null)
+  double *loglik, *ll_obs, *fs, *ps, *fc, *pc;
+  int* info;
+  double* tape;  // predicted (a_t, tri(P_t)) for t = 1..n-1
+  // backward
+  const double *g_loglik, *g_ll_obs;
+  double *ga0, *gP0, *gT, *gZ, *gH, *gC, *gc, *gd, *gPss, *gGss;
+};
+
+KFB_HD int tape_width(int m) { return m + (m * (m + 1)) / 2; }
+
+KFB_HD double kf_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return fma(a, b, c);
+#else
+  return a * b + c;  // host simulation only
+#endif
+}
+
+KFB_HD bool kf_isnan(double v) { return v != v; }
+
+// Deferred logarithm: sum_t log(f_t) = log(prod mantissas) + ln2 * sum exponents.  One fp64 multiply
+// and a few integer ops per factor instead of a ~40-instruction fp64 log on the serial critical path.
+struct LogAcc {
+  double mant;
+  int expo;
+  int count;
+  KFB_HD LogAcc() : mant(1.0), expo(0), count(0) {}
+  KFB_HD void mul(double f) {  // f must be a positive normal number (checked by the caller)
+    mant *= f;               // mant in [1,2) * f
+    int hi;
+#if defined(__CUDA_ARCH__)
+    hi = __double2hiint(mant);
+    int e = ((hi >> 20) & 0x7ff) - 1023;
+    expo += e;
+    mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
+#else
+    long long bits;
+    std::memcpy(&bits, &mant, 8);
+    hi = (int)(bits >> 32);
+    int e = ((hi >> 20) & 0x7ff) - 1023;
+    expo += e;
+    bits -= ((long long)e) << 52;
+    std::memcpy(&mant, &bits, 8);
+#endif
+  }
+  KFB_HD double value() const { return log(mant) + KF_LN2 * (double)expo; }
+};
+
+#define KFB_FOR(i, cnt) _Pragma("unroll") for (int i = x.lane(); i < (cnt); i += x.G())
+
+// C (r x c)  = / += / -=  op(A) (r x kk) * op(B) (kk x c);  row-major storage of the un-transposed operand
+template <bool TA, bool TB, int MODE, class X, class TC, class TAa, class TBb>
+KFB_HD void gemm(X& x, TC& C, const TAa& A, const TBb& B, int r, int kk, int c) {
+  KFB_FOR(idx, r * c) {
+    const int i = idx / c, j = idx - i * c;
+    double s = (MODE == 0) ? 0.0 : C[idx];
+#pragma unroll
+    for (int k = 0; k < kk; ++k) {
+      const double av = A[TA ? k * r + i : i * kk + k];
+      const double bv = B[TB ? j * kk + k : k * c + j];
+      s = kf_fma(MODE == 2 ? -av : av, bv, s);
+    }
+    C[idx] = s;
+  }
+  x.sync();
+}
+
+template <class X, class TD>
+KFB_HD void load_or_zero(X& x, TD& dst, const double* src, int cnt) {
+  KFB_FOR(i, cnt) dst[i] = src ? src[i] : 0.0;
+}
+
+// Symmetric positive-definite p x p inverse via L D L^T (no square roots).  Reads the lower triangle
+// of F.  Serial; executed by one lane.  piv[] receives D (det F = prod D).  Returns false if a pivot
+// is not a positive finite number.
+template <class TF, class TG, class TL, class TP>
+KFB_HD bool ldl_inverse(const TF& F, TG& G, TL& L, TL& Li, TP& piv, int p) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < p; ++j) {
+    double dj = F[j * p + j];
+#pragma unroll
+    for (int k = 0; k < p; ++k)
+      if (k < j) dj = kf_fma(-L[j * p + k] * L[j * p + k], piv[k], dj);
+    piv[j] = dj;
+    ok = ok && (dj > 0.0) && (dj < 1.0e300);
+    const double rj = 1.0 / dj;
+#pragma unroll
+    for (int i = 0; i < p; ++i) {
+      if (i > j) {
+        double s = F[i * p + j];
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          if (k < j) s = kf_fma(-L[i * p + k] * L[j * p + k], piv[k], s);
+        L[i * p + j] = s * rj;
+      }
+    }
+    L[j * p + j] = rj;  // store 1/D on the diagonal
+  }
+  // Li = L^{-1} (unit lower triangular)
+#pragma unroll
+  for (int c = 0; c < p; ++c) {
+#pragma unroll
+    for (int i = 0; i < p; ++i) {
+      if (i == c) Li[i * p + c] = 1.0;
+      if (i < c) Li[i * p + c] = 0.0;
+      if (i > c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          if (k >= c && k < i) s = kf_fma(-L[i * p + k], Li[k * p + c], s);
+        Li[i * p + c] = s;
+      }
+    }
+  }
+  // G = Li^T D^{-1} Li
+#pragma unroll
+  for (int i = 0; i < p; ++i) {
+#pragma unroll
+    for (int j = 0; j < p; ++j) {
+      if (j <= i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          if (k >= i) s = kf_fma(Li[k * p + i] * L[k * p + k], Li[k * p + j], s);
+        G[i * p + j] = s;
+        G[j * p + i] = s;
+      }
+    }
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-unit constant parameters + scratch, allocated from the context (registers or shared memory)
+// ------------------------------------------------------------------------------------------------
+template <class X>
+struct Params {
+  typename X::template Buf<SZ_MM> T;
+  typename X::template Buf<SZ_MP> Z;   // p x m
+  typename X::template Buf<SZ_PP> H;
+  typename X::template Buf<SZ_P> d;
+  typename X::template Buf<SZ_PP> Gss;  // steady state only
+  KFB_HD Params(X& x) : T(x), Z(x), H(x), d(x), Gss(x) {}
+};
+
+template <class X>
+struct UpdTmp {
+  typename X::template Buf<SZ_P> v, w, piv;
+  typename X::template Buf<SZ_MP> Mm, K, KH;
+  typename X::template Buf<SZ_PP> F, Fi, L, Li;
+  typename X::template Buf<SZ_MM> A, S1, S2;
+  KFB_HD UpdTmp(X& x) : v(x), w(x), piv(x), Mm(x), K(x), KH(x), F(x), Fi(x), L(x), Li(x), A(x), S1(x), S2(x) {}
+};
+
+struct StepStat {
+  double quad;    // v^T G v
+  double logdet;  // only when per-step logs are requested
+  bool ok;
+};
+
+// Update for an observed row.  MK_STD: StandardFilter / CholeskyFilter(p=1 or corrected) /
+// SingleTimeseriesFilter; MK_STEADY: SteadyStateFilter (gain uses the fixed Gss).
+// Outputs af, Pf and keeps v, Mm, F, Fi(=F^-1), K, A, w in `u` for the adjoint.
+template <int MK, class X, class TA, class TPm>
+KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, double d_sign, const TA& a,
+                                const TPm& P, UpdTmp<X>& u, TA& af, TPm& Pf, LogAcc* acc, bool per_step_log) {
+  const int m = x.m(), p = x.p();
+  StepStat st;
+  KFB_FOR(i, p) {
+    double s = yt[i] - d_sign * prm.d[i];
+#pragma unroll
+    for (int k = 0; k < m; ++k) s = kf_fma(-prm.Z[i * m + k], a[k], s);
+    u.v[i] = s;
+  }
+  gemm<false, true, 0>(x, u.Mm, P, prm.Z, m, m, p);  // Mm = P Z^T
+  KFB_FOR(idx, p * p) {
+    const int i = idx / p, j = idx - i * p;
+    double s = prm.H[idx];
+#pragma unroll
+    for (int k = 0; k < m; ++k) s = kf_fma(prm.Z[i * m + k], u.Mm[k * p + j], s);
+    u.F[idx] = s;
+  }
+  x.sync();
+  st.ok = true;
+  st.logdet = 0.0;
+  if (x.lane() == 0) {
+    st.ok = ldl_inverse(u.F, u.Fi, u.L, u.Li, u.piv, p);
+    if (st.ok) {
+#pragma unroll
+      for (int i = 0; i < p; ++i) {
+        if (per_step_log) st.logdet += log(u.piv[i]);
+        else if (acc) acc->mul(u.piv[i]);
+      }
+    }
+  }
+  x.sync();
+  if (MK == MK_STEADY) {
+    gemm<false, false, 0>(x, u.K, u.Mm, prm.Gss, m, p, p);
+    KFB_FOR(i, p) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < p; ++j) s = kf_fma(prm.Gss[i * p + j], u.v[j], s);
+      u.w[i] = s;
+    }
+  } else {
+    gemm<false, false, 0>(x, u.K, u.Mm, u.Fi, m, p, p);
+    KFB_FOR(i, p) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < p; ++j) s = kf_fma(u.Fi[i * p + j], u.v[j], s);
+      u.w[i] = s;
+    }
+  }
+  KFB_FOR(idx, m * m) {  // A = I - K Z
+    const int i = idx / m, j = idx - i * m;
+    double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < p; ++k) s = kf_fma(-u.K[i * p + k], prm.Z[k * m + j], s);
+    u.A[idx] = s;
+  }
+  KFB_FOR(i, m) {
+    double s = a[i];
+#pragma unroll
+    for (int k = 0; k < p; ++k) s = kf_fma(u.K[i * p + k], u.v[k], s);
+    af[i] = s;
+  }
+  x.sync();
+  double q = 0.0;
+#pragma unroll
+  for (int i = 0; i < p; ++i) q = kf_fma(u.v[i], u.w[i], q);
+  st.quad = q;
+  gemm<false, false, 0>(x, u.S1, u.A, P, m, m, m);      // A P
+  gemm<false, true, 0>(x, Pf, u.S1, u.A, m, m, m);      // (A P) A^T
+  gemm<false, false, 0>(x, u.KH, u.K, prm.H, m, p, p);  // K H
+  gemm<false, true, 1>(x, Pf, u.KH, u.K, m, p, m);      // + (K H) K^T   Joseph form :278
+  return st;
+}
+
+// predict, kalman_filter.py:216-223.  a <- T af + c ; P <- sym(T Pf T^T + C)
+template <class X, class TT, class TC, class Tc, class TA, class TPm, class TS>
+KFB_HD void predict(X& x, const TT& T, const TC& C, const Tc& c, const TA& af, const TPm& Pf, TA& a, TPm& P, TS& S1,
+                    TS& S2) {
+  const int m = x.m();
+  KFB_FOR(i, m) {
+    double s = c[i];
+#pragma unroll
+    for (int k = 0; k < m; ++k) s = kf_fma(T[i * m + k], af[k], s);
+    a[i] = s;
+  }
+  gemm<false, false, 0>(x, S1, T, Pf, m, m, m);
+  KFB_FOR(idx, m * m) S2[idx] = C[idx];
+  x.sync();
+  gemm<false, true, 1>(x, S2, S1, T, m, m, m);
+  KFB_FOR(idx, m * m) {
+    const int i = idx / m, j = idx - i * m;
+    P[idx] = 0.5 * (S2[idx] + S2[j * m + i]);
+  }
+  x.sync();
+}
+
+// One inner step of the univariate filter (kalman_filter.py:460-480) on observation i; in place.
+// Returns false if the observation is skipped (NaN or F == 0).  Kv <- K, *vo <- v, *Fo <- F.
+template <class X, class TA, class TPm, class TK>
+KFB_HD bool univariate_inner(X& x, const Params<X>& prm, const double* yt, double d_sign, int i, TA& a, TPm& P, TK& Mv,
+                             TK& Kv, double* vo, double* Fo) {
+  const int m = x.m(), p = x.p();
+  const double yi = yt[i];
+  if (kf_isnan(yi)) return false;
+  double v = yi - d_sign * prm.d[i];
+#pragma unroll
+  for (int k = 0; k < m; ++k) v = kf_fma(-prm.Z[i * m + k], a[k], v);
+  KFB_FOR(r, m) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < m; ++k) s = kf_fma(P[r * m + k], prm.Z[i * m + k], s);
+    Mv[r] = s;
+  }
+  x.sync();
+  double F = prm.H[i * p + i];
+#pragma unroll
+  for (int k = 0; k < m; ++k) F = kf_fma(prm.Z[i * m + k], Mv[k], F);
+  *vo = v;
+  *Fo = F;
+  if (F == 0.0) return false;
+  const double rF = 1.0 / F;
+  KFB_FOR(r, m) Kv[r] = Mv[r] * rF;
+  x.sync();
+  KFB_FOR(idx, m * m) {
+    const int r = idx / m, c = idx - r * m;
+    P[idx] = kf_fma(-Kv[r] * Kv[c], F, P[idx]);  // P - K K^T F  (:477, not Joseph)
+  }
+  KFB_FOR(r, m) a[r] = kf_fma(Kv[r], v, a[r]);
+  x.sync();
+  return true;
+}
+
+template <class X>
+KFB_HD int count_missing(X& x, const double* yt) {
+  int nm = 0;
+#pragma unroll
+  for (int i = 0; i < x.p(); ++i) nm += kf_isnan(yt[i]) ? 1 : 0;
+  return nm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward recursion for one unit
+// ------------------------------------------------------------------------------------------------
+template <int MK, class X>
+KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
+  const int m = x.m(), p = x.p(), n = A.n;
+  const long long draw = u / A.n_series, series = u - draw * A.n_series;
+  const int kt = tape_width(m);
+  Params<X> prm(x);
+  typename X::template Buf<SZ_MM> C(x), P(x), Pf(x);
+  typename X::template Buf<SZ_M> c(x), a(x), af(x), Mv(x), Kv(x);
+  UpdTmp<X> tmp(x);
+
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* Cp = A.C.p + draw * A.C.bs;
+  const double* cp = A.c.p ? A.c.p + draw * A.c.bs : nullptr;
+  const double* dp = A.d.p ? A.d.p + draw * A.d.bs : nullptr;
+  load_or_zero(x, prm.T, Tp, m * m);
+  load_or_zero(x, prm.Z, Zp, p * m);
+  load_or_zero(x, prm.H, Hp, p * p);
+  load_or_zero(x, C, Cp, m * m);
+  load_or_zero(x, c, cp, m);
+  load_or_zero(x, prm.d, dp, p);
+  load_or_zero(x, a, A.a0.p + draw * A.a0.bs, m);
+  if (MK == MK_STEADY) {
+    load_or_zero(x, P, A.Pss.p + u * A.Pss.bs, m * m);  // recursion starts at P_steady (:391, Q7)
+    load_or_zero(x, prm.Gss, A.Gss.p + u * A.Gss.bs, p * p);
+  } else {
+    load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
+  }
+  x.sync();
+
+  const double* y = x.y_base(A, series);
+  const bool full = (A.ll_obs != nullptr);
+  const bool lane0 = (x.lane() == 0);
+  LogAcc acc;
+  double llsum = 0.0;
+  int info = 0;
+
+  if (A.ps) {
+    const double* a0p = A.a0.p + draw * A.a0.bs;
+    const double* P0p = A.P0.p + draw * A.P0.bs;
+    KFB_FOR(i, m) A.ps[(u * (n + 1)) * m + i] = a0p[i];
+    if (A.pc) KFB_FOR(i, m * m) A.pc[(u * (n + 1)) * m * m + i] = P0p[i];
+  }
+
+  for (int t = 0; t < n; ++t) {
+    if (X::TV) {
+      if (A.T.ts) load_or_zero(x, prm.T, Tp + t * A.T.ts, m * m);
+      if (A.Z.ts) load_or_zero(x, prm.Z, Zp + t * A.Z.ts, p * m);
+      if (A.H.ts) load_or_zero(x, prm.H, Hp + t * A.H.ts, p * p);
+      if (A.C.ts) load_or_zero(x, C, Cp + t * A.C.ts, m * m);
+      if (A.c.ts) load_or_zero(x, c, cp + t * A.c.ts, m);
+      if (A.d.ts) load_or_zero(x, prm.d, dp + t * A.d.ts, p);
+      x.sync();
+    }
+    const double* yt = y + (long long)t * p;
+    double ll_t = 0.0;
+    if (MK == MK_UNIV) {
+      KFB_FOR(i, m) af[i] = a[i];
+      KFB_FOR(i, m * m) Pf[i] = P[i];
+      x.sync();
+      double s = 0.0;
+      int cnt = 0;
+      for (int i = 0; i < p; ++i) {
+        double v, F;
+        if (univariate_inner(x, prm, yt, A.d_sign, i, af, Pf, Mv, Kv, &v, &F)) {
+          if (!(F > 0.0) && info == 0) info = t + 1;
+          double li = v * v / F;
+          if (full) {
+            li += log(F);
+            cnt += (li != 0.0) ? 1 : 0;  // (ll_inner != 0).sum(), :503
+          } else {
+            if (F > 0.0 && F < 1.0e300 && lane0) acc.mul(F);
+            cnt += 1;
+          }
+          s += li;
+        }
+      }
+      ll_t = -0.5 * (cnt * KF_LOG_2PI + s);
+    } else {
+      const int nm = count_missing(x, yt);
+      if (nm == 0) {
+        StepStat st = update_observed<MK>(x, prm, yt, A.d_sign, a, P, tmp, af, Pf, &acc, full);
+        if (!st.ok && info == 0) info = t + 1;
+        ll_t = -0.5 * (A.ll_const + st.logdet + st.quad);
+      } else {
+        if (nm != p && info == 0) info = -(t + 1);  // partial row: reference raises (A.2-Q2)
+        KFB_FOR(i, m) af[i] = a[i];                 // all missing: K = 0, a_f = a, P_f = P, ll = 0
+        KFB_FOR(i, m * m) Pf[i] = P[i];
+        x.sync();
+      }
+    }
+    llsum += ll_t;
+    if (full && lane0) A.ll_obs[u * n + t] = ll_t;
+    if (A.fs) KFB_FOR(i, m) A.fs[(u * n + t) * m + i] = af[i];
+    if (A.fc) KFB_FOR(i, m * m) A.fc[(u * n + t) * m * m + i] = Pf[i];
+    predict(x, prm.T, C, c, af, Pf, a, P, tmp.S1, tmp.S2);
+    if (A.ps) KFB_FOR(i, m) A.ps[(u * (n + 1) + t + 1) * m + i] = a[i];
+    if (A.pc) KFB_FOR(i, m * m) A.pc[(u * (n + 1) + t + 1) * m * m + i] = P[i];
+    if (A.tape && t + 1 < n) {
+      KFB_FOR(k, m) A.tape[x.tape_index(A, u, t + 1, k)] = a[k];
+      KFB_FOR(idx, m * m) {
+        const int i = idx / m, j = idx - i * m;
+        if (j >= i) A.tape[x.tape_index(A, u, t + 1, m + i * m - (i * (i - 1)) / 2 + (j - i))] = P[idx];
+      }
+    }
+  }
+  if (lane0) {
+    double ll = llsum;
+    if (!full) ll -= 0.5 * acc.value();
+    if (info != 0) ll = nan("");
+    if (A.loglik) A.loglik[u] = ll;
+    if (A.info) A.info[u] = info;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint recursion for one unit
+// ------------------------------------------------------------------------------------------------
+template <int MK, class X>
+KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
+  const int m = x.m(), p = x.p(), n = A.n;
+  const long long draw = u / A.n_series, series = u - draw * A.n_series;
+  const int kt = tape_width(m);
+  Params<X> prm(x);
+  typename X::template Buf<SZ_MM> P(x), Pf(x), Pb(x), Pfb(x), Tb(x), Cb(x), S3(x), S4(x);
+  typename X::template Buf<SZ_M> a(x), af(x), ab(x), afb(x), cb(x), Mv(x), Kv(x), Mvb(x);
+  typename X::template Buf<SZ_MP> Zb(x), Kb(x), Mb(x), PK(x);
+  typename X::template Buf<SZ_PP> Hb(x), Fb(x), Gb(x), Q1(x);
+  typename X::template Buf<SZ_P> db(x), vb(x);
+  UpdTmp<X> tmp(x);
+
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* dp = A.d.p ? A.d.p + draw * A.d.bs : nullptr;
+  load_or_zero(x, prm.T, Tp, m * m);
+  load_or_zero(x, prm.Z, Zp, p * m);
+  load_or_zero(x, prm.H, Hp, p * p);
+  load_or_zero(x, prm.d, dp, p);
+  if (MK == MK_STEADY) load_or_zero(x, prm.Gss, A.Gss.p + u * A.Gss.bs, p * p);
+  KFB_FOR(i, m) { ab[i] = 0.0; cb[i] = 0.0; }
+  KFB_FOR(i, m * m) { Pb[i] = 0.0; Tb[i] = 0.0; Cb[i] = 0.0; }
+  KFB_FOR(i, p * m) Zb[i] = 0.0;
+  KFB_FOR(i, p * p) { Hb[i] = 0.0; Gb[i] = 0.0; }
+  KFB_FOR(i, p) db[i] = 0.0;
+  x.sync();
+
+  const double* y = x.y_base(A, series);
+  const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
+
+  for (int t = n - 1; t >= 0; --t) {
+    if (X::TV) {
+      if (A.T.ts) load_or_zero(x, prm.T, Tp + t * A.T.ts, m * m);
+      if (A.Z.ts) load_or_zero(x, prm.Z, Zp + t * A.Z.ts, p * m);
+      if (A.H.ts) load_or_zero(x, prm.H, Hp + t * A.H.ts, p * p);
+      if (A.d.ts) load_or_zero(x, prm.d, dp + t * A.d.ts, p);
+      x.sync();
+    }
+    // predicted moments entering step t
+    if (t == 0) {
+      load_or_zero(x, a, A.a0.p + draw * A.a0.bs, m);
+      if (MK == MK_STEADY) load_or_zero(x, P, A.Pss.p + u * A.Pss.bs, m * m);
+      else load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
+    } else {
+      KFB_FOR(k, m) a[k] = A.tape[x.tape_index(A, u, t, k)];
+      KFB_FOR(idx, m * m) {
+        int i = idx / m, j = idx - i * m;
+        if (j < i) { const int s = i; i = j; j = s; }
+        const int k = m + i * m - (i * (i - 1)) / 2 + (j - i);
+        P[idx] = A.tape[x.tape_index(A, u, t, k)];
+      }
+    }
+    x.sync();
+    const double* yt = y + (long long)t * p;
+    const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);  // cotangent of ll_t
+
+    bool observed = false;
+    if (MK == MK_UNIV) {
+      KFB_FOR(i, m) af[i] = a[i];
+      KFB_FOR(i, m * m) Pf[i] = P[i];
+      x.sync();
+      for (int i = 0; i < p; ++i) {
+        double v, F;
+        univariate_inner(x, prm, yt, A.d_sign, i, af, Pf, Mv, Kv, &v, &F);
+      }
+    } else {
+      observed = (count_missing(x, yt) == 0);
+      if (observed) {
+        update_observed<MK>(x, prm, yt, A.d_sign, a, P, tmp, af, Pf, (LogAcc*)nullptr, false);
+      } else {
+        KFB_FOR(i, m) af[i] = a[i];
+        KFB_FOR(i, m * m) Pf[i] = P[i];
+        x.sync();
+      }
+    }
+
+    // ---- adjoint of predict: a' = T af + c ; P' = sym(T Pf T^T + C)
+    KFB_FOR(idx, m * m) {  // S3 = Ps = sym(Pb) ; S4 = Pf + Pf^T
+      const int i = idx / m, j = idx - i * m;
+      S3[idx] = 0.5 * (Pb[idx] + Pb[j * m + i]);
+      S4[idx] = Pf[idx] + Pf[j * m + i];
+    }
+    x.sync();
+    KFB_FOR(idx, m * m) Cb[idx] += S3[idx];
+    KFB_FOR(i, m) cb[i] += ab[i];
+    gemm<false, false, 0>(x, tmp.S1, prm.T, S4, m, m, m);    // T (Pf + Pf^T)
+    gemm<false, false, 1>(x, Tb, S3, tmp.S1, m, m, m);       // Tb += Ps T (Pf + Pf^T)
+    KFB_FOR(idx, m * m) {
+      const int i = idx / m, j = idx - i * m;
+      Tb[idx] = kf_fma(ab[i], af[j], Tb[idx]);               // + ab af^T
+    }
+    KFB_FOR(i, m) {                                          // afb = T^T ab
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < m; ++k) s = kf_fma(prm.T[k * m + i], ab[k], s);
+      afb[i] = s;
+    }
+    gemm<false, false, 0>(x, tmp.S1, S3, prm.T, m, m, m);    // Ps T
+    gemm<true, false, 0>(x, Pfb, prm.T, tmp.S1, m, m, m);    // Pfb = T^T Ps T
+    if (X::TV) {
+      if (A.T.ts && A.gT) { KFB_FOR(i, m * m) { A.gT[(u * n + t) * m * m + i] = Tb[i]; Tb[i] = 0.0; } }
+      if (A.C.ts && A.gC) { KFB_FOR(i, m * m) { A.gC[(u * n + t) * m * m + i] = Cb[i]; Cb[i] = 0.0; } }
+      if (A.c.ts && A.gc) { KFB_FOR(i, m) { A.gc[(u * n + t) * m + i] = cb[i]; cb[i] = 0.0; } }
+      x.sync();
+    }
+
+    if (MK == MK_UNIV) {
+      // reverse the p sequential scalar updates; intermediate (a,P) are recomputed from (a,P)
+      for (int i = p - 1; i >= 0; --i) {
+        KFB_FOR(k, m) af[k] = a[k];
+        KFB_FOR(k, m * m) Pf[k] = P[k];
+        x.sync();
+        double v = 0.0, F = 1.0;
+        for (int i2 = 0; i2 < i; ++i2) univariate_inner(x, prm, yt, A.d_sign, i2, af, Pf, Mv, Kv, &v, &F);
+        // (af, Pf) = state before inner update i.  Recompute its pieces without modifying them.
+        const double yi = yt[i];
+        if (kf_isnan(yi)) continue;
+        v = yi - A.d_sign * prm.d[i];
+#pragma unroll
+        for (int k = 0; k < m; ++k) v = kf_fma(-prm.Z[i * m + k], af[k], v);
+        KFB_FOR(r, m) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(Pf[r * m + k], prm.Z[i * m + k], s);
+          Mv[r] = s;
+        }
+        x.sync();
+        F = prm.H[i * p + i];
+#pragma unroll
+        for (int k = 0; k < m; ++k) F = kf_fma(prm.Z[i * m + k], Mv[k], F);
+        if (F == 0.0) continue;
+        const double rF = 1.0 / F;
+        KFB_FOR(r, m) Kv[r] = Mv[r] * rF;
+        x.sync();
+        const double lq = -0.5 * lb;  // cotangent of ll_inner_i
+        // Kb = afb v - (Pfb + Pfb^T) K F
+        KFB_FOR(r, m) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(Pfb[r * m + k] + Pfb[k * m + r], Kv[k], s);
+          Mvb[r] = kf_fma(afb[r], v, -s * F);  // holds Kb
+        }
+        x.sync();
+        double ktab = 0.0, kpk = 0.0, kbk = 0.0;
+#pragma unroll
+        for (int r = 0; r < m; ++r) {
+          ktab = kf_fma(Kv[r], afb[r], ktab);
+          kbk = kf_fma(Mvb[r], Kv[r], kbk);
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(Pfb[r * m + k], Kv[k], s);
+          kpk = kf_fma(Kv[r], s, kpk);
+        }
+        const double vbar = ktab + lq * 2.0 * v * rF;
+        const double Fbar = -kpk + lq * (rF - v * v * rF * rF) - kbk * rF;
+        x.sync();
+        KFB_FOR(r, m) Mvb[r] = kf_fma(prm.Z[i * m + r], Fbar, Mvb[r] * rF);  // Mvb = Kb / F + z Fbar
+        x.sync();
+        if (x.lane() == 0) {
+          Hb[i * p + i] += Fbar;
+          db[i] -= A.d_sign * vbar;
+        }
+        KFB_FOR(r, m) {  // Zb row i += Mv Fbar + Pf^T Mvb - vbar a
+          double s = kf_fma(Mv[r], Fbar, -vbar * af[r]);
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(Pf[k * m + r], Mvb[k], s);
+          Zb[i * m + r] += s;
+        }
+        KFB_FOR(idx, m * m) {
+          const int r = idx / m, c2 = idx - r * m;
+          Pfb[idx] = kf_fma(Mvb[r], prm.Z[i * m + c2], Pfb[idx]);
+        }
+        KFB_FOR(r, m) afb[r] = kf_fma(-prm.Z[i * m + r], vbar, afb[r]);
+        x.sync();
+      }
+      KFB_FOR(i, m) ab[i] = afb[i];
+      KFB_FOR(i, m * m) Pb[i] = Pfb[i];
+      x.sync();
+    } else if (!observed) {
+      KFB_FOR(i, m) ab[i] = afb[i];
+      KFB_FOR(i, m * m) Pb[i] = Pfb[i];
+      x.sync();
+    } else {
+      // ---- adjoint of the Joseph update
+      KFB_FOR(idx, m * m) {
+        const int i = idx / m, j = idx - i * m;
+        S4[idx] = P[idx] + P[j * m + i];
+      }
+      x.sync();
+      gemm<false, false, 0>(x, tmp.S1, tmp.A, S4, m, m, m);   // A (P + P^T)
+      gemm<false, false, 0>(x, S3, Pfb, tmp.S1, m, m, m);     // Ab = Pfb A (P + P^T)      (S3 = Ab)
+      gemm<false, false, 0>(x, tmp.S1, Pfb, tmp.A, m, m, m);  // Pfb A
+      gemm<true, false, 0>(x, Pb, tmp.A, tmp.S1, m, m, m);    // Pb = A^T Pfb A
+      KFB_FOR(idx, p * p) {
+        const int i = idx / p, j = idx - i * p;
+        Q1[idx] = prm.H[idx] + prm.H[j * p + i];
+      }
+      x.sync();
+      gemm<false, false, 0>(x, tmp.KH, tmp.K, Q1, m, p, p);   // K (H + H^T)
+      gemm<false, false, 0>(x, Kb, Pfb, tmp.KH, m, m, p);     // Kb = Pfb K (H + H^T)
+      KFB_FOR(idx, m * p) {
+        const int i = idx / p, j = idx - i * p;
+        double s = kf_fma(afb[i], tmp.v[j], Kb[idx]);         // + afb v^T
+#pragma unroll
+        for (int k = 0; k < m; ++k) s = kf_fma(-S3[i * m + k], prm.Z[j * m + k], s);  // - Ab Z^T
+        Kb[idx] = s;
+      }
+      gemm<false, false, 0>(x, PK, Pfb, tmp.K, m, m, p);      // Pfb K
+      gemm<true, false, 1>(x, Hb, tmp.K, PK, p, m, p);        // Hb += K^T Pfb K
+      gemm<true, false, 2>(x, Zb, tmp.K, S3, p, m, m);        // Zb -= K^T Ab
+      // vb, Fb
+      if (MK == MK_STEADY) {
+        KFB_FOR(i, p) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(tmp.K[k * p + i], afb[k], s);
+#pragma unroll
+          for (int j = 0; j < p; ++j) s = kf_fma(-0.5 * lb * (prm.Gss[i * p + j] + prm.Gss[j * p + i]), tmp.v[j], s);
+          vb[i] = s;
+        }
+        gemm<true, false, 1>(x, Gb, tmp.Mm, Kb, p, m, p);     // Gssb += Mm^T Kb
+        KFB_FOR(idx, p * p) {
+          const int i = idx / p, j = idx - i * p;
+          Gb[idx] = kf_fma(-0.5 * lb * tmp.v[i], tmp.v[j], Gb[idx]);
+          Fb[idx] = -0.5 * lb * tmp.Fi[j * p + i];
+        }
+        x.sync();
+        gemm<false, true, 0>(x, Mb, Kb, prm.Gss, m, p, p);    // Mb = Kb Gss^T
+      } else {
+        KFB_FOR(i, p) {
+          double s = -lb * tmp.w[i];
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(tmp.K[k * p + i], afb[k], s);
+          vb[i] = s;
+        }
+        gemm<true, false, 0>(x, Q1, tmp.K, Kb, p, m, p);      // K^T Kb
+        KFB_FOR(idx, p * p) {
+          const int i = idx / p, j = idx - i * p;
+          double s = -0.5 * lb * (tmp.Fi[j * p + i] - tmp.w[i] * tmp.w[j]);
+#pragma unroll
+          for (int k = 0; k < p; ++k) s = kf_fma(-Q1[i * p + k], tmp.Fi[j * p + k], s);  // - K^T Kb G^T
+          Fb[idx] = s;
+        }
+        x.sync();
+        gemm<false, true, 0>(x, Mb, Kb, tmp.Fi, m, p, p);     // Mb = Kb G^T
+      }
+      gemm<true, false, 1>(x, Mb, prm.Z, Fb, m, p, p);        // Mb += Z^T Fb
+      KFB_FOR(idx, p * m) {                                   // Zb += Fb Mm^T + Mb^T P - vb a^T
+        const int i = idx / m, j = idx - i * m;
+        double s = kf_fma(-vb[i], a[j], Zb[idx]);
+#pragma unroll
+        for (int k = 0; k < p; ++k) s = kf_fma(Fb[i * p + k], tmp.Mm[j * p + k], s);
+#pragma unroll
+        for (int k = 0; k < m; ++k) s = kf_fma(Mb[k * p + i], P[k * m + j], s);
+        Zb[idx] = s;
+      }
+      KFB_FOR(idx, p * p) Hb[idx] += Fb[idx];
+      gemm<false, false, 1>(x, Pb, Mb, prm.Z, m, p, m);       // Pb += Mb Z
+      KFB_FOR(i, m) {                                         // ab = afb - Z^T vb
+        double s = afb[i];
+#pragma unroll
+        for (int k = 0; k < p; ++k) s = kf_fma(-prm.Z[k * m + i], vb[k], s);
+        ab[i] = s;
+      }
+      KFB_FOR(i, p) db[i] = kf_fma(-A.d_sign, vb[i], db[i]);
+      x.sync();
+    }
+    if (X::TV) {
+      if (A.Z.ts && A.gZ) { KFB_FOR(i, p * m) { A.gZ[(u * n + t) * p * m + i] = Zb[i]; Zb[i] = 0.0; } }
+      if (A.H.ts && A.gH) { KFB_FOR(i, p * p) { A.gH[(u * n + t) * p * p + i] = Hb[i]; Hb[i] = 0.0; } }
+      if (A.d.ts && A.gd) { KFB_FOR(i, p) { A.gd[(u * n + t) * p + i] = db[i]; db[i] = 0.0; } }
+      x.sync();
+    }
+  }
+  if (A.ga0) KFB_FOR(i, m) A.ga0[u * m + i] = ab[i];
+  if (MK == MK_STEADY) {
+    if (A.gPss) KFB_FOR(i, m * m) A.gPss[u * m * m + i] = Pb[i];
+    if (A.gGss) KFB_FOR(i, p * p) A.gGss[u * p * p + i] = Gb[i];
+    if (A.gP0) KFB_FOR(i, m * m) A.gP0[u * m * m + i] = 0.0;  // Q7: P0 is not used by the recursion
+  } else {
+    if (A.gP0) KFB_FOR(i, m * m) A.gP0[u * m * m + i] = Pb[i];
+  }
+  if (A.gT && !(X::TV && A.T.ts)) KFB_FOR(i, m * m) A.gT[u * m * m + i] = Tb[i];
+  if (A.gC && !(X::TV && A.C.ts)) KFB_FOR(i, m * m) A.gC[u * m * m + i] = Cb[i];
+  if (A.gc && !(X::TV && A.c.ts)) KFB_FOR(i, m) A.gc[u * m + i] = cb[i];
+  if (A.gZ && !(X::TV && A.Z.ts)) KFB_FOR(i, p * m) A.gZ[u * p * m + i] = Zb[i];
+  if (A.gH && !(X::TV && A.H.ts)) KFB_FOR(i, p * p) A.gH[u * p * p + i] = Hb[i];
+  if (A.gd && !(X::TV && A.d.ts)) KFB_FOR(i, p) A.gd[u * p + i] = db[i];
+}
+
+}  // namespace kfb

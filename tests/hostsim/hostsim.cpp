@@ -1,0 +1,78 @@
+// hostsim.cpp - TEST-ONLY host build of the device step programs in
+// pymc_statespace_b200/csrc/kf_core.cuh.  The container that builds this repo has no GPU, so the
+// Kalman/adjoint math is debugged here against the oracle before it is run on a B200.  This file is
+// NOT part of the product: the package never loads it, and it cannot be reached from any public API.
+//
+//   g++ -O1 -shared -fPIC -I pymc_statespace_b200/csrc tests/hostsim/hostsim.cpp -o tests/hostsim/_hostsim.so
+#include <vector>
+
+#include "kf_ctx.cuh"
+
+using namespace kfb;
+
+template <int MK, class X>
+static void run_both(X& x, KfArgs& A, int do_bwd) {
+  forward_unit<MK>(x, A, 0);
+  if (do_bwd) backward_unit<MK>(x, A, 0);
+}
+
+template <class X>
+static void run_kind(X& x, KfArgs& A, int do_bwd) {
+  if (A.math_kind == MK_STD) run_both<MK_STD>(x, A, do_bwd);
+  else if (A.math_kind == MK_UNIV) run_both<MK_UNIV>(x, A, do_bwd);
+  else if (A.math_kind == MK_STEADY) run_both<MK_STEADY>(x, A, do_bwd);
+}
+
+extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const double* a0, const double* P0,
+                           const double* T, const double* Z, const double* H, const double* C, const double* c,
+                           const double* d, const double* Pss, const double* Gss, const long long* ts /*T,Z,H,C,c,d*/,
+                           double ll_const, double d_sign, int static_dims, double* loglik, double* ll_obs, double* fs,
+                           double* ps, double* fc, double* pc, int* info, int do_bwd, const double* g_loglik,
+                           const double* g_ll_obs, double* ga0, double* gP0, double* gT, double* gZ, double* gH,
+                           double* gC, double* gc, double* gd, double* gPss, double* gGss) {
+  KfArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.U = 1; A.n_series = 1; A.n = n; A.m = m; A.p = p; A.math_kind = mk;
+  A.y = {y, 0, 0}; A.a0 = {a0, 0, 0}; A.P0 = {P0, 0, 0};
+  A.T = {T, 0, ts[0]}; A.Z = {Z, 0, ts[1]}; A.H = {H, 0, ts[2]}; A.C = {C, 0, ts[3]};
+  A.c = {c, 0, ts[4]}; A.d = {d, 0, ts[5]};
+  A.Pss = {Pss, 0, 0}; A.Gss = {Gss, 0, 0};
+  A.ll_const = ll_const; A.d_sign = d_sign;
+  A.loglik = loglik; A.ll_obs = ll_obs; A.fs = fs; A.ps = ps; A.fc = fc; A.pc = pc; A.info = info;
+  std::vector<double> tape((size_t)(n > 1 ? n - 1 : 1) * tape_width(m));
+  A.tape = tape.data();
+  A.g_loglik = g_loglik; A.g_ll_obs = g_ll_obs;
+  A.ga0 = ga0; A.gP0 = gP0; A.gT = gT; A.gZ = gZ; A.gH = gH; A.gC = gC; A.gc = gc; A.gd = gd;
+  A.gPss = gPss; A.gGss = gGss;
+
+  if (static_dims) {
+#define KFB_CASE(MM, PP)                                   \
+  if (m == MM && p == PP) {                                \
+    ThreadCtx<MM, PP> x{nullptr};                          \
+    run_kind(x, A, do_bwd);                                \
+    return 0;                                              \
+  }
+    KFB_CASE(1, 1) KFB_CASE(2, 1) KFB_CASE(2, 2) KFB_CASE(3, 1) KFB_CASE(3, 2) KFB_CASE(3, 3)
+    KFB_CASE(4, 1) KFB_CASE(4, 2) KFB_CASE(4, 3)
+#undef KFB_CASE
+    return 2;
+  }
+  const int cap = coop_arena_doubles(m, p, true) + coop_arena_doubles(m, p, false);
+  std::vector<double> arena((size_t)cap);
+  CoopCtx x;
+  x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false;
+  x.off = 0;
+  if (A.math_kind == MK_STD) forward_unit<MK_STD>(x, A, 0);
+  else if (A.math_kind == MK_UNIV) forward_unit<MK_UNIV>(x, A, 0);
+  else forward_unit<MK_STEADY>(x, A, 0);
+  const int fwd_used = x.off;
+  if (fwd_used > coop_arena_doubles(m, p, false)) return 3;
+  if (do_bwd) {
+    x.off = 0;
+    if (A.math_kind == MK_STD) backward_unit<MK_STD>(x, A, 0);
+    else if (A.math_kind == MK_UNIV) backward_unit<MK_UNIV>(x, A, 0);
+    else backward_unit<MK_STEADY>(x, A, 0);
+    if (x.off > coop_arena_doubles(m, p, true)) return 4;
+  }
+  return x.overflow ? 5 : 0;
+}
