@@ -1,0 +1,265 @@
+// kf_api.cu - the extern "C" boundary declared in include/kfb200.h.
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/kfb200.h"
+#include "kf_aux.cuh"
+#include "kf_kernels.cuh"
+
+namespace kfb {
+
+static std::atomic<long long> g_launches{0};
+static thread_local const char* g_cuda_err = "";
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+thread_launch_fn thread_launcher_m1(int p, int mk);
+thread_launch_fn thread_launcher_m2(int p, int mk);
+thread_launch_fn thread_launcher_m3(int p, int mk);
+thread_launch_fn thread_launcher_m4(int p, int mk);
+
+thread_launch_fn find_thread_launcher(int m, int p, int mk) {
+  switch (m) {
+    case 1: return thread_launcher_m1(p, mk);
+    case 2: return thread_launcher_m2(p, mk);
+    case 3: return thread_launcher_m3(p, mk);
+    case 4: return thread_launcher_m4(p, mk);
+    default: return nullptr;
+  }
+}
+
+struct Plan {
+  int mk;
+  double ll_const, d_sign;
+  bool tv_any, use_thread;
+  long long U, nD;
+  int nTC;           // time entries of C = R Q R^T (1 or n)
+  long long C_bs;    // 0 if R and Q are shared by all draws
+  size_t off_C, off_Pss, off_Gss, off_tape, off_gC, off_gPss, off_gGss, total;
+};
+
+static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
+  if (!d || d->n_draws <= 0 || d->n_series <= 0 || d->n <= 0 || d->m <= 0 || d->p <= 0 || d->r <= 0)
+    return KFB_ERR_INVALID_ARG;
+  const bool corrected = (d->flags & KFB_FLAG_CORRECTED) != 0;
+  const double l2pi = KF_LOG_2PI;
+  switch (d->filter_kind) {
+    case KFB_STANDARD:
+      pl->mk = MK_STD; pl->ll_const = corrected ? d->p * l2pi : l2pi; pl->d_sign = 1.0; break;
+    case KFB_SINGLE:
+      if (d->p != 1) return KFB_ERR_INVALID_ARG;  // assert_data_is_1d, kalman_filter.py:19,329
+      pl->mk = MK_STD; pl->ll_const = l2pi; pl->d_sign = corrected ? 1.0 : -1.0; break;
+    case KFB_CHOLESKY:
+      if (d->p != 1 && !corrected) return KFB_ERR_UNSUPPORTED;  // strict Q4 variant for p > 1: not built yet
+      pl->mk = MK_STD; pl->ll_const = d->p * l2pi; pl->d_sign = 1.0; break;
+    case KFB_UNIVARIATE:
+      pl->mk = MK_UNIV; pl->ll_const = 0.0; pl->d_sign = 1.0; break;
+    case KFB_STEADY_STATE:
+      pl->mk = MK_STEADY; pl->ll_const = corrected ? d->p * l2pi : l2pi; pl->d_sign = corrected ? 1.0 : 0.0; break;
+    default: return KFB_ERR_INVALID_ARG;
+  }
+  pl->tv_any = d->T_ts || d->Z_ts || d->R_ts || d->H_ts || d->Q_ts || d->c_ts || d->d_ts;
+  if (pl->tv_any && (pl->mk == MK_UNIV || pl->mk == MK_STEADY)) return KFB_ERR_UNSUPPORTED;
+  if (pl->mk == MK_STEADY) return KFB_ERR_UNSUPPORTED;  // DARE kernel: not built yet
+  pl->U = d->n_draws * d->n_series;
+  pl->nD = d->n_draws;
+  pl->nTC = (d->R_ts || d->Q_ts) ? d->n : 1;
+  const bool C_batched = d->R_bs || d->Q_bs;
+  const long long nDC = C_batched ? d->n_draws : 1;
+  pl->C_bs = C_batched ? (long long)pl->nTC * d->m * d->m : 0;
+  pl->use_thread =
+      !pl->tv_any && !(d->flags & KFB_FLAG_FORCE_COOP) && find_thread_launcher(d->m, d->p, pl->mk) != nullptr;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off += ((doubles * 8 + 255) / 256) * 256; return o; };
+  pl->off_C = take((size_t)nDC * pl->nTC * d->m * d->m);
+  pl->off_Pss = pl->off_Gss = pl->off_gPss = pl->off_gGss = 0;
+  if (pl->mk == MK_STEADY) {
+    pl->off_Pss = take((size_t)pl->U * d->m * d->m);
+    pl->off_Gss = take((size_t)pl->U * d->p * d->p);
+  }
+  pl->off_tape = pl->off_gC = 0;
+  if (save) {
+    pl->off_tape = take((size_t)pl->U * (d->n > 1 ? d->n - 1 : 0) * tape_width(d->m));
+    pl->off_gC = take((size_t)pl->U * pl->nTC * d->m * d->m);
+    if (pl->mk == MK_STEADY) {
+      pl->off_gPss = take((size_t)pl->U * d->m * d->m);
+      pl->off_gGss = take((size_t)pl->U * d->p * d->p);
+    }
+  }
+  pl->total = off;
+  return KFB_OK;
+}
+
+static void fill_args(const kfb_desc* d, const kfb_inputs* in, const Plan& pl, char* ws, KfArgs* A) {
+  std::memset(A, 0, sizeof(*A));
+  A->U = pl.U; A->n_series = d->n_series; A->n = d->n; A->m = d->m; A->p = d->p; A->math_kind = pl.mk;
+  A->y = {in->y, d->y_bs, 0};
+  A->a0 = {in->a0, d->a0_bs, 0};
+  A->P0 = {in->P0, d->P0_bs, 0};
+  A->T = {in->T, d->T_bs, d->T_ts};
+  A->Z = {in->Z, d->Z_bs, d->Z_ts};
+  A->H = {in->H, d->H_bs, d->H_ts};
+  A->C = {(const double*)(ws + pl.off_C), pl.C_bs, pl.nTC > 1 ? (long long)d->m * d->m : 0};
+  A->c = {in->c, d->c_bs, d->c_ts};
+  A->d = {in->d, d->d_bs, d->d_ts};
+  if (pl.mk == MK_STEADY) {
+    A->Pss = {(const double*)(ws + pl.off_Pss), (long long)d->m * d->m, 0};
+    A->Gss = {(const double*)(ws + pl.off_Gss), (long long)d->p * d->p, 0};
+  }
+  A->ll_const = pl.ll_const;
+  A->d_sign = pl.d_sign;
+}
+
+static kfb_status cuda_fail(cudaError_t e) {
+  g_cuda_err = cudaGetErrorString(e);
+  return KFB_ERR_CUDA;
+}
+
+static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A, bool bwd, cudaStream_t s) {
+  cudaError_t e;
+  if (pl.use_thread) {
+    // shared observation stream -> stage it in shared memory once per CTA
+    int ysm = 0, bulk_ok = 0;
+    const long long ydoubles = (long long)d->n * d->p;
+    if (d->y_bs == 0 && d->n_series == 1 && ydoubles * 8 <= 96 * 1024) {
+      ysm = (int)ydoubles;
+      bulk_ok = ((uintptr_t)A.y.p % 16 == 0) ? 1 : 0;
+    }
+    e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
+  } else {
+    e = launch_coop(A, bwd, s);
+    if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+  }
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+}  // namespace kfb
+
+using namespace kfb;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int32_t kfb_version(void) { return KFB_VERSION; }
+
+const char* kfb_status_string(kfb_status s) {
+  switch (s) {
+    case KFB_OK: return "ok";
+    case KFB_ERR_INVALID_ARG: return "invalid argument";
+    case KFB_ERR_UNSUPPORTED: return "unsupported configuration";
+    case KFB_ERR_WORKSPACE: return "workspace missing or too small";
+    case KFB_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+const char* kfb_last_cuda_error(void) { return g_cuda_err; }
+
+int64_t kfb_launch_count(void) { return g_launches.load(); }
+
+kfb_status kfb_workspace_bytes(const kfb_desc* desc, int32_t save_for_backward, size_t* bytes) {
+  if (!bytes) return KFB_ERR_INVALID_ARG;
+  Plan pl;
+  kfb_status st = make_plan(desc, save_for_backward != 0, &pl);
+  if (st != KFB_OK) return st;
+  *bytes = pl.total;
+  return KFB_OK;
+}
+
+kfb_status kfb_forward(const kfb_desc* desc, const kfb_inputs* in, const kfb_outputs* out, void* workspace,
+                       size_t workspace_bytes, int32_t save_for_backward, void* stream) {
+  if (!in || !out || !in->y || !in->a0 || !in->P0 || !in->T || !in->Z || !in->R || !in->H || !in->Q)
+    return KFB_ERR_INVALID_ARG;
+  Plan pl;
+  kfb_status st = make_plan(desc, save_for_backward != 0, &pl);
+  if (st != KFB_OK) return st;
+  if (!workspace || workspace_bytes < pl.total) return KFB_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  KfArgs A;
+  fill_args(desc, in, pl, ws, &A);
+  A.loglik = out->loglik; A.ll_obs = out->ll_obs; A.fs = out->filtered_states; A.ps = out->predicted_states;
+  A.fc = out->filtered_covs; A.pc = out->predicted_covs; A.info = out->info;
+  A.tape = save_for_backward ? (double*)(ws + pl.off_tape) : nullptr;
+  const long long nDC = pl.C_bs ? desc->n_draws : 1;
+  cudaError_t e = launch_rqr_forward(nDC, pl.nTC, desc->m, desc->r, MatArg{in->R, desc->R_bs, desc->R_ts},
+                                     MatArg{in->Q, desc->Q_bs, desc->Q_ts}, (double*)(ws + pl.off_C), s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return launch_main(desc, pl, A, false, s);
+}
+
+kfb_status kfb_backward(const kfb_desc* desc, const kfb_inputs* in, const kfb_cotangents* cot, const kfb_grads* g,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!in || !g || !in->y || !in->a0 || !in->P0 || !in->T || !in->Z || !in->R || !in->H || !in->Q)
+    return KFB_ERR_INVALID_ARG;
+  Plan pl;
+  kfb_status st = make_plan(desc, true, &pl);
+  if (st != KFB_OK) return st;
+  if (!workspace || workspace_bytes < pl.total) return KFB_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  KfArgs A;
+  fill_args(desc, in, pl, ws, &A);
+  A.tape = (double*)(ws + pl.off_tape);
+  A.g_loglik = cot ? cot->g_loglik : nullptr;
+  A.g_ll_obs = cot ? cot->g_ll_obs : nullptr;
+  A.ga0 = g->a0; A.gP0 = g->P0; A.gT = g->T; A.gZ = g->Z; A.gH = g->H; A.gc = g->c; A.gd = g->d;
+  const bool want_C = g->R || g->Q;
+  A.gC = want_C ? (double*)(ws + pl.off_gC) : nullptr;
+  st = launch_main(desc, pl, A, true, s);
+  if (st != KFB_OK) return st;
+  if (want_C) {
+    cudaError_t e = launch_rqr_backward(pl.U, desc->n_series, pl.nTC, desc->R_ts ? desc->n : 1, desc->Q_ts ? desc->n : 1,
+                                        desc->m, desc->r, MatArg{in->R, desc->R_bs, desc->R_ts},
+                                        MatArg{in->Q, desc->Q_bs, desc->Q_ts}, A.gC, g->R, g->Q, 0, s);
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
+  return KFB_OK;
+}
+
+kfb_status kfb_lyapunov_forward(int64_t B, int32_t m, int32_t r, const double* A, int64_t A_bs, const double* R,
+                                int64_t R_bs, const double* Q, int64_t Q_bs, double* X, int32_t* info, void* stream) {
+  if (B <= 0 || m <= 0 || r <= 0 || !A || !R || !Q || !X) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_lyapunov_forward(B, m, r, MatArg{A, A_bs, 0}, MatArg{R, R_bs, 0}, MatArg{Q, Q_bs, 0}, X, info,
+                                          (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_lyapunov_backward(int64_t B, int32_t m, int32_t r, const double* A, int64_t A_bs, const double* R,
+                                 int64_t R_bs, const double* Q, int64_t Q_bs, const double* X, const double* Xbar,
+                                 double* Abar, double* Rbar, double* Qbar, void* stream) {
+  if (B <= 0 || m <= 0 || r <= 0 || !A || !R || !Q || !X || !Xbar) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_lyapunov_backward(B, m, r, MatArg{A, A_bs, 0}, MatArg{R, R_bs, 0}, MatArg{Q, Q_bs, 0}, X, Xbar,
+                                           Abar, Rbar, Qbar, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_scatter_forward(int64_t B, int32_t n_theta, int32_t block, int32_t n_map, const double* theta,
+                               const double* base, const int32_t* src_idx, const int32_t* dst_idx, double* dst,
+                               void* stream) {
+  if (B <= 0 || n_theta <= 0 || block <= 0 || n_map < 0 || !theta || !base || !dst) return KFB_ERR_INVALID_ARG;
+  if (n_map > 0 && (!src_idx || !dst_idx)) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_scatter_forward(B, n_theta, block, n_map, theta, base, src_idx, dst_idx, dst,
+                                         (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32_t n_map, const double* gdst,
+                                const int32_t* src_idx, const int32_t* dst_idx, double* gtheta, void* stream) {
+  if (B <= 0 || n_theta <= 0 || block <= 0 || n_map < 0 || !gdst || !gtheta) return KFB_ERR_INVALID_ARG;
+  if (n_map > 0 && (!src_idx || !dst_idx)) return KFB_ERR_INVALID_ARG;
+  cudaError_t e =
+      launch_scatter_backward(B, n_theta, block, n_map, gdst, src_idx, dst_idx, gtheta, (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_fp64_peak(int32_t iters, int32_t blocks, int32_t threads, double* sink, double* h_flops, void* stream) {
+  if (iters <= 0 || blocks <= 0 || threads <= 0 || threads > 1024 || !sink) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_fp64_peak(iters, blocks, threads, sink, (cudaStream_t)stream);
+  if (h_flops) *h_flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,49 @@
+// kf_coop.cu - cooperative (shared-memory) kernels: any (k_states, k_endog), time-varying matrices.
+#include "kf_kernels.cuh"
+
+namespace kfb {
+
+template <int MK, bool WARP>
+static cudaError_t launch_coop_kind(const KfArgs& A, bool bwd, int arena, int block, unsigned grid, size_t smem,
+                                    cudaStream_t s) {
+  if (bwd) {
+    cudaFuncSetAttribute(kf_coop_kernel<MK, true, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kf_coop_kernel<MK, true, WARP><<<grid, block, smem, s>>>(A, arena);
+  } else {
+    cudaFuncSetAttribute(kf_coop_kernel<MK, false, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kf_coop_kernel<MK, false, WARP><<<grid, block, smem, s>>>(A, arena);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <bool WARP>
+static cudaError_t launch_coop_mode(const KfArgs& A, bool bwd, int arena, int block, unsigned grid, size_t smem,
+                                    cudaStream_t s) {
+  switch (A.math_kind) {
+    case MK_STD: return launch_coop_kind<MK_STD, WARP>(A, bwd, arena, block, grid, smem, s);
+    case MK_UNIV: return launch_coop_kind<MK_UNIV, WARP>(A, bwd, arena, block, grid, smem, s);
+    case MK_STEADY: return launch_coop_kind<MK_STEADY, WARP>(A, bwd, arena, block, grid, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Warp-per-unit while >= 4 arenas fit in one SM's shared memory; otherwise one CTA (256 threads) per unit.
+cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s) {
+  int arena = coop_arena_doubles(A.m, A.p, bwd);
+  arena = (arena + 1) & ~1;  // keep every arena 16-byte aligned
+  const size_t arena_bytes = (size_t)arena * sizeof(double);
+  const size_t smem_max = 227 * 1024;
+  if (arena_bytes > smem_max) return cudaErrorInvalidConfiguration;
+  if (arena_bytes * 4 <= smem_max) {
+    int warps = 4;
+    // more warps per CTA only helps when the arena is tiny; keep CTAs small so many are resident
+    const int block = warps * 32;
+    const unsigned grid = (unsigned)((A.U + warps - 1) / warps);
+    return launch_coop_mode<true>(A, bwd, arena, block, grid, arena_bytes * warps, s);
+  }
+  const int block = 256;
+  return launch_coop_mode<false>(A, bwd, arena, block, (unsigned)A.U, arena_bytes, s);
+}
+
+}  // namespace kfb

@@ -1,0 +1,98 @@
+// kf_kernels.cuh - __global__ wrappers around forward_unit / backward_unit (kf_core.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kf_ctx.cuh"
+
+namespace kfb {
+
+constexpr int KFB_THREAD_BLOCK = 64;  // thread-per-unit CTA size: 65,536 units -> 1024 CTAs = 6.9 per SM on 148 SMs
+
+// Stage `count` doubles of the (shared) observation stream into shared memory with one TMA bulk copy
+// (cp.async.bulk -> SASS UBLKCP) completed on an mbarrier; every thread then reads y_t as a shared-memory
+// broadcast.  Requires 16-byte aligned src; the odd tail double (if any) is copied by thread 0.
+__device__ __forceinline__ void stage_y(double* ysm, const double* ysrc, int count, bool bulk_ok) {
+  __shared__ __align__(8) unsigned long long bar;
+  const int bulk_doubles = bulk_ok ? (count & ~1) : 0;
+  if (bulk_doubles > 0) {
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(ysm);
+    const unsigned bytes = (unsigned)bulk_doubles * 8u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+          "l"(ysrc), "r"(bytes), "r"(bar_s)
+          : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar_s)
+          : "memory");
+    }
+  }
+  for (int i = bulk_doubles + threadIdx.x; i < count; i += blockDim.x) ysm[i] = ysrc[i];
+  __syncthreads();
+}
+
+template <int M, int P, int MK, bool BWD>
+__global__ void __launch_bounds__(KFB_THREAD_BLOCK)
+    kf_thread_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  const double* ysm = nullptr;
+  if (y_smem_doubles > 0) {
+    stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
+    ysm = kf_dyn_smem;
+  }
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= A.U) return;
+  ThreadCtx<M, P> x{ysm};
+  if (BWD) backward_unit<MK>(x, A, u);
+  else forward_unit<MK>(x, A, u);
+}
+
+template <int MK, bool BWD, bool WARP>
+__global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  CoopCtx x;
+  x.m_ = A.m;
+  x.p_ = A.p;
+  x.off = 0;
+  x.cap = arena_doubles;
+  x.overflow = false;
+  long long u;
+  if (WARP) {
+    const int warp = threadIdx.x >> 5;
+    x.lane_ = threadIdx.x & 31;
+    x.G_ = 32;
+    x.arena = kf_dyn_smem + (size_t)warp * arena_doubles;
+    u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (u >= A.U) return;
+  } else {
+    x.lane_ = threadIdx.x;
+    x.G_ = blockDim.x;
+    x.arena = kf_dyn_smem;
+    u = blockIdx.x;
+  }
+  if (BWD) backward_unit<MK>(x, A, u);
+  else forward_unit<MK>(x, A, u);
+  if (x.overflow) __trap();
+}
+
+// launchers implemented in kf_thread_m*.cu / kf_coop.cu
+typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);
+thread_launch_fn find_thread_launcher(int m, int p, int mk);
+cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s);
+void count_launch();
+
+}  // namespace kfb

@@ -1,0 +1,209 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Tolerance: rtol 1e-8 in float64 (BASELINE.json north_star) on logp, per-step ll, filtered / predicted
+moments and every gradient.  Sizes are small enough for the per-step Python oracle to finish in seconds.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kalman_numpy as kn
+from oracle import kalman_torch as kt
+from tests.helpers import make_test_inputs, nile_inputs, random_system, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+ALL_OUT = ("filtered_states", "predicted_states", "filtered_covs", "predicted_covs", "loglik", "ll_obs")
+
+
+def _dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device="cuda")
+
+
+def run_single(kind, args, c=None, d=None, strict=True, force_coop=False, time_varying=(), bwd=True, g_ll_obs=None):
+    """One unit through BatchedKalman; returns (outs, grads) as numpy in reference shapes."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    y, a0, P0, T, Z, R, H, Q = args
+    n, p = y.shape[0], y.shape[1]
+    m, r = T.shape[-1], R.shape[-1]
+    bk = BatchedKalman(kind, n, m, p, r, n_draws=1, strict_reference=strict, force_coop=force_coop,
+                       time_varying=time_varying)
+
+    def prep(name, x):
+        if x is None:
+            return None
+        x = np.asarray(x, dtype=float)
+        return _dev(x[None]) if name not in () else _dev(x)
+
+    ins = {k: prep(k, v) for k, v in zip(("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d"), (a0, P0, T, Z, R, H, Q, c, d))}
+    out = bk.forward(_dev(y[..., 0]), **ins, outputs=ALL_OUT, save_for_backward=bwd)
+    torch.cuda.synchronize()
+    res = [out["filtered_states"][0].cpu().numpy()[..., None], out["predicted_states"][0].cpu().numpy()[..., None],
+           out["filtered_covs"][0].cpu().numpy(), out["predicted_covs"][0].cpu().numpy(),
+           float(out["loglik"][0]), out["ll_obs"][0].cpu().numpy()]
+    info = int(out["info"][0])
+    grads = None
+    if bwd:
+        gl = None if g_ll_obs is None else _dev(np.zeros(1))
+        glo = None if g_ll_obs is None else _dev(np.asarray(g_ll_obs)[None])
+        g = bk.backward(g_loglik=gl, g_ll_obs=glo)
+        torch.cuda.synchronize()
+        grads = {k: v[0].cpu().numpy() for k, v in g.items()}
+        for k in ("a0", "c", "d"):
+            grads[k] = grads[k][..., None]
+    return res, grads, info
+
+
+def check_against_oracle(kind, args, c=None, d=None, strict=True, force_coop=False, time_varying=(), g_ll_obs=None,
+                         rtol=RTOL):
+    ref = kn.kalman_filter(kind, *args, c=c, d=d, strict_reference=strict)
+    res, grads, info = run_single(kind, args, c, d, strict, force_coop, time_varying, True, g_ll_obs)
+    assert info == 0
+    for name, a, b in zip(ALL_OUT, res, ref):
+        assert rel_err(a, b) < rtol, (kind, name, rel_err(a, b))
+    _, gref = kt.loglik_and_grads(kind, *args, c=c, d=d, strict_reference=strict, g_ll_obs=g_ll_obs)
+    for k in gref:
+        scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+        assert np.abs(grads[k] - gref[k]).max() / scale < rtol, (kind, k, np.abs(grads[k] - gref[k]).max() / scale)
+
+
+KINDS_P1 = ["standard", "cholesky", "single", "univariate"]
+
+
+@pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
+@pytest.mark.parametrize("kind", KINDS_P1)
+@pytest.mark.parametrize("n_missing", [0, 5])
+def test_nile_local_linear_trend(kind, n_missing, force_coop):
+    # the fixture of reference tests/test_kalman_filter.py:226-241 (m=2, p=1, P0 = 1e6 I)
+    check_against_oracle(kind, nile_inputs(n_missing), force_coop=force_coop)
+
+
+@pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (2, 2, 1), (3, 2, 2), (3, 3, 3), (4, 1, 2), (4, 3, 2)],
+                         ids=lambda d: "m%dp%dr%d" % d)
+def test_random_systems_with_intercepts(kind, dims, force_coop):
+    m, p, r = dims
+    rng = np.random.default_rng(100 * m + 10 * p + r)
+    args = random_system(rng, m, p, r, 40, n_missing=4)
+    c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+    check_against_oracle(kind, args, c, d, strict=True, force_coop=force_coop)
+    check_against_oracle(kind, args, c, d, strict=False, force_coop=force_coop,
+                         g_ll_obs=rng.normal(size=40))
+
+
+@pytest.mark.parametrize("dims", [(6, 3, 3), (5, 5, 1), (9, 2, 4)], ids=lambda d: "m%dp%dr%d" % d)
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+def test_larger_systems_coop(kind, dims):
+    m, p, r = dims
+    rng = np.random.default_rng(7 + m)
+    args = random_system(rng, m, p, r, 30, n_missing=3, scale_T=0.25)
+    check_against_oracle(kind, args)
+
+
+def test_cta_per_unit_mode():
+    # arena too large for 4 warps per SM -> one CTA per unit
+    m, p, r = 30, 1, 3
+    rng = np.random.default_rng(3)
+    args = random_system(rng, m, p, r, 12, n_missing=1, scale_T=0.1)
+    check_against_oracle("standard", args)
+    check_against_oracle("univariate", args)
+
+
+def test_univariate_partial_missing():
+    rng = np.random.default_rng(11)
+    args = random_system(rng, 4, 3, 2, 40, n_missing=3, partial=True, diag_H=True)
+    check_against_oracle("univariate", args, force_coop=False)
+    check_against_oracle("univariate", args, force_coop=True)
+
+
+def test_partial_missing_flags_info_in_standard():
+    rng = np.random.default_rng(12)
+    args = list(random_system(rng, 3, 2, 2, 20))
+    args[0][7, 1] = np.nan
+    res, _, info = run_single("standard", args, bwd=False)
+    assert info == -(7 + 1) and np.isnan(res[4])
+
+
+def test_time_varying_matrices():
+    # reference tests/test_kalman_filter.py:102-156 (shapes only there; values here)
+    rng = np.random.default_rng(5)
+    n, m, p, r = 12, 3, 2, 2
+    sys_t = [random_system(rng, m, p, r, n) for _ in range(n)]
+    y, a0, P0 = sys_t[0][:3]
+    T, Z, R, H, Q = (np.stack([s[i] for s in sys_t]) for i in range(3, 8))
+    c, d = rng.normal(size=(n, m, 1)), rng.normal(size=(n, p, 1))
+    check_against_oracle("standard", (y, a0, P0, T, Z, R, H, Q), c, d, time_varying=("T", "Z", "R", "H", "Q", "c", "d"))
+    # only some matrices time varying
+    check_against_oracle("standard", (y, a0, P0, T, sys_t[0][4], sys_t[0][5], H, sys_t[0][7]),
+                         time_varying=("T", "H"))
+
+
+@pytest.mark.parametrize("p,m,r,n", [(1, 1, 1, 10), (1, 2, 2, 10), (1, 5, 2, 10), (1, 5, 1, 10), (5, 5, 1, 10)])
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+def test_reference_shape_fixtures(kind, p, m, r, n):
+    # make_test_inputs of reference tests/utilities/test_helpers.py:62-76 incl. missing data (:192-209)
+    for missing in (None, 1):
+        args = make_test_inputs(p, m, r, n, missing_data=missing)
+        ref = kn.kalman_filter(kind, *args)
+        res, _, info = run_single(kind, args, bwd=False)
+        assert info == 0
+        for name, a, b in zip(ALL_OUT, res, ref):
+            assert np.asarray(a).shape == np.asarray(b).shape
+            assert not np.any(np.isnan(a))
+            assert rel_err(a, b) < RTOL, (name, rel_err(a, b))
+
+
+def test_batched_draws_and_series_match_unit_runs():
+    from pymc_statespace_b200 import BatchedKalman
+
+    rng = np.random.default_rng(21)
+    B, S, n, m, p, r = 37, 3, 50, 2, 1, 1
+    systems = [random_system(rng, m, p, r, n) for _ in range(B)]
+    ys = np.stack([random_system(rng, m, p, r, n, n_missing=3)[0][..., 0] for _ in range(S)])
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    bk = BatchedKalman("standard", n, m, p, r, n_draws=B, n_series=S)
+    out = bk.forward(_dev(ys), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                     outputs=("loglik",), save_for_backward=True)
+    g = bk.backward()
+    ll = out["loglik"].cpu().numpy().reshape(B, S)
+    gT = g["T"].cpu().numpy().reshape(B, S, m, m)
+    for b in (0, 17, 36):
+        for s in range(S):
+            args = (ys[s][..., None],) + tuple(systems[b][1:])
+            ref = kn.kalman_filter("standard", *args)[4]
+            assert abs(ll[b, s] - ref) < RTOL * abs(ref)
+            _, gref = kt.loglik_and_grads("standard", *args)
+            assert rel_err(gT[b, s], gref["T"]) < RTOL
+
+
+def test_lyapunov_forward_backward():
+    import scipy.linalg
+
+    from pymc_statespace_b200 import lyapunov_backward, lyapunov_forward
+
+    rng = np.random.default_rng(4)
+    B, m, r = 33, 5, 2
+    A = rng.normal(size=(B, m, m))
+    A *= (rng.uniform(0.2, 0.97, size=B) / np.abs(np.linalg.eigvals(A)).max(axis=1))[:, None, None]
+    R = rng.normal(size=(B, m, r))
+    L = rng.normal(size=(B, r, r))
+    Q = L @ L.transpose(0, 2, 1) + 0.1 * np.eye(r)
+    X, info = lyapunov_forward(_dev(A), _dev(R), _dev(Q))
+    assert int(info.abs().sum()) == 0
+    Xn = X.cpu().numpy()
+    for b in range(B):
+        ref = scipy.linalg.solve_discrete_lyapunov(A[b], R[b] @ Q[b] @ R[b].T, method="bilinear")
+        assert rel_err(Xn[b], ref) < RTOL
+    Xbar = rng.normal(size=(B, m, m))
+    Ab, Rb, Qb = (torch.zeros_like(_dev(x)) for x in (A, R, Q))
+    lyapunov_backward(_dev(A), _dev(R), _dev(Q), X, _dev(Xbar), Ab, Rb, Qb)
+    for b in (0, 5, 32):
+        At, Rt, Qt = (torch.tensor(x[b], requires_grad=True) for x in (A, R, Q))
+        Xt = kt.solve_discrete_lyapunov(At, Rt @ Qt @ Rt.T)
+        (Xt * torch.tensor(Xbar[b])).sum().backward()
+        assert rel_err(Ab[b].cpu().numpy(), At.grad.numpy()) < 1e-7
+        assert rel_err(Rb[b].cpu().numpy(), Rt.grad.numpy()) < 1e-7
+        assert rel_err(Qb[b].cpu().numpy(), Qt.grad.numpy()) < 1e-7
