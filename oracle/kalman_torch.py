@@ -235,4 +235,4 @@ def loglik_and_grads(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict_r
     target = out[4] if g_ll_obs is None else (out[5] * torch.as_tensor(g_ll_obs, dtype=DT)).sum()
     grads = torch.autograd.grad(target, list(ins.values()), allow_unused=True)
     gd = {k: (np.zeros_like(ins[k].detach().numpy()) if g is None else g.numpy()) for k, g in zip(GRAD_NAMES, grads)}
-    return float(out[4]), gd
+    return float(out[4].detach()), gd

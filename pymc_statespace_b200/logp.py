@@ -1,0 +1,140 @@
+"""theta-level batched log-likelihood and gradient: what NUTS asks for at every leapfrog step.
+
+Pipeline for a batch ``theta[B, n_theta]`` (all on the GPU, stream-ordered, no host round trip):
+
+    scatter theta -> (a0,P0,T,Z,R,H,Q,c,d)[B]        kfb_scatter_forward   (models/*.py update())
+    [P0 = Lyapunov(T, R Q R^T)]                       kfb_lyapunov_forward  (SARIMAX.py:100-107)
+    Kalman forward (tape of predicted moments)        kfb_forward           (kalman_filter.py:152-159)
+    adjoint recursion -> matrix cotangents            kfb_backward          (PyTensor Scan.L_op)
+    [Lyapunov adjoint]                                kfb_lyapunov_backward
+    scatter^T -> dlogp/dtheta[B, n_theta]             kfb_scatter_backward
+
+This is the batched equivalent of PyMC's ``logp_dlogp_function`` for the ``pm.Potential("log_likelihood")``
+term registered at reference ``pymc_statespace/core/statespace.py:174``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from ._lib import check, load
+from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapunov_forward
+from .models import MATRICES, StateSpaceSpec
+
+
+class KalmanLogp:
+    def __init__(self, spec: StateSpaceSpec, data, n_draws: int, filter_type: str = "standard",
+                 strict_reference: bool = True, device="cuda", force_coop: bool = False):
+        self.spec = spec
+        self.device = torch.device(device)
+        self.lib = load()
+        y = np.asarray(data, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        if y.ndim == 3 and y.shape[-1] == 1:
+            y = y[..., 0]  # reference data layout [n, p, 1] (core/representation.py:13-24)
+        self.n, p = y.shape
+        if p != spec.k_endog:
+            raise ValueError("data has %d columns, model expects %d" % (p, spec.k_endog))
+        if filter_type == "single" and p > 1:
+            # reference core/statespace.py:71-72
+            raise ValueError('Cannot use filter_type = "single" with multiple observed time series')
+        self.B = int(n_draws)
+        self.y = torch.as_tensor(y, dtype=torch.float64, device=self.device).contiguous()
+        self.kalman = BatchedKalman(filter_type, self.n, spec.k_states, spec.k_endog, spec.k_posdef, n_draws=self.B,
+                                    strict_reference=strict_reference, device=device, force_coop=force_coop)
+        m, pp, r = spec.k_states, spec.k_endog, spec.k_posdef
+        self._shape = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (pp, m), "R": (m, r), "H": (pp, pp), "Q": (r, r),
+                       "c": (m,), "d": (pp,)}
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._base = {k: torch.as_tensor(np.asarray(spec.base[k], dtype=np.float64).reshape(self._shape[k]), **f64)
+                      for k in MATRICES}
+        self._maps = {}
+        self._buf: Dict[str, torch.Tensor] = {}
+        for k in MATRICES:
+            mp = spec.maps.get(k, [])
+            if mp:
+                src = torch.as_tensor([a for a, _ in mp], dtype=torch.int32, device=self.device)
+                dst = torch.as_tensor([b for _, b in mp], dtype=torch.int32, device=self.device)
+                self._maps[k] = (src, dst, len(mp))
+                self._buf[k] = torch.empty((self.B,) + self._shape[k], **f64)
+        if spec.stationary_initialization:
+            self._buf["P0"] = torch.empty((self.B, m, m), **f64)
+        self._lyap_batched = None
+
+    # ------------------------------------------------------------------
+    def _size(self, k):
+        s = 1
+        for d in self._shape[k]:
+            s *= d
+        return s
+
+    def _scatter(self, theta):
+        sp = self.spec
+        mats = {}
+        with torch.cuda.device(self.device):
+            for k in MATRICES:
+                if k in self._maps:
+                    src, dst, nmap = self._maps[k]
+                    check(self.lib.kfb_scatter_forward(self.B, sp.n_theta, self._size(k), nmap, _ptr(theta),
+                                                       _ptr(self._base[k]), _ptr(src), _ptr(dst), _ptr(self._buf[k]),
+                                                       _stream_ptr(self.device)), "kfb_scatter_forward")
+                    mats[k] = self._buf[k]
+                else:
+                    mats[k] = self._base[k]
+        if sp.stationary_initialization:
+            A = mats["T"] if mats["T"].ndim == 3 else mats["T"].expand(self.B, -1, -1).contiguous()
+            X, info = lyapunov_forward(A, mats["R"], mats["Q"])
+            self._lyap = (A, X, info)
+            mats["P0"] = X
+        return mats
+
+    def _check_theta(self, theta):
+        if not (isinstance(theta, torch.Tensor) and theta.is_cuda and theta.dtype == torch.float64):
+            raise TypeError("theta: expected a float64 CUDA tensor")
+        if tuple(theta.shape) != (self.B, self.spec.n_theta):
+            raise ValueError(f"theta: expected shape {(self.B, self.spec.n_theta)}, got {tuple(theta.shape)}")
+        return theta.contiguous()
+
+    def system_matrices(self, theta) -> Dict[str, torch.Tensor]:
+        return dict(self._scatter(self._check_theta(theta)))
+
+    def filter(self, theta, outputs=("filtered_states", "predicted_states", "filtered_covs", "predicted_covs", "loglik",
+                                     "ll_obs")):
+        """Forward pass with the reference's six outputs (batched over draws)."""
+        mats = self._scatter(self._check_theta(theta))
+        return self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=outputs)
+
+    def logp(self, theta) -> torch.Tensor:
+        mats = self._scatter(self._check_theta(theta))
+        out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",))
+        self.info = out["info"]
+        return out["loglik"]
+
+    def logp_and_grad(self, theta, g_loglik: Optional[torch.Tensor] = None):
+        """Returns (logp[B], dlogp/dtheta[B, n_theta]); ``self.info[B]`` holds per-draw status."""
+        theta = self._check_theta(theta)
+        sp = self.spec
+        mats = self._scatter(theta)
+        out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",), save_for_backward=True)
+        self.info = out["info"]
+        wrt = [k for k in MATRICES if k in self._maps]
+        if sp.stationary_initialization and "P0" not in wrt:
+            wrt.append("P0")
+        g = self.kalman.backward(g_loglik=g_loglik, wrt=wrt)
+        if sp.stationary_initialization:
+            # P0 = Lyapunov(T, R Q R^T): push P0-bar back into T-bar, R-bar, Q-bar (only those theta reaches)
+            A, X, _ = self._lyap
+            lyapunov_backward(A, mats["R"], mats["Q"], X, g["P0"], g.get("T"), g.get("R"), g.get("Q"))
+        gtheta = torch.zeros((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            for k, (src, dst, nmap) in self._maps.items():
+                if sp.stationary_initialization and k == "P0":
+                    continue
+                check(self.lib.kfb_scatter_backward(self.B, sp.n_theta, self._size(k), nmap, _ptr(g[k]), _ptr(src),
+                                                    _ptr(dst), _ptr(gtheta), _stream_ptr(self.device)),
+                      "kfb_scatter_backward")
+        return out["loglik"], gtheta

@@ -57,7 +57,7 @@ def run_single(kind, args, c=None, d=None, strict=True, force_coop=False, time_v
 
 
 def check_against_oracle(kind, args, c=None, d=None, strict=True, force_coop=False, time_varying=(), g_ll_obs=None,
-                         rtol=RTOL):
+                         rtol=RTOL, grad_rtol=RTOL):
     ref = kn.kalman_filter(kind, *args, c=c, d=d, strict_reference=strict)
     res, grads, info = run_single(kind, args, c, d, strict, force_coop, time_varying, True, g_ll_obs)
     assert info == 0
@@ -66,7 +66,7 @@ def check_against_oracle(kind, args, c=None, d=None, strict=True, force_coop=Fal
     _, gref = kt.loglik_and_grads(kind, *args, c=c, d=d, strict_reference=strict, g_ll_obs=g_ll_obs)
     for k in gref:
         scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
-        assert np.abs(grads[k] - gref[k]).max() / scale < rtol, (kind, k, np.abs(grads[k] - gref[k]).max() / scale)
+        assert np.abs(grads[k] - gref[k]).max() / scale < grad_rtol, (kind, k, np.abs(grads[k] - gref[k]).max() / scale)
 
 
 KINDS_P1 = ["standard", "cholesky", "single", "univariate"]
@@ -77,7 +77,11 @@ KINDS_P1 = ["standard", "cholesky", "single", "univariate"]
 @pytest.mark.parametrize("n_missing", [0, 5])
 def test_nile_local_linear_trend(kind, n_missing, force_coop):
     # the fixture of reference tests/test_kalman_filter.py:226-241 (m=2, p=1, P0 = 1e6 I)
-    check_against_oracle(kind, nile_inputs(n_missing), force_coop=force_coop)
+    # Forward moments / logp: rtol 1e-8.  Gradients: P0 = 1e6 I makes the first updates cancel ~6 digits
+    # (P - K K^T F in the univariate filter), so oracle and kernel - both float64, different rounding order -
+    # agree to ~1e-7 on the tiny dlogp/dP0 entries; the reference's own tolerance on this fixture is
+    # rtol = atol = 1e-7 (tests/test_kalman_filter.py:241).
+    check_against_oracle(kind, nile_inputs(n_missing), force_coop=force_coop, grad_rtol=1e-6)
 
 
 @pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
