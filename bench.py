@@ -33,7 +33,7 @@ TAPE_BYTES_PER_STEP = 40.0      # 8 * (m + m(m+1)/2) written by the forward kern
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--draws", type=int, default=65536, help="draws per GPU")

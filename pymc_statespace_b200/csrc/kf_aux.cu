@@ -249,8 +249,187 @@ __global__ void lyapunov_backward_kernel(long long B, int m, int r, MatArg A, Ma
   }
 }
 
+// ---- thread-per-draw variants for small k_states: everything in registers, zero synchronisation ----
+template <int M>
+__device__ __forceinline__ bool smith_doubling_reg(double (&Ak)[M * M], double (&X)[M * M]) {
+  double S[M * M];
+#pragma unroll 1
+  for (int it = 0; it < 64; ++it) {
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) mx = fmax(mx, fabs(Ak[i]));
+    if (!(mx < 1.0e150)) return false;
+    if (mx < 1.0e-11) return true;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(Ak[i * M + k], X[k * M + j], s);
+        S[i * M + j] = s;
+      }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s = X[i * M + j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(S[i * M + k], Ak[j * M + k], s);
+        X[i * M + j] = s;
+      }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(Ak[i * M + k], Ak[k * M + j], s);
+        S[i * M + j] = s;
+      }
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) Ak[i] = S[i];
+  }
+  return false;
+}
+
+template <int M>
+__global__ void __launch_bounds__(128)
+    lyapunov_forward_thread_kernel(long long B, int r, MatArg A, MatArg R, MatArg Q, double* __restrict__ Xo,
+                                   int* __restrict__ info) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* Ap = A.p + b * A.bs;
+  const double* Rp = R.p + b * R.bs;
+  const double* Qp = Q.p + b * Q.bs;
+  double Ak[M * M], X[M * M];
+#pragma unroll
+  for (int i = 0; i < M * M; ++i) Ak[i] = Ap[i];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < r; ++k) {
+        double rq = 0.0;
+        for (int l = 0; l < r; ++l) rq = fma(Rp[i * r + l], Qp[l * r + k], rq);
+        s = fma(rq, Rp[j * r + k], s);
+      }
+      X[i * M + j] = s;
+    }
+  const bool ok = smith_doubling_reg<M>(Ak, X);
+#pragma unroll
+  for (int i = 0; i < M * M; ++i) Xo[b * M * M + i] = ok ? X[i] : nan("");
+  if (info) info[b] = ok ? 0 : 1;
+}
+
+template <int M>
+__global__ void __launch_bounds__(128)
+    lyapunov_backward_thread_kernel(long long B, int r, MatArg A, MatArg R, MatArg Q, const double* __restrict__ Xs,
+                                    const double* __restrict__ Xbar, double* __restrict__ Abar,
+                                    double* __restrict__ Rbar, double* __restrict__ Qbar) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* Ap = A.p + b * A.bs;
+  const double* Rp = R.p + b * R.bs;
+  const double* Qp = Q.p + b * Q.bs;
+  double Ak[M * M], S[M * M], Am[M * M], Xm[M * M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      Am[i * M + j] = Ap[i * M + j];
+      Ak[j * M + i] = Am[i * M + j];  // A^T
+      S[i * M + j] = Xbar[b * M * M + i * M + j];
+      Xm[i * M + j] = Xs[b * M * M + i * M + j];
+    }
+  smith_doubling_reg<M>(Ak, S);
+  if (Abar) {
+    double W[M * M], W2[M * M];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          s1 = fma(Am[i * M + k], Xm[j * M + k], s1);
+          s2 = fma(Am[i * M + k], Xm[k * M + j], s2);
+        }
+        W[i * M + j] = s1;
+        W2[i * M + j] = s2;
+      }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s = Abar[b * M * M + i * M + j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          s = fma(S[i * M + k], W[k * M + j], s);
+          s = fma(S[k * M + i], W2[k * M + j], s);
+        }
+        Abar[b * M * M + i * M + j] = s;
+      }
+  }
+  if (Rbar) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+      for (int j = 0; j < r; ++j) {
+        double s = Rbar[b * M * r + i * r + j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          double rq1 = 0.0, rq2 = 0.0;
+          for (int l = 0; l < r; ++l) {
+            rq1 = fma(Rp[k * r + l], Qp[j * r + l], rq1);
+            rq2 = fma(Rp[k * r + l], Qp[l * r + j], rq2);
+          }
+          s = fma(S[i * M + k], rq1, s);
+          s = fma(S[k * M + i], rq2, s);
+        }
+        Rbar[b * M * r + i * r + j] = s;
+      }
+  }
+  if (Qbar) {
+    for (int a = 0; a < r; ++a)
+      for (int c = 0; c < r; ++c) {
+        double s = Qbar[b * r * r + a * r + c];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          double cr = 0.0;
+#pragma unroll
+          for (int j = 0; j < M; ++j) cr = fma(S[i * M + j], Rp[j * r + c], cr);
+          s = fma(Rp[i * r + a], cr, s);
+        }
+        Qbar[b * r * r + a * r + c] = s;
+      }
+  }
+}
+
+template <int M>
+static cudaError_t lyap_thread_fwd(long long B, int r, MatArg A, MatArg R, MatArg Q, double* X, int* info,
+                                   cudaStream_t s) {
+  lyapunov_forward_thread_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(B, r, A, R, Q, X, info);
+  count_launch();
+  return cudaGetLastError();
+}
+template <int M>
+static cudaError_t lyap_thread_bwd(long long B, int r, MatArg A, MatArg R, MatArg Q, const double* X, const double* Xbar,
+                                   double* Abar, double* Rbar, double* Qbar, cudaStream_t s) {
+  lyapunov_backward_thread_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(B, r, A, R, Q, X, Xbar, Abar, Rbar, Qbar);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lyapunov_forward(long long B, int m, int r, MatArg A, MatArg R, MatArg Q, double* X, int* info,
                                     cudaStream_t s) {
+  switch (m) {
+    case 1: return lyap_thread_fwd<1>(B, r, A, R, Q, X, info, s);
+    case 2: return lyap_thread_fwd<2>(B, r, A, R, Q, X, info, s);
+    case 3: return lyap_thread_fwd<3>(B, r, A, R, Q, X, info, s);
+    case 4: return lyap_thread_fwd<4>(B, r, A, R, Q, X, info, s);
+    default: break;
+  }
   const size_t per_warp = (size_t)3 * m * m * sizeof(double);
   int warps = 4;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
@@ -264,6 +443,13 @@ cudaError_t launch_lyapunov_forward(long long B, int m, int r, MatArg A, MatArg 
 
 cudaError_t launch_lyapunov_backward(long long B, int m, int r, MatArg A, MatArg R, MatArg Q, const double* X,
                                      const double* Xbar, double* Abar, double* Rbar, double* Qbar, cudaStream_t s) {
+  switch (m) {
+    case 1: return lyap_thread_bwd<1>(B, r, A, R, Q, X, Xbar, Abar, Rbar, Qbar, s);
+    case 2: return lyap_thread_bwd<2>(B, r, A, R, Q, X, Xbar, Abar, Rbar, Qbar, s);
+    case 3: return lyap_thread_bwd<3>(B, r, A, R, Q, X, Xbar, Abar, Rbar, Qbar, s);
+    case 4: return lyap_thread_bwd<4>(B, r, A, R, Q, X, Xbar, Abar, Rbar, Qbar, s);
+    default: break;
+  }
   const size_t per_warp = (size_t)4 * m * m * sizeof(double);
   int warps = 4;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;

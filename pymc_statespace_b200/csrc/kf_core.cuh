@@ -26,7 +26,7 @@ constexpr double KF_LOG_2PI = 1.8378770664093454835606594728112;  // MVN_CONST k
 constexpr double KF_LN2 = 0.69314718055994530941723212145818;
 
 enum MathKind : int { MK_STD = 0, MK_UNIV = 1, MK_STEADY = 2, MK_CHOLS = 3 };
-enum SizeClass : int { SZ_M = 0, SZ_P = 1, SZ_MM = 2, SZ_MP = 3, SZ_PP = 4 };
+enum SizeClass : int { SZ_M = 0, SZ_P = 1, SZ_MM = 2, SZ_MP = 3, SZ_PP = 4, SZ_TAPE = 5 };
 
 struct MatArg {
   const double* p;
@@ -349,7 +349,9 @@ KFB_HD int count_missing(X& x, const double* yt) {
 // ------------------------------------------------------------------------------------------------
 // forward recursion for one unit
 // ------------------------------------------------------------------------------------------------
-template <int MK, class X>
+// FULL = false: only loglik (+ tape) is produced - the per-leapfrog hot path; all per-step output stores, their
+// address arithmetic and the per-step log are compiled out.
+template <int MK, bool FULL, class X>
 KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
   const int m = x.m(), p = x.p(), n = A.n;
   const long long draw = u / A.n_series, series = u - draw * A.n_series;
@@ -381,13 +383,15 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
   x.sync();
 
   const double* y = x.y_base(A, series);
-  const bool full = (A.ll_obs != nullptr);
+  const bool full = FULL && (A.ll_obs != nullptr);
   const bool lane0 = (x.lane() == 0);
   LogAcc acc;
   double llsum = 0.0;
   int info = 0;
 
-  if (A.ps) {
+  double* tp = A.tape ? x.tape_base(A, u) : nullptr;  // entry of step t+1 is written at the end of step t
+  const long long tstep = x.tape_step(A), telem = x.tape_elem(A);
+  if (FULL && A.ps) {
     const double* a0p = A.a0.p + draw * A.a0.bs;
     const double* P0p = A.P0.p + draw * A.P0.bs;
     KFB_FOR(i, m) A.ps[(u * (n + 1)) * m + i] = a0p[i];
@@ -443,17 +447,18 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
     }
     llsum += ll_t;
     if (full && lane0) A.ll_obs[u * n + t] = ll_t;
-    if (A.fs) KFB_FOR(i, m) A.fs[(u * n + t) * m + i] = af[i];
-    if (A.fc) KFB_FOR(i, m * m) A.fc[(u * n + t) * m * m + i] = Pf[i];
+    if (FULL && A.fs) KFB_FOR(i, m) A.fs[(u * n + t) * m + i] = af[i];
+    if (FULL && A.fc) KFB_FOR(i, m * m) A.fc[(u * n + t) * m * m + i] = Pf[i];
     predict(x, prm.T, C, c, af, Pf, a, P, tmp.S1, tmp.S2);
-    if (A.ps) KFB_FOR(i, m) A.ps[(u * (n + 1) + t + 1) * m + i] = a[i];
-    if (A.pc) KFB_FOR(i, m * m) A.pc[(u * (n + 1) + t + 1) * m * m + i] = P[i];
-    if (A.tape && t + 1 < n) {
-      KFB_FOR(k, m) A.tape[x.tape_index(A, u, t + 1, k)] = a[k];
+    if (FULL && A.ps) KFB_FOR(i, m) A.ps[(u * (n + 1) + t + 1) * m + i] = a[i];
+    if (FULL && A.pc) KFB_FOR(i, m * m) A.pc[(u * (n + 1) + t + 1) * m * m + i] = P[i];
+    if (tp && t + 1 < n) {
+      KFB_FOR(k, m) tp[k * telem] = a[k];
       KFB_FOR(idx, m * m) {
         const int i = idx / m, j = idx - i * m;
-        if (j >= i) A.tape[x.tape_index(A, u, t + 1, m + i * m - (i * (i - 1)) / 2 + (j - i))] = P[idx];
+        if (j >= i) tp[(m + i * m - (i * (i - 1)) / 2 + (j - i)) * telem] = P[idx];
       }
+      tp += tstep;
     }
   }
   if (lane0) {
@@ -499,6 +504,13 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
 
   const double* y = x.y_base(A, series);
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
+  // Tape read-ahead: the entry of step t-1 is requested while step t is being processed, so the HBM latency
+  // of the (strictly sequential) adjoint recursion is hidden behind one step of arithmetic.
+  typename X::template Buf<SZ_TAPE> nxt(x);
+  const long long tstep = x.tape_step(A), telem = x.tape_elem(A);
+  const double* tp = x.tape_base(A, u) + (long long)(n - 2) * tstep;  // entry of step n-1
+  if (n > 1) KFB_FOR(k, kt) nxt[k] = tp[k * telem];
+  x.sync();
 
   for (int t = n - 1; t >= 0; --t) {
     if (X::TV) {
@@ -514,15 +526,18 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       if (MK == MK_STEADY) load_or_zero(x, P, A.Pss.p + u * A.Pss.bs, m * m);
       else load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
     } else {
-      KFB_FOR(k, m) a[k] = A.tape[x.tape_index(A, u, t, k)];
+      KFB_FOR(k, m) a[k] = nxt[k];
       KFB_FOR(idx, m * m) {
         int i = idx / m, j = idx - i * m;
         if (j < i) { const int s = i; i = j; j = s; }
-        const int k = m + i * m - (i * (i - 1)) / 2 + (j - i);
-        P[idx] = A.tape[x.tape_index(A, u, t, k)];
+        P[idx] = nxt[m + i * m - (i * (i - 1)) / 2 + (j - i)];
       }
     }
     x.sync();
+    if (t > 1) {
+      tp -= tstep;
+      KFB_FOR(k, kt) nxt[k] = tp[k * telem];
+    }
     const double* yt = y + (long long)t * p;
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);  // cotangent of ll_t
 

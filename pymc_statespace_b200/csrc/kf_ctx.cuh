@@ -22,7 +22,7 @@ template <int M, int P>
 struct ThreadCtx {
   static constexpr bool TV = false;
   template <int SZ>
-  using Buf = RegBuf<(SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : P * P)>;
+  using Buf = RegBuf<(SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : M + (M * (M + 1)) / 2)>;
   const double* y_smem;  // observations staged in shared memory (shared y) or nullptr
   KFB_HD static constexpr int m() { return M; }
   KFB_HD static constexpr int p() { return P; }
@@ -32,9 +32,10 @@ struct ThreadCtx {
   KFB_HD const double* y_base(const KfArgs& A, long long series) const {
     return y_smem ? y_smem : A.y.p + series * A.y.bs;
   }
-  KFB_HD long long tape_index(const KfArgs& A, long long u, int t, int k) const {
-    return ((long long)(t - 1) * tape_width(M) + k) * A.U + u;
-  }
+  // tape entry of step t (t >= 1) = tape_base + (t-1) * tape_step; element k at [k * tape_elem]
+  KFB_HD double* tape_base(const KfArgs& A, long long u) const { return A.tape + u; }
+  KFB_HD long long tape_step(const KfArgs& A) const { return (long long)tape_width(M) * A.U; }
+  KFB_HD long long tape_elem(const KfArgs& A) const { return A.U; }
 };
 
 // ---------------------------------------------------------------------------
@@ -50,7 +51,7 @@ struct CoopCtx {
   bool overflow;
 
   KFB_HD int size_of(int sz) const {
-    return sz == SZ_M ? m_ : sz == SZ_P ? p_ : sz == SZ_MM ? m_ * m_ : sz == SZ_MP ? m_ * p_ : p_ * p_;
+    return sz == SZ_M ? m_ : sz == SZ_P ? p_ : sz == SZ_MM ? m_ * m_ : sz == SZ_MP ? m_ * p_ : sz == SZ_PP ? p_ * p_ : tape_width(m_);
   }
   KFB_HD double* bump(int cnt) {
     double* r = arena + off;
@@ -76,9 +77,11 @@ struct CoopCtx {
 #endif
   }
   KFB_HD const double* y_base(const KfArgs& A, long long series) const { return A.y.p + series * A.y.bs; }
-  KFB_HD long long tape_index(const KfArgs& A, long long u, int t, int k) const {
-    return (u * (long long)(A.n - 1) + (t - 1)) * tape_width(m_) + k;
+  KFB_HD double* tape_base(const KfArgs& A, long long u) const {
+    return A.tape + u * (long long)(A.n - 1) * tape_width(m_);
   }
+  KFB_HD long long tape_step(const KfArgs&) const { return tape_width(m_); }
+  KFB_HD long long tape_elem(const KfArgs&) const { return 1; }
 };
 
 // doubles of arena one unit needs (upper bound of what forward_unit / backward_unit bump-allocate)
@@ -87,7 +90,7 @@ inline int coop_arena_doubles(int m, int p, bool backward) {
   const int params = mm + mp + pp + p + pp;
   const int upd = 3 * p + 3 * mp + 4 * pp + 3 * mm;
   if (!backward) return params + 3 * mm + 5 * m + upd;
-  return params + 8 * mm + 8 * m + 4 * mp + 4 * pp + 2 * p + upd;
+  return params + 8 * mm + 8 * m + 4 * mp + 4 * pp + 2 * p + upd + m + (m * (m + 1)) / 2;
 }
 
 }  // namespace kfb

@@ -45,7 +45,8 @@ __device__ __forceinline__ void stage_y(double* ysm, const double* ysrc, int cou
   __syncthreads();
 }
 
-template <int M, int P, int MK, bool BWD>
+// MODE: 0 = forward, loglik (+tape) only; 1 = forward with per-step outputs; 2 = adjoint
+template <int M, int P, int MK, int MODE>
 __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     kf_thread_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= A.U) return;
   ThreadCtx<M, P> x{ysm};
-  if (BWD) backward_unit<MK>(x, A, u);
-  else forward_unit<MK>(x, A, u);
+  if (MODE == 2) backward_unit<MK>(x, A, u);
+  else forward_unit<MK, MODE == 1>(x, A, u);
 }
 
 template <int MK, bool BWD, bool WARP>
@@ -85,7 +86,7 @@ __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubl
     u = blockIdx.x;
   }
   if (BWD) backward_unit<MK>(x, A, u);
-  else forward_unit<MK>(x, A, u);
+  else forward_unit<MK, true>(x, A, u);
   if (x.overflow) __trap();
 }
 

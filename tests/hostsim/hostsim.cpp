@@ -12,7 +12,8 @@ using namespace kfb;
 
 template <int MK, class X>
 static void run_both(X& x, KfArgs& A, int do_bwd) {
-  forward_unit<MK>(x, A, 0);
+  if (A.ll_obs || A.fs) forward_unit<MK, true>(x, A, 0);
+  else forward_unit<MK, false>(x, A, 0);
   if (do_bwd) backward_unit<MK>(x, A, 0);
 }
 
@@ -62,9 +63,9 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   CoopCtx x;
   x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false;
   x.off = 0;
-  if (A.math_kind == MK_STD) forward_unit<MK_STD>(x, A, 0);
-  else if (A.math_kind == MK_UNIV) forward_unit<MK_UNIV>(x, A, 0);
-  else forward_unit<MK_STEADY>(x, A, 0);
+  if (A.math_kind == MK_STD) forward_unit<MK_STD, true>(x, A, 0);
+  else if (A.math_kind == MK_UNIV) forward_unit<MK_UNIV, true>(x, A, 0);
+  else forward_unit<MK_STEADY, true>(x, A, 0);
   const int fwd_used = x.off;
   if (fwd_used > coop_arena_doubles(m, p, false)) return 3;
   if (do_bwd) {
