@@ -34,7 +34,7 @@ struct Plan {
   long long U, nD;
   int nTC;           // time entries of C = R Q R^T (1 or n)
   long long C_bs;    // 0 if R and Q are shared by all draws
-  size_t off_C, off_Pss, off_Gss, off_tape, off_gC, off_gPss, off_gGss, total;
+  size_t off_C, off_Pss, off_Gss, off_dinfo, off_tape, off_gC, off_gPss, off_gGss, total;
 };
 
 static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
@@ -49,8 +49,8 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
       if (d->p != 1) return KFB_ERR_INVALID_ARG;  // assert_data_is_1d, kalman_filter.py:19,329
       pl->mk = MK_STD; pl->ll_const = l2pi; pl->d_sign = corrected ? 1.0 : -1.0; break;
     case KFB_CHOLESKY:
-      if (d->p != 1 && !corrected) return KFB_ERR_UNSUPPORTED;  // strict Q4 variant for p > 1: not built yet
-      pl->mk = MK_STD; pl->ll_const = d->p * l2pi; pl->d_sign = 1.0; break;
+      // as coded the filter is exact only for p = 1; p > 1 strict = bug-compatible MK_CHOLS
+      pl->mk = (d->p != 1 && !corrected) ? MK_CHOLS : MK_STD; pl->ll_const = d->p * l2pi; pl->d_sign = 1.0; break;
     case KFB_UNIVARIATE:
       pl->mk = MK_UNIV; pl->ll_const = 0.0; pl->d_sign = 1.0; break;
     case KFB_STEADY_STATE:
@@ -59,7 +59,6 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
   }
   pl->tv_any = d->T_ts || d->Z_ts || d->R_ts || d->H_ts || d->Q_ts || d->c_ts || d->d_ts;
   if (pl->tv_any && (pl->mk == MK_UNIV || pl->mk == MK_STEADY)) return KFB_ERR_UNSUPPORTED;
-  if (pl->mk == MK_STEADY) return KFB_ERR_UNSUPPORTED;  // DARE kernel: not built yet
   pl->U = d->n_draws * d->n_series;
   pl->nD = d->n_draws;
   pl->nTC = (d->R_ts || d->Q_ts) ? d->n : 1;
@@ -72,9 +71,11 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
   auto take = [&](size_t doubles) { size_t o = off; off += ((doubles * 8 + 255) / 256) * 256; return o; };
   pl->off_C = take((size_t)nDC * pl->nTC * d->m * d->m);
   pl->off_Pss = pl->off_Gss = pl->off_gPss = pl->off_gGss = 0;
+  pl->off_dinfo = 0;
   if (pl->mk == MK_STEADY) {
-    pl->off_Pss = take((size_t)pl->U * d->m * d->m);
-    pl->off_Gss = take((size_t)pl->U * d->p * d->p);
+    pl->off_Pss = take((size_t)pl->nD * d->m * d->m);
+    pl->off_Gss = take((size_t)pl->nD * d->p * d->p);
+    pl->off_dinfo = take((size_t)(pl->nD + 1) / 2);
   }
   pl->off_tape = pl->off_gC = 0;
   if (save) {
@@ -102,7 +103,7 @@ static void fill_args(const kfb_desc* d, const kfb_inputs* in, const Plan& pl, c
   A->c = {in->c, d->c_bs, d->c_ts};
   A->d = {in->d, d->d_bs, d->d_ts};
   if (pl.mk == MK_STEADY) {
-    A->Pss = {(const double*)(ws + pl.off_Pss), (long long)d->m * d->m, 0};
+    A->Pss = {(const double*)(ws + pl.off_Pss), (long long)d->m * d->m, 0};  // one per draw
     A->Gss = {(const double*)(ws + pl.off_Gss), (long long)d->p * d->p, 0};
   }
   A->ll_const = pl.ll_const;
@@ -184,6 +185,18 @@ kfb_status kfb_forward(const kfb_desc* desc, const kfb_inputs* in, const kfb_out
   cudaError_t e = launch_rqr_forward(nDC, pl.nTC, desc->m, desc->r, MatArg{in->R, desc->R_bs, desc->R_ts},
                                      MatArg{in->Q, desc->Q_bs, desc->Q_ts}, (double*)(ws + pl.off_C), s);
   if (e != cudaSuccess) return cuda_fail(e);
+  if (pl.mk == MK_STEADY) {
+    // P_steady = DARE(T^T, Z^T, R Q R^T, H), F_inv = (Z P_steady Z^T + H)^-1   (kalman_filter.py:384-386)
+    DareArgs D;
+    std::memset(&D, 0, sizeof(D));
+    D.nD = desc->n_draws; D.U = pl.U; D.n_series = desc->n_series; D.m = desc->m; D.p = desc->p;
+    D.T = MatArg{in->T, desc->T_bs, 0}; D.Z = MatArg{in->Z, desc->Z_bs, 0}; D.H = MatArg{in->H, desc->H_bs, 0};
+    D.C = A.C;
+    D.Pss = (double*)(ws + pl.off_Pss); D.Gss = (double*)(ws + pl.off_Gss); D.info = (int*)(ws + pl.off_dinfo);
+    e = launch_dare(D, false, s);
+    if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
   return launch_main(desc, pl, A, false, s);
 }
 
@@ -205,8 +218,25 @@ kfb_status kfb_backward(const kfb_desc* desc, const kfb_inputs* in, const kfb_co
   A.ga0 = g->a0; A.gP0 = g->P0; A.gT = g->T; A.gZ = g->Z; A.gH = g->H; A.gc = g->c; A.gd = g->d;
   const bool want_C = g->R || g->Q;
   A.gC = want_C ? (double*)(ws + pl.off_gC) : nullptr;
+  if (pl.mk == MK_STEADY) {
+    A.gPss = (double*)(ws + pl.off_gPss);
+    A.gGss = (double*)(ws + pl.off_gGss);
+  }
   st = launch_main(desc, pl, A, true, s);
   if (st != KFB_OK) return st;
+  if (pl.mk == MK_STEADY) {
+    // chain (P_steady-bar, F_inv-bar) through the DARE (utils/pytensor_scipy.py:39-60) into T, Z, H, C
+    DareArgs D;
+    std::memset(&D, 0, sizeof(D));
+    D.nD = desc->n_draws; D.U = pl.U; D.n_series = desc->n_series; D.m = desc->m; D.p = desc->p;
+    D.T = MatArg{in->T, desc->T_bs, 0}; D.Z = MatArg{in->Z, desc->Z_bs, 0}; D.H = MatArg{in->H, desc->H_bs, 0};
+    D.C = A.C;
+    D.Pss = (double*)(ws + pl.off_Pss); D.Gss = (double*)(ws + pl.off_Gss);
+    D.gPss = A.gPss; D.gGss = A.gGss; D.gT = g->T; D.gZ = g->Z; D.gH = g->H; D.gC = A.gC;
+    cudaError_t e = launch_dare(D, true, s);
+    if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+    if (e != cudaSuccess) return cuda_fail(e);
+  }
   if (want_C) {
     cudaError_t e = launch_rqr_backward(pl.U, desc->n_series, pl.nTC, desc->R_ts ? desc->n : 1, desc->Q_ts ? desc->n : 1,
                                         desc->m, desc->r, MatArg{in->R, desc->R_bs, desc->R_ts},

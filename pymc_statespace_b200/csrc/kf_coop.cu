@@ -24,6 +24,7 @@ static cudaError_t launch_coop_mode(const KfArgs& A, bool bwd, int arena, int bl
     case MK_STD: return launch_coop_kind<MK_STD, WARP>(A, bwd, arena, block, grid, smem, s);
     case MK_UNIV: return launch_coop_kind<MK_UNIV, WARP>(A, bwd, arena, block, grid, smem, s);
     case MK_STEADY: return launch_coop_kind<MK_STEADY, WARP>(A, bwd, arena, block, grid, smem, s);
+    case MK_CHOLS: return launch_coop_kind<MK_CHOLS, WARP>(A, bwd, arena, block, grid, smem, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -44,6 +45,36 @@ cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s) {
   }
   const int block = 256;
   return launch_coop_mode<false>(A, bwd, arena, block, (unsigned)A.U, arena_bytes, s);
+}
+
+cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s) {
+  int arena = (dare_arena_doubles(D.m, D.p) + 1) & ~1;
+  const size_t arena_bytes = (size_t)arena * sizeof(double);
+  const size_t smem_max = 227 * 1024;
+  if (arena_bytes > smem_max) return cudaErrorInvalidConfiguration;
+  const long long count = bwd ? D.U : D.nD;
+  if (arena_bytes * 4 <= smem_max) {
+    const int warps = 4;
+    const unsigned grid = (unsigned)((count + warps - 1) / warps);
+    const size_t smem = arena_bytes * warps;
+    if (bwd) {
+      cudaFuncSetAttribute(kf_dare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kf_dare_kernel<true, true><<<grid, warps * 32, smem, s>>>(D, arena);
+    } else {
+      cudaFuncSetAttribute(kf_dare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kf_dare_kernel<false, true><<<grid, warps * 32, smem, s>>>(D, arena);
+    }
+  } else {
+    if (bwd) {
+      cudaFuncSetAttribute(kf_dare_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena_bytes);
+      kf_dare_kernel<true, false><<<(unsigned)count, 256, arena_bytes, s>>>(D, arena);
+    } else {
+      cudaFuncSetAttribute(kf_dare_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena_bytes);
+      kf_dare_kernel<false, false><<<(unsigned)count, 256, arena_bytes, s>>>(D, arena);
+    }
+  }
+  count_launch();
+  return cudaGetLastError();
 }
 
 }  // namespace kfb

@@ -174,6 +174,89 @@ KFB_HD bool ldl_inverse(const TF& F, TG& G, TL& L, TL& Li, TP& piv, int p) {
   return ok;
 }
 
+// Cholesky F = L L^T (lower, full storage) and Li = L^-1, serial (one lane).  Used only by the as-coded
+// CholeskyFilter for k_endog > 1 (MK_CHOLS).  logdet <- log det F.
+template <class TF, class TL>
+KFB_HD bool chol_factor(const TF& F, TL& L, TL& Li, int p, double* logdet) {
+  bool ok = true;
+  double ld = 0.0;
+  for (int j = 0; j < p; ++j) {
+    double dj = F[j * p + j];
+    for (int k = 0; k < j; ++k) dj -= L[j * p + k] * L[j * p + k];
+    ok = ok && (dj > 0.0) && (dj < 1.0e300);
+    const double lj = sqrt(dj);
+    ld += log(dj);
+    L[j * p + j] = lj;
+    for (int i = 0; i < p; ++i) {
+      if (i < j) L[i * p + j] = 0.0;
+      if (i > j) {
+        double s = F[i * p + j];
+        for (int k = 0; k < j; ++k) s -= L[i * p + k] * L[j * p + k];
+        L[i * p + j] = s / lj;
+      }
+    }
+  }
+  for (int c = 0; c < p; ++c)
+    for (int i = 0; i < p; ++i) {
+      if (i < c) Li[i * p + c] = 0.0;
+      else {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) s -= L[i * p + k] * Li[k * p + c];
+        Li[i * p + c] = s / L[i * p + i];
+      }
+    }
+  *logdet = ld;
+  return ok;
+}
+
+// Adjoint of the as-coded gain matrix Gk[k][i] = Li[i][k] / L_ii (and of -sum log L_ii) back to F, serial.
+//   Gb  cotangent of Gk;  lb cotangent of ll;  W1, W2 scratch (p x p);  Fb <- cotangent of F (symmetrised, the
+//   convention of torch.linalg.cholesky; PyTensor folds it into the lower triangle - same symmetric part).
+template <class TG, class TL, class TW>
+KFB_HD void chols_adjoint(const TG& Gb, const TL& L, const TL& Li, const TG& Gk, double lb, TW& W1, TW& W2, TG& Fb,
+                          int p) {
+  // W1 = Lib : Lib[i][k] = Gb[k][i] / L_ii
+  for (int i = 0; i < p; ++i)
+    for (int k = 0; k < p; ++k) W1[i * p + k] = Gb[k * p + i] / L[i * p + i];
+  // W2 = Lb = -Li^T Lib Li^T
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) {
+      double s = 0.0;
+      for (int a = 0; a < p; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[j * p + b];
+        s += Li[a * p + i] * t;
+      }
+      W2[i * p + j] = -s;
+    }
+  for (int i = 0; i < p; ++i) {
+    double s = 0.0;
+    for (int k = 0; k < p; ++k) s += Gb[k * p + i] * Gk[k * p + i];
+    W2[i * p + i] += -s / L[i * p + i] - lb / L[i * p + i];
+  }
+  // W1 = Phi = tril(L^T Lb), diagonal halved
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) {
+      double s = 0.0;
+      if (j <= i)
+        for (int k = 0; k < p; ++k) s += L[k * p + i] * W2[k * p + j];
+      W1[i * p + j] = (i == j) ? 0.5 * s : s;
+    }
+  // W2 = S = Li^T Phi Li ; Fb = (S + S^T) / 2
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) {
+      double s = 0.0;
+      for (int a = 0; a < p; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[b * p + j];
+        s += Li[a * p + i] * t;
+      }
+      W2[i * p + j] = s;
+    }
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) Fb[i * p + j] = 0.5 * (W2[i * p + j] + W2[j * p + i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-unit constant parameters + scratch, allocated from the context (registers or shared memory)
 // ------------------------------------------------------------------------------------------------
@@ -227,7 +310,15 @@ KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, do
   x.sync();
   st.ok = true;
   st.logdet = 0.0;
-  if (x.lane() == 0) {
+  if (MK == MK_CHOLS) {
+    if (x.lane() == 0) {
+      double ld = 0.0;
+      st.ok = chol_factor(u.F, u.L, u.Li, p, &ld);
+      st.logdet = ld;  // -sum log L_ii = -0.5 log det F  (:314)
+      for (int k = 0; k < p; ++k)
+        for (int i = 0; i < p; ++i) u.Fi[k * p + i] = u.Li[i * p + k] / u.L[i * p + i];  // Gk
+    }
+  } else if (x.lane() == 0) {
     st.ok = ldl_inverse(u.F, u.Fi, u.L, u.Li, u.piv, p);
     if (st.ok) {
 #pragma unroll
@@ -251,7 +342,7 @@ KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, do
     KFB_FOR(i, p) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < p; ++j) s = kf_fma(u.Fi[i * p + j], u.v[j], s);
+      for (int j = 0; j < p; ++j) s = kf_fma(MK == MK_CHOLS ? u.Fi[j * p + i] : u.Fi[i * p + j], u.v[j], s);
       u.w[i] = s;
     }
   }
@@ -375,8 +466,8 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
   load_or_zero(x, prm.d, dp, p);
   load_or_zero(x, a, A.a0.p + draw * A.a0.bs, m);
   if (MK == MK_STEADY) {
-    load_or_zero(x, P, A.Pss.p + u * A.Pss.bs, m * m);  // recursion starts at P_steady (:391, Q7)
-    load_or_zero(x, prm.Gss, A.Gss.p + u * A.Gss.bs, p * p);
+    load_or_zero(x, P, A.Pss.p + draw * A.Pss.bs, m * m);  // recursion starts at P_steady (:391, Q7)
+    load_or_zero(x, prm.Gss, A.Gss.p + draw * A.Gss.bs, p * p);
   } else {
     load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
   }
@@ -494,7 +585,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
   load_or_zero(x, prm.Z, Zp, p * m);
   load_or_zero(x, prm.H, Hp, p * p);
   load_or_zero(x, prm.d, dp, p);
-  if (MK == MK_STEADY) load_or_zero(x, prm.Gss, A.Gss.p + u * A.Gss.bs, p * p);
+  if (MK == MK_STEADY) load_or_zero(x, prm.Gss, A.Gss.p + draw * A.Gss.bs, p * p);
   KFB_FOR(i, m) { ab[i] = 0.0; cb[i] = 0.0; }
   KFB_FOR(i, m * m) { Pb[i] = 0.0; Tb[i] = 0.0; Cb[i] = 0.0; }
   KFB_FOR(i, p * m) Zb[i] = 0.0;
@@ -504,14 +595,10 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
 
   const double* y = x.y_base(A, series);
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
-  // Tape read-ahead: the entry of step t-1 is requested while step t is being processed, so the HBM latency
-  // of the (strictly sequential) adjoint recursion is hidden behind one step of arithmetic.
+  // Tape read-ahead (X::TapeReader): entries of steps t-1, t-2, ... are already in flight while step t is being
+  // processed, so the HBM latency of the strictly sequential adjoint recursion is hidden behind arithmetic.
   typename X::template Buf<SZ_TAPE> nxt(x);
-  const long long tstep = x.tape_step(A), telem = x.tape_elem(A);
-  const double* tp = x.tape_base(A, u) + (long long)(n - 2) * tstep;  // entry of step n-1
-  if (n > 1) KFB_FOR(k, kt) nxt[k] = tp[k * telem];
-  x.sync();
-
+  typename X::TapeReader rd(x, A, u);
   for (int t = n - 1; t >= 0; --t) {
     if (X::TV) {
       if (A.T.ts) load_or_zero(x, prm.T, Tp + t * A.T.ts, m * m);
@@ -523,9 +610,10 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
     // predicted moments entering step t
     if (t == 0) {
       load_or_zero(x, a, A.a0.p + draw * A.a0.bs, m);
-      if (MK == MK_STEADY) load_or_zero(x, P, A.Pss.p + u * A.Pss.bs, m * m);
+      if (MK == MK_STEADY) load_or_zero(x, P, A.Pss.p + draw * A.Pss.bs, m * m);
       else load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
     } else {
+      rd.get(x, nxt);  // entry of step t
       KFB_FOR(k, m) a[k] = nxt[k];
       KFB_FOR(idx, m * m) {
         int i = idx / m, j = idx - i * m;
@@ -534,10 +622,6 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       }
     }
     x.sync();
-    if (t > 1) {
-      tp -= tstep;
-      KFB_FOR(k, kt) nxt[k] = tp[k * telem];
-    }
     const double* yt = y + (long long)t * p;
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);  // cotangent of ll_t
 
@@ -570,8 +654,8 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
     x.sync();
     KFB_FOR(idx, m * m) Cb[idx] += S3[idx];
     KFB_FOR(i, m) cb[i] += ab[i];
-    gemm<false, false, 0>(x, tmp.S1, prm.T, S4, m, m, m);    // T (Pf + Pf^T)
-    gemm<false, false, 1>(x, Tb, S3, tmp.S1, m, m, m);       // Tb += Ps T (Pf + Pf^T)
+    gemm<false, false, 0>(x, tmp.S1, S3, prm.T, m, m, m);    // W = Ps T        (shared by Tb and Pfb)
+    gemm<false, false, 1>(x, Tb, tmp.S1, S4, m, m, m);       // Tb += Ps T (Pf + Pf^T)
     KFB_FOR(idx, m * m) {
       const int i = idx / m, j = idx - i * m;
       Tb[idx] = kf_fma(ab[i], af[j], Tb[idx]);               // + ab af^T
@@ -582,7 +666,6 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       for (int k = 0; k < m; ++k) s = kf_fma(prm.T[k * m + i], ab[k], s);
       afb[i] = s;
     }
-    gemm<false, false, 0>(x, tmp.S1, S3, prm.T, m, m, m);    // Ps T
     gemm<true, false, 0>(x, Pfb, prm.T, tmp.S1, m, m, m);    // Pfb = T^T Ps T
     if (X::TV) {
       if (A.T.ts && A.gT) { KFB_FOR(i, m * m) { A.gT[(u * n + t) * m * m + i] = Tb[i]; Tb[i] = 0.0; } }
@@ -674,17 +757,15 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         S4[idx] = P[idx] + P[j * m + i];
       }
       x.sync();
-      gemm<false, false, 0>(x, tmp.S1, tmp.A, S4, m, m, m);   // A (P + P^T)
-      gemm<false, false, 0>(x, S3, Pfb, tmp.S1, m, m, m);     // Ab = Pfb A (P + P^T)      (S3 = Ab)
-      gemm<false, false, 0>(x, tmp.S1, Pfb, tmp.A, m, m, m);  // Pfb A
+      gemm<false, false, 0>(x, tmp.S1, Pfb, tmp.A, m, m, m);  // Pfb A            (shared by Ab and Pb)
+      gemm<false, false, 0>(x, S3, tmp.S1, S4, m, m, m);      // Ab = Pfb A (P + P^T)      (S3 = Ab)
       gemm<true, false, 0>(x, Pb, tmp.A, tmp.S1, m, m, m);    // Pb = A^T Pfb A
       KFB_FOR(idx, p * p) {
         const int i = idx / p, j = idx - i * p;
         Q1[idx] = prm.H[idx] + prm.H[j * p + i];
       }
-      x.sync();
-      gemm<false, false, 0>(x, tmp.KH, tmp.K, Q1, m, p, p);   // K (H + H^T)
-      gemm<false, false, 0>(x, Kb, Pfb, tmp.KH, m, m, p);     // Kb = Pfb K (H + H^T)
+      gemm<false, false, 0>(x, PK, Pfb, tmp.K, m, m, p);      // Pfb K            (shared by Kb and Hb)
+      gemm<false, false, 0>(x, Kb, PK, Q1, m, p, p);          // Kb = Pfb K (H + H^T)
       KFB_FOR(idx, m * p) {
         const int i = idx / p, j = idx - i * p;
         double s = kf_fma(afb[i], tmp.v[j], Kb[idx]);         // + afb v^T
@@ -692,7 +773,6 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         for (int k = 0; k < m; ++k) s = kf_fma(-S3[i * m + k], prm.Z[j * m + k], s);  // - Ab Z^T
         Kb[idx] = s;
       }
-      gemm<false, false, 0>(x, PK, Pfb, tmp.K, m, m, p);      // Pfb K
       gemm<true, false, 1>(x, Hb, tmp.K, PK, p, m, p);        // Hb += K^T Pfb K
       gemm<true, false, 2>(x, Zb, tmp.K, S3, p, m, m);        // Zb -= K^T Ab
       // vb, Fb
@@ -713,6 +793,23 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         }
         x.sync();
         gemm<false, true, 0>(x, Mb, Kb, prm.Gss, m, p, p);    // Mb = Kb Gss^T
+      } else if (MK == MK_CHOLS) {
+        KFB_FOR(i, p) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(tmp.K[k * p + i], afb[k], s);
+          for (int j = 0; j < p; ++j) s = kf_fma(-0.5 * lb * (tmp.Fi[i * p + j] + tmp.Fi[j * p + i]), tmp.v[j], s);
+          vb[i] = s;
+        }
+        gemm<true, false, 0>(x, Q1, tmp.Mm, Kb, p, m, p);     // Gk-bar = Mm^T Kb - 0.5 lb v v^T
+        KFB_FOR(idx, p * p) {
+          const int i = idx / p, j = idx - i * p;
+          Q1[idx] = kf_fma(-0.5 * lb * tmp.v[i], tmp.v[j], Q1[idx]);
+        }
+        x.sync();
+        if (x.lane() == 0) chols_adjoint(Q1, tmp.L, tmp.Li, tmp.Fi, lb, tmp.F, Gb, Fb, p);
+        x.sync();
+        gemm<false, true, 0>(x, Mb, Kb, tmp.Fi, m, p, p);     // Mb = Kb Gk^T
       } else {
         KFB_FOR(i, p) {
           double s = -lb * tmp.w[i];

@@ -24,11 +24,68 @@ struct ThreadCtx {
   template <int SZ>
   using Buf = RegBuf<(SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : M + (M * (M + 1)) / 2)>;
   const double* y_smem;  // observations staged in shared memory (shared y) or nullptr
+  double* ring;          // shared-memory ring for the adjoint kernel's tape read-ahead (device only)
+  int tid, nthr;
+  static constexpr int KT = M + (M * (M + 1)) / 2;
+  static constexpr int TAPE_DEPTH = 4;              // entries in flight
+  static constexpr int TAPE_SLOTS = TAPE_DEPTH + 1;  // +1: the slot being refilled was consumed one step earlier
+
+  // Streams the tape backwards.  Device: every thread cp.async's (LDGSTS) its own KT doubles of entries
+  // t-1 .. t-DEPTH into its private column of a shared-memory ring; completion is tracked by cp.async groups, not
+  // by the register scoreboard, so the loads never serialise with the arithmetic of the current step.
+  struct TapeReader {
+    const double* gp;
+    long long tstep, telem;
+    int next_t, slot_fetch, slot_read;
+    KFB_HD TapeReader(ThreadCtx& x, const KfArgs& A, long long u) {
+      tstep = x.tape_step(A);
+      telem = x.tape_elem(A);
+      gp = x.tape_base(A, u) + (long long)(A.n - 2) * tstep;  // entry of step n-1
+      next_t = A.n - 1;
+      slot_fetch = slot_read = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+      for (int s = 0; s < TAPE_DEPTH; ++s) issue(x);
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    __device__ __forceinline__ void issue(ThreadCtx& x) {
+      if (next_t >= 1) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(x.ring + (size_t)slot_fetch * KT * x.nthr + x.tid);
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(k * x.nthr * 8)),
+                       "l"(gp + k * telem)
+                       : "memory");
+        gp -= tstep;
+        --next_t;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      slot_fetch = (slot_fetch + 1 == TAPE_SLOTS) ? 0 : slot_fetch + 1;
+    }
+#endif
+    template <class TB>
+    KFB_HD void get(ThreadCtx& x, TB& dst) {
+#if defined(__CUDA_ARCH__)
+      asm volatile("cp.async.wait_group %0;" ::"n"(TAPE_DEPTH - 1) : "memory");
+      const double* src = x.ring + (size_t)slot_read * KT * x.nthr + x.tid;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) dst[k] = src[k * x.nthr];
+      slot_read = (slot_read + 1 == TAPE_SLOTS) ? 0 : slot_read + 1;
+      issue(x);
+#else
+      for (int k = 0; k < KT; ++k) dst[k] = gp[k * telem];
+      gp -= tstep;
+#endif
+    }
+  };
   KFB_HD static constexpr int m() { return M; }
   KFB_HD static constexpr int p() { return P; }
   KFB_HD static constexpr int lane() { return 0; }
   KFB_HD static constexpr int G() { return 1; }
   KFB_HD void sync() const {}
+  KFB_HD double reduce_max(double v) const { return v; }
+  KFB_HD bool all_ok(bool v) const { return v; }
   KFB_HD const double* y_base(const KfArgs& A, long long series) const {
     return y_smem ? y_smem : A.y.p + series * A.y.bs;
   }
@@ -49,6 +106,7 @@ struct CoopCtx {
   double* arena;
   int off, cap;
   bool overflow;
+  double* red;  // 34 doubles of scratch for cross-lane reductions (CTA mode)
 
   KFB_HD int size_of(int sz) const {
     return sz == SZ_M ? m_ : sz == SZ_P ? p_ : sz == SZ_MM ? m_ * m_ : sz == SZ_MP ? m_ * p_ : sz == SZ_PP ? p_ * p_ : tape_width(m_);
@@ -76,12 +134,52 @@ struct CoopCtx {
     else __syncthreads();
 #endif
   }
+  // max over the G lanes of a unit; every lane gets the result
+  KFB_HD double reduce_max(double v) const {
+#if defined(__CUDA_ARCH__)
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (G_ > 32) {
+      __syncthreads();
+      if ((lane_ & 31) == 0) red[lane_ >> 5] = v;
+      __syncthreads();
+      v = red[0];
+      for (int w = 1; w < (G_ >> 5); ++w) v = fmax(v, red[w]);
+    }
+#endif
+    return v;
+  }
+  // lane 0's flag, broadcast to every lane
+  KFB_HD bool all_ok(bool v) const {
+#if defined(__CUDA_ARCH__)
+    if (G_ <= 32) return __shfl_sync(0xffffffffu, (int)v, 0) != 0;
+    __syncthreads();
+    if (lane_ == 0) red[33] = v ? 1.0 : 0.0;
+    __syncthreads();
+    return red[33] != 0.0;
+#else
+    return v;
+#endif
+  }
   KFB_HD const double* y_base(const KfArgs& A, long long series) const { return A.y.p + series * A.y.bs; }
   KFB_HD double* tape_base(const KfArgs& A, long long u) const {
     return A.tape + u * (long long)(A.n - 1) * tape_width(m_);
   }
   KFB_HD long long tape_step(const KfArgs&) const { return tape_width(m_); }
   KFB_HD long long tape_elem(const KfArgs&) const { return 1; }
+  struct TapeReader {
+    const double* gp;
+    int kt;
+    KFB_HD TapeReader(CoopCtx& x, const KfArgs& A, long long u) {
+      kt = tape_width(x.m_);
+      gp = x.tape_base(A, u) + (long long)(A.n - 2) * kt;
+    }
+    template <class TB>
+    KFB_HD void get(CoopCtx& x, TB& dst) {
+      for (int k = x.lane_; k < kt; k += x.G_) dst[k] = gp[k];
+      gp -= kt;
+      x.sync();
+    }
+  };
 };
 
 // doubles of arena one unit needs (upper bound of what forward_unit / backward_unit bump-allocate)

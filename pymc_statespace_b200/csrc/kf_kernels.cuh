@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "kf_ctx.cuh"
+#include "kf_dare.cuh"
 
 namespace kfb {
 
@@ -57,7 +58,9 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
   }
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= A.U) return;
-  ThreadCtx<M, P> x{ysm};
+  // the adjoint kernel's tape ring lives behind the staged observations (16-byte aligned)
+  double* ring = kf_dyn_smem + ((y_smem_doubles + 1) & ~1);
+  ThreadCtx<M, P> x{ysm, ring, (int)threadIdx.x, (int)blockDim.x};
   if (MODE == 2) backward_unit<MK>(x, A, u);
   else forward_unit<MK, MODE == 1>(x, A, u);
 }
@@ -71,6 +74,7 @@ __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubl
   x.off = 0;
   x.cap = arena_doubles;
   x.overflow = false;
+  x.red = nullptr;
   long long u;
   if (WARP) {
     const int warp = threadIdx.x >> 5;
@@ -89,6 +93,57 @@ __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubl
   else forward_unit<MK, true>(x, A, u);
   if (x.overflow) __trap();
 }
+
+// ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----
+struct DareArgs {
+  long long nD, U, n_series;
+  int m, p;
+  MatArg T, Z, H, C;
+  double *Pss, *Gss;  // [nD, m, m], [nD, p, p]
+  int* info;          // [nD] or null
+  const double *gPss, *gGss;  // [U, ...]
+  double *gT, *gZ, *gH, *gC;  // [U, ...] accumulated
+};
+
+template <bool BWD, bool WARP>
+__global__ void kf_dare_kernel(const __grid_constant__ DareArgs D, int arena_doubles) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  CoopCtx x;
+  x.m_ = D.m;
+  x.p_ = D.p;
+  x.off = 0;
+  x.cap = arena_doubles;
+  x.overflow = false;
+  long long u;
+  const long long count = BWD ? D.U : D.nD;
+  if (WARP) {
+    const int warp = threadIdx.x >> 5;
+    x.lane_ = threadIdx.x & 31;
+    x.G_ = 32;
+    x.arena = kf_dyn_smem + (size_t)warp * arena_doubles;
+    u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (u >= count) return;
+  } else {
+    x.lane_ = threadIdx.x;
+    x.G_ = blockDim.x;
+    x.arena = kf_dyn_smem;
+    u = blockIdx.x;
+  }
+  x.red = x.bump(34);
+  if (BWD) {
+    const long long d = u / D.n_series;
+    dare_adjoint_unit(x, D.T.p + d * D.T.bs, D.Z.p + d * D.Z.bs, D.H.p + d * D.H.bs, D.Pss + d * D.m * D.m,
+                      D.Gss + d * D.p * D.p, D.gPss + u * D.m * D.m, D.gGss + u * D.p * D.p,
+                      D.gT ? D.gT + u * D.m * D.m : nullptr, D.gZ ? D.gZ + u * D.p * D.m : nullptr,
+                      D.gH ? D.gH + u * D.p * D.p : nullptr, D.gC ? D.gC + u * D.m * D.m : nullptr);
+  } else {
+    const int info = dare_unit(x, D.T.p + u * D.T.bs, D.Z.p + u * D.Z.bs, D.H.p + u * D.H.bs, D.C.p + u * D.C.bs,
+                               D.Pss + u * D.m * D.m, D.Gss + u * D.p * D.p);
+    if (D.info && x.lane_ == 0) D.info[u] = info;
+  }
+  if (x.overflow) __trap();
+}
+cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s);
 
 // launchers implemented in kf_thread_m*.cu / kf_coop.cu
 typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);

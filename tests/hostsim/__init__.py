@@ -22,7 +22,7 @@ MK = {"standard": 0, "single": 0, "cholesky": 0, "univariate": 1, "steady_state"
 
 def build(force=False):
     src = os.path.join(HERE, "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "pymc_statespace_b200", "csrc", f) for f in ("kf_core.cuh", "kf_ctx.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pymc_statespace_b200", "csrc", f) for f in ("kf_core.cuh", "kf_ctx.cuh", "kf_dare.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(
             ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -56,12 +56,15 @@ def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_d
     ts = np.array([m * m * tv(T), p * m * tv(Z), p * p * tv(H), m * m * (C.ndim == 3), m * tv(c), p * tv(d)],
                   dtype=np.int64)
     mk = MK[kind]
+    if kind == "cholesky" and p > 1 and strict and static_dims:
+        raise ValueError("MK_CHOLS has no thread-per-unit instantiation")
     if kind == "standard":
         ll_const, d_sign = (LOG_2PI if strict else p * LOG_2PI), 1.0
     elif kind == "single":
         ll_const, d_sign = LOG_2PI, (-1.0 if strict else 1.0)
     elif kind == "cholesky":
-        assert p == 1 or not strict
+        if p > 1 and strict:
+            mk = 3  # MK_CHOLS: the as-coded filter
         ll_const, d_sign = p * LOG_2PI, 1.0
     elif kind == "steady_state":
         ll_const, d_sign = (LOG_2PI if strict else p * LOG_2PI), (0.0 if strict else 1.0)

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "kf_ctx.cuh"
+#include "kf_dare.cuh"
 
 using namespace kfb;
 
@@ -22,6 +23,7 @@ static void run_kind(X& x, KfArgs& A, int do_bwd) {
   if (A.math_kind == MK_STD) run_both<MK_STD>(x, A, do_bwd);
   else if (A.math_kind == MK_UNIV) run_both<MK_UNIV>(x, A, do_bwd);
   else if (A.math_kind == MK_STEADY) run_both<MK_STEADY>(x, A, do_bwd);
+  else if (A.math_kind == MK_CHOLS) run_both<MK_CHOLS>(x, A, do_bwd);
 }
 
 extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const double* a0, const double* P0,
@@ -49,7 +51,7 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   if (static_dims) {
 #define KFB_CASE(MM, PP)                                   \
   if (m == MM && p == PP) {                                \
-    ThreadCtx<MM, PP> x{nullptr};                          \
+    ThreadCtx<MM, PP> x{nullptr, nullptr, 0, 1};                         \
     run_kind(x, A, do_bwd);                                \
     return 0;                                              \
   }
@@ -65,6 +67,7 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   x.off = 0;
   if (A.math_kind == MK_STD) forward_unit<MK_STD, true>(x, A, 0);
   else if (A.math_kind == MK_UNIV) forward_unit<MK_UNIV, true>(x, A, 0);
+  else if (A.math_kind == MK_CHOLS) forward_unit<MK_CHOLS, true>(x, A, 0);
   else forward_unit<MK_STEADY, true>(x, A, 0);
   const int fwd_used = x.off;
   if (fwd_used > coop_arena_doubles(m, p, false)) return 3;
@@ -72,8 +75,27 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
     x.off = 0;
     if (A.math_kind == MK_STD) backward_unit<MK_STD>(x, A, 0);
     else if (A.math_kind == MK_UNIV) backward_unit<MK_UNIV>(x, A, 0);
+    else if (A.math_kind == MK_CHOLS) backward_unit<MK_CHOLS>(x, A, 0);
     else backward_unit<MK_STEADY>(x, A, 0);
     if (x.off > coop_arena_doubles(m, p, true)) return 4;
   }
   return x.overflow ? 5 : 0;
+}
+
+extern "C" int hostsim_dare(int m, int p, const double* T, const double* Z, const double* H, const double* C, double* Pss,
+                            double* Gss, int do_bwd, const double* gPss, const double* gGss, double* gT, double* gZ,
+                            double* gH, double* gC) {
+  const int cap = dare_arena_doubles(m, p);
+  std::vector<double> arena((size_t)cap);
+  CoopCtx x;
+  x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false; x.off = 0;
+  x.red = x.bump(34);
+  int info = dare_unit(x, T, Z, H, C, Pss, Gss);
+  if (x.overflow) return 5;
+  if (do_bwd && info == 0) {
+    x.off = 34;
+    dare_adjoint_unit(x, T, Z, H, Pss, Gss, gPss, gGss, gT, gZ, gH, gC);
+    if (x.overflow) return 6;
+  }
+  return info;
 }

@@ -211,3 +211,35 @@ def test_lyapunov_forward_backward():
         assert rel_err(Ab[b].cpu().numpy(), At.grad.numpy()) < 1e-7
         assert rel_err(Rb[b].cpu().numpy(), Rt.grad.numpy()) < 1e-7
         assert rel_err(Qb[b].cpu().numpy(), Qt.grad.numpy()) < 1e-7
+
+
+@pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("dims", [(2, 1, 1), (4, 2, 2)], ids=lambda d: "m%dp%dr%d" % d)
+def test_steady_state_filter(dims, strict, force_coop):
+    # SteadyStateFilter: on-GPU DARE (Riccati + Newton-Hewer) + fixed-gain recursion + DARE adjoint
+    m, p, r = dims
+    rng = np.random.default_rng(40 + m)
+    args = random_system(rng, m, p, r, 30)
+    d = rng.normal(size=(p, 1))
+    check_against_oracle("steady_state", args, None, d, strict=strict, force_coop=force_coop, rtol=1e-8, grad_rtol=1e-7)
+
+
+def test_steady_state_nile_and_trend_seasonal():
+    from pymc_statespace_b200.models import trend_seasonal_spec
+
+    check_against_oracle("steady_state", nile_inputs(0), grad_rtol=1e-6)
+    mats = trend_seasonal_spec(29).matrices(np.array([0.1, 0.01, 0.05, 0.5]))
+    rng = np.random.default_rng(0)
+    y = rng.normal(size=(40, 1, 1))
+    args = (y, mats["a0"], mats["P0"], mats["T"], mats["Z"], mats["R"], mats["H"], mats["Q"])
+    check_against_oracle("steady_state", args, rtol=1e-8, grad_rtol=1e-6)
+
+
+@pytest.mark.parametrize("dims", [(4, 2, 2), (6, 3, 3)], ids=lambda d: "m%dp%dr%d" % d)
+def test_as_coded_cholesky_filter_multivariate(dims):
+    # CholeskyFilter as coded (second triangular solve reads only diag(L)) for k_endog > 1
+    m, p, r = dims
+    rng = np.random.default_rng(60 + m)
+    args = random_system(rng, m, p, r, 30, n_missing=3)
+    check_against_oracle("cholesky", args, rng.normal(size=(m, 1)), rng.normal(size=(p, 1)), strict=True)

@@ -64,3 +64,54 @@ def test_deferred_log_matches_per_step_log():
     ref = kn.kalman_filter("standard", *args)[4]
     outs, _, _ = hostsim.run("standard", *args, static_dims=True, full=False, do_bwd=False)
     assert abs(outs[4] - ref) < 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("dims", [(4, 2, 2), (6, 3, 3), (3, 3, 1)])
+def test_as_coded_cholesky_filter_multivariate(dims):
+    # bug-compatible CholeskyFilter for k_endog > 1 (cooperative kernels only)
+    m, p, r = dims
+    rng = np.random.default_rng(m + p)
+    args = random_system(rng, m, p, r, 25, n_missing=2)
+    _check("cholesky", args, rng.normal(size=(m, 1)), rng.normal(size=(p, 1)), True, False, tol=1e-8)
+
+
+def test_dare_solver_and_adjoint_on_host():
+    import ctypes
+
+    import scipy.linalg
+    import torch
+
+    from pymc_statespace_b200.models import arma_spec, trend_seasonal_spec
+
+    lib = hostsim.build()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+    def run(T, Z, H, C, grad_tol):
+        m, p = T.shape[0], Z.shape[0]
+        T, Z, H, C = [np.ascontiguousarray(v, dtype=float) for v in (T, Z, H, C)]
+        Pss, Gss = np.zeros((m, m)), np.zeros((p, p))
+        gP, gG = np.random.default_rng(0).normal(size=(m, m)), np.random.default_rng(1).normal(size=(p, p))
+        gT, gZ, gH, gC = np.zeros((m, m)), np.zeros((p, m)), np.zeros((p, p)), np.zeros((m, m))
+        rc = lib.hostsim_dare(m, p, vp(T), vp(Z), vp(H), vp(C), vp(Pss), vp(Gss), 1, vp(gP), vp(gG), vp(gT), vp(gZ),
+                              vp(gH), vp(gC))
+        assert rc == 0
+        ref = scipy.linalg.solve_discrete_are(T.T, Z.T, C, H)
+        assert rel_err(Pss, ref) < 1e-12
+        ts = [torch.tensor(v, requires_grad=True) for v in (T, Z, H, C)]
+        X = kt.solve_discrete_are(ts[0].T, ts[1].T, ts[3], ts[2])
+        G = torch.linalg.inv(ts[1] @ X @ ts[1].T + ts[2])
+        ((X * torch.tensor(gP)).sum() + (G * torch.tensor(gG)).sum()).backward()
+        if grad_tol:
+            for a, b in zip((gT, gZ, gH, gC), ts):
+                assert rel_err(a, b.grad.numpy()) < grad_tol
+
+    rng = np.random.default_rng(3)
+    m, p, r = 4, 2, 2
+    T, Z, R = rng.normal(size=(m, m)) * 0.4, rng.normal(size=(p, m)), rng.normal(size=(m, r))
+    A = rng.normal(size=(p, p))
+    run(T, Z, A @ A.T + 0.1 * np.eye(p), R @ R.T, 1e-10)
+    mats = arma_spec((1, 1)).matrices(np.array([0, 0, 1.3, 0.7, 0.4]))  # H = 0: exact observation
+    run(mats["T"], mats["Z"], mats["H"], mats["R"] @ mats["Q"] @ mats["R"].T, None)
+    mats = trend_seasonal_spec(29).matrices(np.array([0.1, 0.01, 0.05, 0.5]))  # k_states = 30, unit roots
+    run(mats["T"], mats["Z"], mats["H"], mats["R"] @ mats["Q"] @ mats["R"].T, 1e-9)
+    run(np.array([[1.0, 1.0], [0.0, 1.0]]), np.array([[1.0, 0.0]]), np.array([[0.8]]), np.diag([0.5, 0.01]), 1e-10)
