@@ -155,3 +155,31 @@ def test_gather_world_size_2_gloo(tmp_path):
          "--master-port", "29517", str(script), ROOT],
         capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0 and "GLOO_OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_filter_factory_surface_matches_reference():
+    # reference core/statespace.py:25-31,66-74 and tests/test_statespace.py:66-76
+    from pymc_statespace_b200 import filters as F
+
+    assert list(F.FILTER_FACTORY) == ["standard", "univariate", "steady_state", "single", "cholesky"]
+    with pytest.raises(NotImplementedError, match="The following are valid filter types: standard, univariate, "
+                                                  "steady_state, single, cholesky"):
+        F.get_filter("kalman")
+    with pytest.raises(ValueError, match='Cannot use filter_type = "single" with multiple observed time series'):
+        F.get_filter("single", k_endog=2)
+    f = F.get_filter("STANDARD")
+    assert isinstance(f, F.StandardFilter) and f.mode is None and f.seq_names == [] and f.non_seq_names == []
+    with pytest.raises(NotImplementedError):
+        F.BaseFilter().update(*[None] * 8)
+    with pytest.raises(ValueError, match="it should either 2"):
+        F.split_vars_into_seq_and_nonseq([np.zeros(3)], ["T"])
+    seqs, non, sn, nn = F.split_vars_into_seq_and_nonseq([np.zeros((2, 2)), np.zeros((5, 2, 2))], ["T", "Q"])
+    assert sn == ["Q"] and nn == ["T"]
+
+
+def test_pytensor_adapter_is_import_guarded():
+    from pymc_statespace_b200 import pytensor_op
+
+    if not pytensor_op.HAVE_PYTENSOR:
+        with pytest.raises(ImportError, match="pytensor is not installed"):
+            pytensor_op.build_symbolic_graph(None, *[None] * 8)
