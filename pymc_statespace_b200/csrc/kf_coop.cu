@@ -6,13 +6,16 @@ namespace kfb {
 template <int MK, bool WARP>
 static cudaError_t launch_coop_kind(const KfArgs& A, bool bwd, int arena, int block, unsigned grid, size_t smem,
                                     cudaStream_t s) {
-  if (bwd) {
-    cudaFuncSetAttribute(kf_coop_kernel<MK, true, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kf_coop_kernel<MK, true, WARP><<<grid, block, smem, s>>>(A, arena);
-  } else {
-    cudaFuncSetAttribute(kf_coop_kernel<MK, false, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kf_coop_kernel<MK, false, WARP><<<grid, block, smem, s>>>(A, arena);
-  }
+  const bool full = A.ll_obs || A.fs || A.ps || A.fc || A.pc;
+#define KFB_LAUNCH(MODE)                                                                                          \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(kf_coop_kernel<MK, MODE, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kf_coop_kernel<MK, MODE, WARP><<<grid, block, smem, s>>>(A, arena);                                           \
+  } while (0)
+  if (bwd) KFB_LAUNCH(2);
+  else if (full) KFB_LAUNCH(1);
+  else KFB_LAUNCH(0);
+#undef KFB_LAUNCH
   count_launch();
   return cudaGetLastError();
 }

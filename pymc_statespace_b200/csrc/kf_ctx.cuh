@@ -184,11 +184,19 @@ struct CoopCtx {
 
 // doubles of arena one unit needs (upper bound of what forward_unit / backward_unit bump-allocate)
 inline int coop_arena_doubles(int m, int p, bool backward) {
-  const int mm = m * m, mp = m * p, pp = p * p;
+  const int mm = m * m, mp = m * p, pp = p * p, kt = m + (m * (m + 1)) / 2;
   const int params = mm + mp + pp + p + pp;
-  const int upd = 3 * p + 3 * mp + 4 * pp + 3 * mm;
-  if (!backward) return params + 3 * mm + 5 * m + upd;
-  return params + 8 * mm + 8 * m + 4 * mp + 4 * pp + 2 * p + upd + m + (m * (m + 1)) / 2;
+  const int upd = 3 * p + 3 * mp + 4 * pp + 3 * mm;    // UpdTmp  (kf_core.cuh)
+  const int prd = 3 * p + 4 * mp + 4 * pp + 3 * mm;    // PredTmp (kf_pred.cuh)
+  int a, b;
+  if (!backward) {
+    a = params + 3 * mm + 5 * m + upd;                 // forward_unit
+    b = params + 2 * mm + 3 * m + prd;                 // forward_unit_pred
+  } else {
+    a = params + 8 * mm + 8 * m + 4 * mp + 4 * pp + 2 * p + upd + kt;  // backward_unit
+    b = params + 7 * mm + 4 * m + 5 * mp + 4 * pp + 2 * p + prd + kt;  // backward_unit_pred
+  }
+  return a > b ? a : b;
 }
 
 }  // namespace kfb

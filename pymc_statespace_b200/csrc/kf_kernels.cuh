@@ -4,6 +4,7 @@
 
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
+#include "kf_pred.cuh"
 
 namespace kfb {
 
@@ -46,7 +47,21 @@ __device__ __forceinline__ void stage_y(double* ysm, const double* ysrc, int cou
   __syncthreads();
 }
 
-// MODE: 0 = forward, loglik (+tape) only; 1 = forward with per-step outputs; 2 = adjoint
+// MODE: 0 = forward, loglik (+tape) only; 1 = forward with per-step outputs; 2 = adjoint.
+// The hot path (MODE 0 / 2 of the standard-family and steady-state filters) runs in one-step-predictor form.
+template <int MK, int MODE, class X>
+__device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
+  constexpr bool PRED = (MK == MK_STD || MK == MK_STEADY);
+  if (MODE == 2) {
+    if (PRED) backward_unit_pred<MK>(x, A, u);
+    else backward_unit<MK>(x, A, u);
+  } else if (MODE == 0 && PRED) {
+    forward_unit_pred<MK>(x, A, u);
+  } else {
+    forward_unit<MK, MODE == 1>(x, A, u);
+  }
+}
+
 template <int M, int P, int MK, int MODE>
 __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     kf_thread_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
@@ -61,11 +76,10 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
   // the adjoint kernel's tape ring lives behind the staged observations (16-byte aligned)
   double* ring = kf_dyn_smem + ((y_smem_doubles + 1) & ~1);
   ThreadCtx<M, P> x{ysm, ring, (int)threadIdx.x, (int)blockDim.x};
-  if (MODE == 2) backward_unit<MK>(x, A, u);
-  else forward_unit<MK, MODE == 1>(x, A, u);
+  run_unit<MK, MODE>(x, A, u);
 }
 
-template <int MK, bool BWD, bool WARP>
+template <int MK, int MODE, bool WARP>
 __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   CoopCtx x;
@@ -89,8 +103,7 @@ __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubl
     x.arena = kf_dyn_smem;
     u = blockIdx.x;
   }
-  if (BWD) backward_unit<MK>(x, A, u);
-  else forward_unit<MK, true>(x, A, u);
+  run_unit<MK, MODE>(x, A, u);
   if (x.overflow) __trap();
 }
 

@@ -8,14 +8,22 @@
 
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
+#include "kf_pred.cuh"
 
 using namespace kfb;
 
+static int g_pred = 0;  // 1: run the one-step-predictor programs (kf_pred.cuh) where they exist
+
 template <int MK, class X>
 static void run_both(X& x, KfArgs& A, int do_bwd) {
+  constexpr bool PRED = (MK == MK_STD || MK == MK_STEADY);
   if (A.ll_obs || A.fs) forward_unit<MK, true>(x, A, 0);
+  else if (g_pred && PRED) forward_unit_pred<MK == MK_STEADY ? MK_STEADY : MK_STD>(x, A, 0);
   else forward_unit<MK, false>(x, A, 0);
-  if (do_bwd) backward_unit<MK>(x, A, 0);
+  if (do_bwd) {
+    if (g_pred && PRED) backward_unit_pred<MK == MK_STEADY ? MK_STEADY : MK_STD>(x, A, 0);
+    else backward_unit<MK>(x, A, 0);
+  }
 }
 
 template <class X>
@@ -48,6 +56,8 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   A.ga0 = ga0; A.gP0 = gP0; A.gT = gT; A.gZ = gZ; A.gH = gH; A.gC = gC; A.gc = gc; A.gd = gd;
   A.gPss = gPss; A.gGss = gGss;
 
+  g_pred = (static_dims >> 1) & 1;
+  static_dims &= 1;
   if (static_dims) {
 #define KFB_CASE(MM, PP)                                   \
   if (m == MM && p == PP) {                                \
@@ -65,18 +75,19 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   CoopCtx x;
   x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false;
   x.off = 0;
-  if (A.math_kind == MK_STD) forward_unit<MK_STD, true>(x, A, 0);
-  else if (A.math_kind == MK_UNIV) forward_unit<MK_UNIV, true>(x, A, 0);
-  else if (A.math_kind == MK_CHOLS) forward_unit<MK_CHOLS, true>(x, A, 0);
-  else forward_unit<MK_STEADY, true>(x, A, 0);
+  run_kind(x, A, 0);
   const int fwd_used = x.off;
   if (fwd_used > coop_arena_doubles(m, p, false)) return 3;
   if (do_bwd) {
+    // run forward again (tape) + backward from a fresh arena
     x.off = 0;
-    if (A.math_kind == MK_STD) backward_unit<MK_STD>(x, A, 0);
-    else if (A.math_kind == MK_UNIV) backward_unit<MK_UNIV>(x, A, 0);
-    else if (A.math_kind == MK_CHOLS) backward_unit<MK_CHOLS>(x, A, 0);
-    else backward_unit<MK_STEADY>(x, A, 0);
+    std::vector<double> arena2((size_t)cap);
+    KfArgs B = A;
+    B.loglik = nullptr; B.ll_obs = nullptr; B.fs = B.ps = B.fc = B.pc = nullptr; B.info = nullptr;
+    if (A.math_kind == MK_STD) { if (g_pred) backward_unit_pred<MK_STD>(x, B, 0); else backward_unit<MK_STD>(x, B, 0); }
+    else if (A.math_kind == MK_UNIV) backward_unit<MK_UNIV>(x, B, 0);
+    else if (A.math_kind == MK_CHOLS) backward_unit<MK_CHOLS>(x, B, 0);
+    else { if (g_pred) backward_unit_pred<MK_STEADY>(x, B, 0); else backward_unit<MK_STEADY>(x, B, 0); }
     if (x.off > coop_arena_doubles(m, p, true)) return 4;
   }
   return x.overflow ? 5 : 0;

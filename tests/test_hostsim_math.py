@@ -115,3 +115,45 @@ def test_dare_solver_and_adjoint_on_host():
     mats = trend_seasonal_spec(29).matrices(np.array([0.1, 0.01, 0.05, 0.5]))  # k_states = 30, unit roots
     run(mats["T"], mats["Z"], mats["H"], mats["R"] @ mats["Q"] @ mats["R"].T, 1e-9)
     run(np.array([[1.0, 1.0], [0.0, 1.0]]), np.array([[1.0, 0.0]]), np.array([[0.8]]), np.diag([0.5, 0.01]), 1e-10)
+
+
+@pytest.mark.parametrize("static", [True, False], ids=["ThreadCtx", "CoopCtx"])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (3, 2, 2), (4, 3, 2)])
+def test_predictor_form_hot_path(dims, static):
+    """kf_pred.cuh: loglik-only forward + adjoint in one-step-predictor form (what the GPU hot path runs)."""
+    m, p, r = dims
+    rng = np.random.default_rng(m * 13 + p)
+    args = random_system(rng, m, p, r, 25, n_missing=2)
+    c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+    for kind, strict, w in (("standard", True, None), ("standard", False, rng.normal(size=25))) + (
+            (("single", True, None), ("cholesky", True, None)) if p == 1 else ()):
+        ref = kn.kalman_filter(kind, *args, c=c, d=d, strict_reference=strict)
+        outs, g, info = hostsim.run(kind, *args, c=c, d=d, strict=strict, static_dims=static, full=False, pred=True,
+                                    g_ll_obs=w, g_loglik=(0.0 if w is not None else None))
+        assert info == 0 and abs(outs[4] - ref[4]) < 1e-12 * abs(ref[4])
+        _, gt = kt.loglik_and_grads(kind, *args, c=c, d=d, strict_reference=strict, g_ll_obs=w)
+        for k in gt:
+            assert rel_err(g[k], gt[k]) < 1e-9 or np.abs(g[k] - gt[k]).max() < 1e-13, (kind, k)
+
+
+def test_predictor_form_steady_state_and_time_varying():
+    rng = np.random.default_rng(77)
+    args = random_system(rng, 4, 2, 2, 30)
+    for static in (True, False):
+        ref = kn.kalman_filter("steady_state", *args)
+        outs, g, _ = hostsim.run("steady_state", *args, static_dims=static, full=False, pred=True)
+        assert abs(outs[4] - ref[4]) < 1e-11 * abs(ref[4])
+        _, gt = kt.loglik_and_grads("steady_state", *args)
+        for k in gt:
+            assert rel_err(g[k], gt[k]) < 1e-8 or np.abs(g[k] - gt[k]).max() < 1e-13, k
+    n, m, p, r = 12, 3, 2, 2
+    S = [random_system(rng, m, p, r, n) for _ in range(n)]
+    y, a0, P0 = S[0][:3]
+    T, Z, R, H, Q = (np.stack([s[i] for s in S]) for i in range(3, 8))
+    c, d = rng.normal(size=(n, m, 1)), rng.normal(size=(n, p, 1))
+    ref = kn.kalman_filter("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d)
+    outs, g, _ = hostsim.run("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d, full=False, pred=True)
+    assert abs(outs[4] - ref[4]) < 1e-12 * abs(ref[4])
+    _, gt = kt.loglik_and_grads("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d)
+    for k in gt:
+        assert rel_err(g[k], gt[k]) < 1e-9, k
