@@ -247,6 +247,13 @@ def main():
             pass
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp64_peak = fp64_peak_tflops(dev)
+        traffic = {}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this exact workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if B == 65536 and n == 1000:
+                traffic = {k: tj[k]["dram_bytes_read"] + tj[k]["dram_bytes_write"] for k in ("adjoint", "forward")}
+        except Exception:
+            pass
         tape_bytes = B * (n - 1) * TAPE_BYTES_PER_STEP
         bwd_gbs = tape_bytes / (ms_bwd * 1e-3) / 1e9
         fwd_gbs = tape_bytes / (ms_fwd * 1e-3) / 1e9
@@ -264,12 +271,16 @@ def main():
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 * world), "d2h_bytes_per_step": int(out_h.numel() * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,STD,BWD> (adjoint recursion)",
+            "roofline": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,MK_STD,2> (adjoint recursion; the longest kernel)",
                          "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bwd_gbs / hbm_peak,
-                         "peak_source": peak_src, "traffic": None, "ms_per_launch": ms_bwd,
-                         "algorithmic_bytes_per_launch": tape_bytes},
-            "roofline_forward": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,STD,FWD>", "achieved": fwd_gbs,
-                                 "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak, "ms_per_launch": ms_fwd},
+                         "peak_source": peak_src, "traffic": traffic.get("adjoint"), "ms_per_launch": ms_bwd,
+                         "algorithmic_bytes_per_launch": tape_bytes,
+                         "note": "algorithmic bytes = 40 B/step tape read; ms_per_launch includes the ~8 us R Q R^T adjoint "
+                                 "helper launched with it; this kernel is fp64-latency bound, see the fp64 block"},
+            "roofline_forward": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,MK_STD,0> (forward: loglik + tape)",
+                                 "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak,
+                                 "traffic": traffic.get("forward"), "ms_per_launch": ms_fwd,
+                                 "algorithmic_bytes_per_launch": tape_bytes},
             "fp64": {"peak_tflops_measured": fp64_peak, "achieved_tflops": ALG_FLOPS_PER_STEP * steps_per_eval /
                      ((ms_fwd + ms_bwd) * 1e-3) / 1e12,
                      "frac": ALG_FLOPS_PER_STEP * steps_per_eval / ((ms_fwd + ms_bwd) * 1e-3) / 1e12 / fp64_peak,
