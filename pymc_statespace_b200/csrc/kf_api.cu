@@ -17,6 +17,21 @@ thread_launch_fn thread_launcher_m2(int p, int mk);
 thread_launch_fn thread_launcher_m3(int p, int mk);
 thread_launch_fn thread_launcher_m4(int p, int mk);
 
+coopT_launch_fn coopT_launcher_m5(int p, int mk);
+coopT_launch_fn coopT_launcher_m6(int p, int mk);
+coopT_launch_fn coopT_launcher_m7(int p, int mk);
+coopT_launch_fn coopT_launcher_m8(int p, int mk);
+
+coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
+  switch (m) {
+    case 5: return coopT_launcher_m5(p, mk);
+    case 6: return coopT_launcher_m6(p, mk);
+    case 7: return coopT_launcher_m7(p, mk);
+    case 8: return coopT_launcher_m8(p, mk);
+    default: return nullptr;
+  }
+}
+
 thread_launch_fn find_thread_launcher(int m, int p, int mk) {
   switch (m) {
     case 1: return thread_launcher_m1(p, mk);
@@ -127,7 +142,12 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
     }
     e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
   } else {
-    e = launch_coop(A, bwd, s);
+    // sub-warp kernels with compile-time dims need uniform control flow across the units of a warp:
+    // static matrices and ONE observation stream shared by every unit
+    coopT_launch_fn ft = nullptr;
+    if (!pl.tv_any && !(d->flags & KFB_FLAG_FORCE_COOP) && d->y_bs == 0 && d->n_series == 1)
+      ft = find_coopT_launcher(d->m, d->p, pl.mk);
+    e = ft ? ft(A, bwd, s) : launch_coop(A, bwd, s);
     if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
   }
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);

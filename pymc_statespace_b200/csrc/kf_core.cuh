@@ -416,8 +416,10 @@ KFB_HD bool univariate_inner(X& x, const Params<X>& prm, const double* yt, doubl
   for (int k = 0; k < m; ++k) F = kf_fma(prm.Z[i * m + k], Mv[k], F);
   *vo = v;
   *Fo = F;
-  if (F == 0.0) return false;
-  const double rF = 1.0 / F;
+  // F == 0 is "treated as missing" (:468-471).  Predicated, not branched: with K = 0 every update below is the
+  // identity, and control flow stays uniform across units that share a warp (sub-warp cooperative mode).
+  const bool live = (F != 0.0);
+  const double rF = live ? 1.0 / F : 0.0;
   KFB_FOR(r, m) Kv[r] = Mv[r] * rF;
   x.sync();
   KFB_FOR(idx, m * m) {
@@ -426,7 +428,7 @@ KFB_HD bool univariate_inner(X& x, const Params<X>& prm, const double* yt, doubl
   }
   KFB_FOR(r, m) a[r] = kf_fma(Kv[r], v, a[r]);
   x.sync();
-  return true;
+  return live;
 }
 
 template <class X>
@@ -698,8 +700,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         F = prm.H[i * p + i];
 #pragma unroll
         for (int k = 0; k < m; ++k) F = kf_fma(prm.Z[i * m + k], Mv[k], F);
-        if (F == 0.0) continue;
-        const double rF = 1.0 / F;
+        const double rF = (F != 0.0) ? 1.0 / F : 0.0;  // F == 0: K = 0 and every contribution below vanishes
         KFB_FOR(r, m) Kv[r] = Mv[r] * rF;
         x.sync();
         const double lq = -0.5 * lb;  // cotangent of ll_inner_i

@@ -182,6 +182,113 @@ struct CoopCtx {
   };
 };
 
+// ---------------------------------------------------------------------------
+// CoopCtxT<M,P,G>: G lanes (a power of two <= 32) cooperate on one unit, 32/G units per warp; COMPILE-TIME dims so
+// every loop unrolls and all index arithmetic folds; matrices in shared memory.  Products whose row count fits the
+// group run "row per lane": lane i keeps one output row in registers, reads A[i][k] once and the (broadcast) row
+// B[k][:] - 1/c instead of 2 shared-memory loads per multiply-add (see the gemm overload below).
+// Control flow must be uniform across the units of a warp: the launcher only uses this context when the observation
+// stream is shared by all units (same missing pattern) and the matrices are static.
+// ---------------------------------------------------------------------------
+template <int M, int P, int G_>
+struct CoopCtxT {
+  static constexpr bool TV = false;
+  static constexpr int KT = M + (M * (M + 1)) / 2;
+  int lane_;
+  unsigned mask_;
+  double* arena;
+  int off;
+  template <int SZ>
+  KFB_HD static constexpr int size_of() {
+    return SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : KT;
+  }
+  template <int SZ>
+  struct Buf {
+    double* v;
+    KFB_HD explicit Buf(CoopCtxT& x) : v(x.arena + x.off) { x.off += (size_of<SZ>() + 1) & ~1; }
+    KFB_HD double& operator[](int i) { return v[i]; }
+    KFB_HD const double& operator[](int i) const { return v[i]; }
+  };
+  KFB_HD static constexpr int m() { return M; }
+  KFB_HD static constexpr int p() { return P; }
+  KFB_HD static constexpr int G() { return G_; }
+  KFB_HD int lane() const { return lane_; }
+  KFB_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+    __syncwarp(mask_);
+#endif
+  }
+  KFB_HD double reduce_max(double v) const {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask_, v, o, G_));
+#endif
+    return v;
+  }
+  KFB_HD bool all_ok(bool v) const {
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(mask_, (int)v, 0, G_) != 0;
+#else
+    return v;
+#endif
+  }
+  KFB_HD const double* y_base(const KfArgs& A, long long series) const { return A.y.p + series * A.y.bs; }
+  KFB_HD double* tape_base(const KfArgs& A, long long u) const { return A.tape + u * (long long)(A.n - 1) * KT; }
+  KFB_HD long long tape_step(const KfArgs&) const { return KT; }
+  KFB_HD long long tape_elem(const KfArgs&) const { return 1; }
+  struct TapeReader {
+    const double* gp;
+    KFB_HD TapeReader(CoopCtxT& x, const KfArgs& A, long long u) {
+      gp = x.tape_base(A, u) + (long long)(A.n - 2) * KT;
+    }
+    template <class TB>
+    KFB_HD void get(CoopCtxT& x, TB& dst) {
+#pragma unroll
+      for (int k = x.lane_; k < KT; k += G_) dst[k] = gp[k];
+      gp -= KT;
+      x.sync();
+    }
+  };
+};
+
+// Row-per-lane product for CoopCtxT (more specialised than the generic gemm in kf_core.cuh).
+template <bool TA, bool TB, int MODE, int M, int P, int G_, class TC, class TAa, class TBb>
+KFB_HD void gemm(CoopCtxT<M, P, G_>& x, TC& C, const TAa& A, const TBb& B, int r, int kk, int c) {
+  constexpr int CMAX = (M > P ? M : P);
+  if (r <= G_) {
+    const int i = x.lane();
+    if (i < r) {
+      double acc[CMAX];
+#pragma unroll
+      for (int j = 0; j < CMAX; ++j)
+        if (j < c) acc[j] = (MODE == 0) ? 0.0 : C[i * c + j];
+#pragma unroll
+      for (int k = 0; k < kk; ++k) {
+        double av = A[TA ? k * r + i : i * kk + k];
+        if (MODE == 2) av = -av;
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j)
+          if (j < c) acc[j] = kf_fma(av, B[TB ? j * kk + k : k * c + j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < CMAX; ++j)
+        if (j < c) C[i * c + j] = acc[j];
+    }
+  } else {
+    KFB_FOR(idx, r * c) {
+      const int i = idx / c, j = idx - i * c;
+      double s = (MODE == 0) ? 0.0 : C[idx];
+#pragma unroll
+      for (int k = 0; k < kk; ++k) {
+        const double av = A[TA ? k * r + i : i * kk + k];
+        s = kf_fma(MODE == 2 ? -av : av, B[TB ? j * kk + k : k * c + j], s);
+      }
+      C[idx] = s;
+    }
+  }
+  x.sync();
+}
+
 // doubles of arena one unit needs (upper bound of what forward_unit / backward_unit bump-allocate)
 inline int coop_arena_doubles(int m, int p, bool backward) {
   const int mm = m * m, mp = m * p, pp = p * p, kt = m + (m * (m + 1)) / 2;

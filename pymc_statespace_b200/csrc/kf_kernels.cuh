@@ -107,6 +107,21 @@ __global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubl
   if (x.overflow) __trap();
 }
 
+// Sub-warp cooperative kernel with compile-time dims: G lanes per unit, 128 threads per CTA.
+template <int M, int P, int G, int MK, int MODE>
+__global__ void __launch_bounds__(128) kf_coopT_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  const int group = threadIdx.x / G;
+  const long long u = (long long)blockIdx.x * (128 / G) + group;
+  if (u >= A.U) return;
+  CoopCtxT<M, P, G> x;
+  x.lane_ = threadIdx.x % G;
+  x.mask_ = __activemask();
+  x.arena = kf_dyn_smem + (size_t)group * arena_doubles;
+  x.off = 0;
+  run_unit<MK, MODE>(x, A, u);
+}
+
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----
 struct DareArgs {
   long long nD, U, n_series;
@@ -162,6 +177,8 @@ cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s);
 typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);
 thread_launch_fn find_thread_launcher(int m, int p, int mk);
 cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s);
+typedef cudaError_t (*coopT_launch_fn)(const KfArgs& A, bool bwd, cudaStream_t s);
+coopT_launch_fn find_coopT_launcher(int m, int p, int mk);
 void count_launch();
 
 }  // namespace kfb

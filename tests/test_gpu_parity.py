@@ -243,3 +243,40 @@ def test_as_coded_cholesky_filter_multivariate(dims):
     rng = np.random.default_rng(60 + m)
     args = random_system(rng, m, p, r, 30, n_missing=3)
     check_against_oracle("cholesky", args, rng.normal(size=(m, 1)), rng.normal(size=(p, 1)), strict=True)
+
+
+@pytest.mark.parametrize("dims", [(5, 1, 2), (6, 3, 3), (7, 2, 3), (8, 3, 2)], ids=lambda d: "m%dp%dr%d" % d)
+@pytest.mark.parametrize("kind", ["standard", "univariate", "steady_state"])
+def test_subwarp_static_kernels(kind, dims):
+    """CoopCtxT<M,P,8>: 8 lanes per unit, 4 units per warp, compile-time dims (k_states 5..8)."""
+    m, p, r = dims
+    rng = np.random.default_rng(90 + 10 * m + p)
+    miss = 0 if kind == "steady_state" else 3
+    args = random_system(rng, m, p, r, 30, n_missing=miss, scale_T=0.25)
+    c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+    check_against_oracle(kind, args, c, d, grad_rtol=1e-7 if kind == "steady_state" else RTOL)
+    # and the generic cooperative kernels give the same numbers
+    check_against_oracle(kind, args, c, d, force_coop=True, grad_rtol=1e-7 if kind == "steady_state" else RTOL)
+
+
+def test_subwarp_kernels_many_units_not_multiple_of_group():
+    # 37 units: the last warp holds a partial set of 8-lane groups (active-mask sync)
+    from pymc_statespace_b200 import BatchedKalman
+
+    rng = np.random.default_rng(5)
+    B, n, m, p, r = 37, 25, 6, 3, 3
+    systems = [random_system(rng, m, p, r, n, scale_T=0.25) for _ in range(B)]
+    y = random_system(rng, m, p, r, n, n_missing=3)[0]
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    for kind in ("standard", "univariate"):
+        bk = BatchedKalman(kind, n, m, p, r, n_draws=B)
+        out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                         outputs=("loglik",), save_for_backward=True)
+        g = bk.backward()
+        ll = out["loglik"].cpu().numpy()
+        for b in (0, 31, 32, 36):
+            args = (y,) + tuple(systems[b][1:])
+            ref, gref = kt.loglik_and_grads(kind, *args)
+            assert abs(ll[b] - ref) < RTOL * abs(ref)
+            assert rel_err(g["T"][b].cpu().numpy(), gref["T"]) < RTOL
+            assert rel_err(g["Q"][b].cpu().numpy(), gref["Q"]) < RTOL
