@@ -32,14 +32,15 @@ static cudaError_t launch_coop_mode(const KfArgs& A, bool bwd, int arena, int bl
   }
 }
 
-// Warp-per-unit while >= 4 arenas fit in one SM's shared memory; otherwise one CTA (256 threads) per unit.
+// Warp-per-unit for small systems (a 32-lane warp covers the m*m outputs of a product in a few rounds and 4+ arenas
+// fit in one SM's shared memory); one 256-thread CTA per unit from k_states = 16 up (>= 256 outputs per product).
 cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s) {
   int arena = coop_arena_doubles(A.m, A.p, bwd);
   arena = (arena + 1) & ~1;  // keep every arena 16-byte aligned
   const size_t arena_bytes = (size_t)arena * sizeof(double);
   const size_t smem_max = 227 * 1024;
   if (arena_bytes > smem_max) return cudaErrorInvalidConfiguration;
-  if (arena_bytes * 4 <= smem_max) {
+  if (arena_bytes * 4 <= smem_max && A.m < 16) {
     int warps = 4;
     // more warps per CTA only helps when the arena is tiny; keep CTAs small so many are resident
     const int block = warps * 32;

@@ -301,7 +301,7 @@ KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, do
   }
   gemm<false, true, 0>(x, u.Mm, P, prm.Z, m, m, p);  // Mm = P Z^T
   KFB_FOR(idx, p * p) {
-    const int i = idx / p, j = idx - i * p;
+    const int i = x.div_p(idx), j = idx - i * p;
     double s = prm.H[idx];
 #pragma unroll
     for (int k = 0; k < m; ++k) s = kf_fma(prm.Z[i * m + k], u.Mm[k * p + j], s);
@@ -347,7 +347,7 @@ KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, do
     }
   }
   KFB_FOR(idx, m * m) {  // A = I - K Z
-    const int i = idx / m, j = idx - i * m;
+    const int i = x.div_m(idx), j = idx - i * m;
     double s = (i == j) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < p; ++k) s = kf_fma(-u.K[i * p + k], prm.Z[k * m + j], s);
@@ -387,7 +387,7 @@ KFB_HD void predict(X& x, const TT& T, const TC& C, const Tc& c, const TA& af, c
   x.sync();
   gemm<false, true, 1>(x, S2, S1, T, m, m, m);
   KFB_FOR(idx, m * m) {
-    const int i = idx / m, j = idx - i * m;
+    const int i = x.div_m(idx), j = idx - i * m;
     P[idx] = 0.5 * (S2[idx] + S2[j * m + i]);
   }
   x.sync();
@@ -423,7 +423,7 @@ KFB_HD bool univariate_inner(X& x, const Params<X>& prm, const double* yt, doubl
   KFB_FOR(r, m) Kv[r] = Mv[r] * rF;
   x.sync();
   KFB_FOR(idx, m * m) {
-    const int r = idx / m, c = idx - r * m;
+    const int r = x.div_m(idx), c = idx - r * m;
     P[idx] = kf_fma(-Kv[r] * Kv[c], F, P[idx]);  // P - K K^T F  (:477, not Joseph)
   }
   KFB_FOR(r, m) a[r] = kf_fma(Kv[r], v, a[r]);
@@ -548,7 +548,7 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
     if (tp && t + 1 < n) {
       KFB_FOR(k, m) tp[k * telem] = a[k];
       KFB_FOR(idx, m * m) {
-        const int i = idx / m, j = idx - i * m;
+        const int i = x.div_m(idx), j = idx - i * m;
         if (j >= i) tp[(m + i * m - (i * (i - 1)) / 2 + (j - i)) * telem] = P[idx];
       }
       tp += tstep;
@@ -618,7 +618,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       rd.get(x, nxt);  // entry of step t
       KFB_FOR(k, m) a[k] = nxt[k];
       KFB_FOR(idx, m * m) {
-        int i = idx / m, j = idx - i * m;
+        int i = x.div_m(idx), j = idx - i * m;
         if (j < i) { const int s = i; i = j; j = s; }
         P[idx] = nxt[m + i * m - (i * (i - 1)) / 2 + (j - i)];
       }
@@ -649,7 +649,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
 
     // ---- adjoint of predict: a' = T af + c ; P' = sym(T Pf T^T + C)
     KFB_FOR(idx, m * m) {  // S3 = Ps = sym(Pb) ; S4 = Pf + Pf^T
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       S3[idx] = 0.5 * (Pb[idx] + Pb[j * m + i]);
       S4[idx] = Pf[idx] + Pf[j * m + i];
     }
@@ -659,7 +659,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
     gemm<false, false, 0>(x, tmp.S1, S3, prm.T, m, m, m);    // W = Ps T        (shared by Tb and Pfb)
     gemm<false, false, 1>(x, Tb, tmp.S1, S4, m, m, m);       // Tb += Ps T (Pf + Pf^T)
     KFB_FOR(idx, m * m) {
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       Tb[idx] = kf_fma(ab[i], af[j], Tb[idx]);               // + ab af^T
     }
     KFB_FOR(i, m) {                                          // afb = T^T ab
@@ -738,7 +738,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
           Zb[i * m + r] += s;
         }
         KFB_FOR(idx, m * m) {
-          const int r = idx / m, c2 = idx - r * m;
+          const int r = x.div_m(idx), c2 = idx - r * m;
           Pfb[idx] = kf_fma(Mvb[r], prm.Z[i * m + c2], Pfb[idx]);
         }
         KFB_FOR(r, m) afb[r] = kf_fma(-prm.Z[i * m + r], vbar, afb[r]);
@@ -754,7 +754,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
     } else {
       // ---- adjoint of the Joseph update
       KFB_FOR(idx, m * m) {
-        const int i = idx / m, j = idx - i * m;
+        const int i = x.div_m(idx), j = idx - i * m;
         S4[idx] = P[idx] + P[j * m + i];
       }
       x.sync();
@@ -762,13 +762,13 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       gemm<false, false, 0>(x, S3, tmp.S1, S4, m, m, m);      // Ab = Pfb A (P + P^T)      (S3 = Ab)
       gemm<true, false, 0>(x, Pb, tmp.A, tmp.S1, m, m, m);    // Pb = A^T Pfb A
       KFB_FOR(idx, p * p) {
-        const int i = idx / p, j = idx - i * p;
+        const int i = x.div_p(idx), j = idx - i * p;
         Q1[idx] = prm.H[idx] + prm.H[j * p + i];
       }
       gemm<false, false, 0>(x, PK, Pfb, tmp.K, m, m, p);      // Pfb K            (shared by Kb and Hb)
       gemm<false, false, 0>(x, Kb, PK, Q1, m, p, p);          // Kb = Pfb K (H + H^T)
       KFB_FOR(idx, m * p) {
-        const int i = idx / p, j = idx - i * p;
+        const int i = x.div_p(idx), j = idx - i * p;
         double s = kf_fma(afb[i], tmp.v[j], Kb[idx]);         // + afb v^T
 #pragma unroll
         for (int k = 0; k < m; ++k) s = kf_fma(-S3[i * m + k], prm.Z[j * m + k], s);  // - Ab Z^T
@@ -788,7 +788,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         }
         gemm<true, false, 1>(x, Gb, tmp.Mm, Kb, p, m, p);     // Gssb += Mm^T Kb
         KFB_FOR(idx, p * p) {
-          const int i = idx / p, j = idx - i * p;
+          const int i = x.div_p(idx), j = idx - i * p;
           Gb[idx] = kf_fma(-0.5 * lb * tmp.v[i], tmp.v[j], Gb[idx]);
           Fb[idx] = -0.5 * lb * tmp.Fi[j * p + i];
         }
@@ -804,7 +804,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         }
         gemm<true, false, 0>(x, Q1, tmp.Mm, Kb, p, m, p);     // Gk-bar = Mm^T Kb - 0.5 lb v v^T
         KFB_FOR(idx, p * p) {
-          const int i = idx / p, j = idx - i * p;
+          const int i = x.div_p(idx), j = idx - i * p;
           Q1[idx] = kf_fma(-0.5 * lb * tmp.v[i], tmp.v[j], Q1[idx]);
         }
         x.sync();
@@ -820,7 +820,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
         }
         gemm<true, false, 0>(x, Q1, tmp.K, Kb, p, m, p);      // K^T Kb
         KFB_FOR(idx, p * p) {
-          const int i = idx / p, j = idx - i * p;
+          const int i = x.div_p(idx), j = idx - i * p;
           double s = -0.5 * lb * (tmp.Fi[j * p + i] - tmp.w[i] * tmp.w[j]);
 #pragma unroll
           for (int k = 0; k < p; ++k) s = kf_fma(-Q1[i * p + k], tmp.Fi[j * p + k], s);  // - K^T Kb G^T
@@ -831,7 +831,7 @@ KFB_HD void backward_unit(X& x, const KfArgs& A, long long u) {
       }
       gemm<true, false, 1>(x, Mb, prm.Z, Fb, m, p, p);        // Mb += Z^T Fb
       KFB_FOR(idx, p * m) {                                   // Zb += Fb Mm^T + Mb^T P - vb a^T
-        const int i = idx / m, j = idx - i * m;
+        const int i = x.div_m(idx), j = idx - i * m;
         double s = kf_fma(-vb[i], a[j], Zb[idx]);
 #pragma unroll
         for (int k = 0; k < p; ++k) s = kf_fma(Fb[i * p + k], tmp.Mm[j * p + k], s);

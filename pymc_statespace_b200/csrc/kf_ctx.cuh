@@ -84,6 +84,8 @@ struct ThreadCtx {
   KFB_HD static constexpr int lane() { return 0; }
   KFB_HD static constexpr int G() { return 1; }
   KFB_HD void sync() const {}
+  KFB_HD static constexpr int div_m(int i) { return i / M; }
+  KFB_HD static constexpr int div_p(int i) { return i / P; }
   KFB_HD double reduce_max(double v) const { return v; }
   KFB_HD bool all_ok(bool v) const { return v; }
   KFB_HD const double* y_base(const KfArgs& A, long long series) const {
@@ -107,6 +109,20 @@ struct CoopCtx {
   int off, cap;
   bool overflow;
   double* red;  // 34 doubles of scratch for cross-lane reductions (CTA mode)
+  unsigned magic_m, magic_p;  // ceil(2^32 / m), ceil(2^32 / p): i / m == umulhi(i, magic) for 0 <= i < 65536
+
+  KFB_HD void set_dims(int m, int p) {
+    m_ = m;
+    p_ = p;
+    magic_m = (unsigned)((0x100000000ull + (unsigned)m - 1) / (unsigned)m);
+    magic_p = (unsigned)((0x100000000ull + (unsigned)p - 1) / (unsigned)p);
+  }
+  KFB_HD int div_m(int i) const {
+    return m_ == 1 ? i : (int)(((unsigned long long)(unsigned)i * magic_m) >> 32);
+  }
+  KFB_HD int div_p(int i) const {
+    return p_ == 1 ? i : (int)(((unsigned long long)(unsigned)i * magic_p) >> 32);
+  }
 
   KFB_HD int size_of(int sz) const {
     return sz == SZ_M ? m_ : sz == SZ_P ? p_ : sz == SZ_MM ? m_ * m_ : sz == SZ_MP ? m_ * p_ : sz == SZ_PP ? p_ * p_ : tape_width(m_);
@@ -182,6 +198,44 @@ struct CoopCtx {
   };
 };
 
+// 2x2 register-tiled product for the run-time-dims cooperative context: each lane owns a 2x2 block of C, so one
+// multiply-add costs one shared-memory load instead of two, and the index arithmetic is paid per tile, not per
+// element (k_states ~ 30: 225 tiles on a 256-thread CTA).
+template <bool TA, bool TB, int MODE, class TC, class TAa, class TBb>
+KFB_HD void gemm(CoopCtx& x, TC& C, const TAa& A, const TBb& B, int r, int kk, int c) {
+  const int tr = (r + 1) >> 1, tc = (c + 1) >> 1;
+  for (int tile = x.lane_; tile < tr * tc; tile += x.G_) {
+    const int ti = tile / tc, tj = tile - ti * tc;
+    const int i0 = 2 * ti, j0 = 2 * tj;
+    const bool i1 = (i0 + 1 < r), j1 = (j0 + 1 < c);
+    const int i1x = i1 ? i0 + 1 : i0, j1x = j1 ? j0 + 1 : j0;
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+    if (MODE != 0) {
+      s00 = C[i0 * c + j0];
+      s01 = C[i0 * c + j1x];
+      s10 = C[i1x * c + j0];
+      s11 = C[i1x * c + j1x];
+    }
+#pragma unroll 2
+    for (int k = 0; k < kk; ++k) {
+      double a0 = A[TA ? k * r + i0 : i0 * kk + k];
+      double a1 = A[TA ? k * r + i1x : i1x * kk + k];
+      if (MODE == 2) { a0 = -a0; a1 = -a1; }
+      const double b0 = B[TB ? j0 * kk + k : k * c + j0];
+      const double b1 = B[TB ? j1x * kk + k : k * c + j1x];
+      s00 = kf_fma(a0, b0, s00);
+      s01 = kf_fma(a0, b1, s01);
+      s10 = kf_fma(a1, b0, s10);
+      s11 = kf_fma(a1, b1, s11);
+    }
+    C[i0 * c + j0] = s00;
+    if (j1) C[i0 * c + j0 + 1] = s01;
+    if (i1) C[(i0 + 1) * c + j0] = s10;
+    if (i1 && j1) C[(i0 + 1) * c + j0 + 1] = s11;
+  }
+  x.sync();
+}
+
 // ---------------------------------------------------------------------------
 // CoopCtxT<M,P,G>: G lanes (a power of two <= 32) cooperate on one unit, 32/G units per warp; COMPILE-TIME dims so
 // every loop unrolls and all index arithmetic folds; matrices in shared memory.  Products whose row count fits the
@@ -212,6 +266,8 @@ struct CoopCtxT {
   KFB_HD static constexpr int m() { return M; }
   KFB_HD static constexpr int p() { return P; }
   KFB_HD static constexpr int G() { return G_; }
+  KFB_HD static constexpr int div_m(int i) { return i / M; }
+  KFB_HD static constexpr int div_p(int i) { return i / P; }
   KFB_HD int lane() const { return lane_; }
   KFB_HD void sync() const {
 #if defined(__CUDA_ARCH__)
@@ -259,16 +315,50 @@ KFB_HD void gemm(CoopCtxT<M, P, G_>& x, TC& C, const TAa& A, const TBb& B, int r
     const int i = x.lane();
     if (i < r) {
       double acc[CMAX];
+      double arow[CMAX];
 #pragma unroll
       for (int j = 0; j < CMAX; ++j)
         if (j < c) acc[j] = (MODE == 0) ? 0.0 : C[i * c + j];
+      // own row of A: one 16-byte shared-memory load per two elements when the row is 16-byte aligned
+      const double* Ap = &A[0];
+      const double* Bp = &B[0];
+#if defined(__CUDA_ARCH__)
+      if (!TA && (kk % 2 == 0)) {
 #pragma unroll
-      for (int k = 0; k < kk; ++k) {
-        double av = A[TA ? k * r + i : i * kk + k];
-        if (MODE == 2) av = -av;
+        for (int k = 0; k < CMAX; k += 2)
+          if (k < kk) {
+            const double2 t = *reinterpret_cast<const double2*>(Ap + i * kk + k);
+            arow[k] = t.x;
+            arow[k + 1 < CMAX ? k + 1 : k] = t.y;
+          }
+      } else
+#endif
+      {
 #pragma unroll
-        for (int j = 0; j < CMAX; ++j)
-          if (j < c) acc[j] = kf_fma(av, B[TB ? j * kk + k : k * c + j], acc[j]);
+        for (int k = 0; k < CMAX; ++k)
+          if (k < kk) arow[k] = Ap[TA ? k * r + i : i * kk + k];
+      }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < kk) {
+          const double av = (MODE == 2) ? -arow[k] : arow[k];
+#if defined(__CUDA_ARCH__)
+          if (!TB && (c % 2 == 0)) {  // broadcast row B[k][:] with 16-byte loads
+#pragma unroll
+            for (int j = 0; j < CMAX; j += 2)
+              if (j < c) {
+                const double2 t = *reinterpret_cast<const double2*>(Bp + k * c + j);
+                acc[j] = kf_fma(av, t.x, acc[j]);
+                acc[j + 1 < CMAX ? j + 1 : j] = kf_fma(av, t.y, acc[j + 1 < CMAX ? j + 1 : j]);
+              }
+          } else
+#endif
+          {
+#pragma unroll
+            for (int j = 0; j < CMAX; ++j)
+              if (j < c) acc[j] = kf_fma(av, Bp[TB ? j * kk + k : k * c + j], acc[j]);
+          }
+        }
       }
 #pragma unroll
       for (int j = 0; j < CMAX; ++j)

@@ -54,7 +54,7 @@ KFB_HD int dare_unit(X& x, const double* Tg, const double* Zg, const double* Hg,
   KFB_FOR(i, p * p) scale = fmax(scale, fabs(prm.H[i]));
   x.sync();
   scale = x.reduce_max(scale);
-  KFB_FOR(idx, m * m) P[idx] = (idx / m == idx % m) ? 1.0e4 * scale : 0.0;
+  KFB_FOR(idx, m * m) P[idx] = (x.div_m(idx) * (m + 1) == idx) ? 1.0e4 * scale : 0.0;
   x.sync();
   int info = 0;
   const double* yp = &y0[0];
@@ -78,7 +78,7 @@ KFB_HD int dare_unit(X& x, const double* Tg, const double* Zg, const double* Hg,
     x.sync();
     gemm<false, true, 1>(x, Rhs, tmp.S2, prm.T, m, m, m);
     KFB_FOR(idx, m * m) {  // symmetrise: keeps the iteration on the symmetric manifold
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       Pn[idx] = 0.5 * (Rhs[idx] + Rhs[j * m + i]);
     }
     x.sync();
@@ -91,7 +91,7 @@ KFB_HD int dare_unit(X& x, const double* Tg, const double* Zg, const double* Hg,
     diff = x.reduce_max(diff);
     mag = x.reduce_max(mag);
     KFB_FOR(idx, m * m) {
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       P[idx] = 0.5 * (Pn[idx] + Pn[j * m + i]);
     }
     x.sync();
@@ -153,7 +153,7 @@ KFB_HD void dare_adjoint_unit(X& x, const double* Tg, const double* Zg, const do
   gemm<false, false, 0>(x, Kp, prm.T, tmp.K, m, m, p);    // Kp = T K  (m x p) = K_ref^T
   // S = At^T S At + sym(Xb)
   KFB_FOR(idx, m * m) {
-    const int i = idx / m, j = idx - i * m;
+    const int i = x.div_m(idx), j = idx - i * m;
     Ak[idx] = W[j * m + i];
     S[idx] = 0.5 * (Xb[idx] + Xb[j * m + i]);
   }

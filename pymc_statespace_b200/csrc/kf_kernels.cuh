@@ -80,11 +80,10 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
 }
 
 template <int MK, int MODE, bool WARP>
-__global__ void kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
+__global__ void __launch_bounds__(WARP ? 128 : 256, WARP ? 4 : 2) kf_coop_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   CoopCtx x;
-  x.m_ = A.m;
-  x.p_ = A.p;
+  x.set_dims(A.m, A.p);
   x.off = 0;
   x.cap = arena_doubles;
   x.overflow = false;
@@ -137,8 +136,7 @@ template <bool BWD, bool WARP>
 __global__ void kf_dare_kernel(const __grid_constant__ DareArgs D, int arena_doubles) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   CoopCtx x;
-  x.m_ = D.m;
-  x.p_ = D.p;
+  x.set_dims(D.m, D.p);
   x.off = 0;
   x.cap = arena_doubles;
   x.overflow = false;

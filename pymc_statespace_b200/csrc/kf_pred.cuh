@@ -37,7 +37,7 @@ KFB_HD StepStat pred_gain(X& x, const Params<X>& prm, const double* yt, double d
   }
   gemm<false, true, 0>(x, u.Mm, P, prm.Z, m, m, p);  // Mm = P Z^T
   KFB_FOR(idx, p * p) {
-    const int i = idx / p, j = idx - i * p;
+    const int i = x.div_p(idx), j = idx - i * p;
     double s = prm.H[idx];
 #pragma unroll
     for (int k = 0; k < m; ++k) s = kf_fma(prm.Z[i * m + k], u.Mm[k * p + j], s);
@@ -75,7 +75,7 @@ KFB_HD StepStat pred_gain(X& x, const Params<X>& prm, const double* yt, double d
     }
   }
   KFB_FOR(idx, m * m) {  // Lm = T - Kp Z
-    const int i = idx / m, j = idx - i * m;
+    const int i = x.div_m(idx), j = idx - i * m;
     double s = prm.T[idx];
 #pragma unroll
     for (int k = 0; k < p; ++k) s = kf_fma(-u.Kp[i * p + k], prm.Z[k * m + j], s);
@@ -175,14 +175,14 @@ KFB_HD void forward_unit_pred(X& x, const KfArgs& A, long long u) {
     }
     KFB_FOR(i, m) a[i] = an[i];
     KFB_FOR(idx, m * m) {
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       P[idx] = 0.5 * (tmp.S2[idx] + tmp.S2[j * m + i]);
     }
     x.sync();
     if (tp && t + 1 < n) {
       KFB_FOR(k, m) tp[k * telem] = a[k];
       KFB_FOR(idx, m * m) {
-        const int i = idx / m, j = idx - i * m;
+        const int i = x.div_m(idx), j = idx - i * m;
         if (j >= i) tp[(m + i * m - (i * (i - 1)) / 2 + (j - i)) * telem] = P[idx];
       }
       tp += tstep;
@@ -248,7 +248,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       rd.get(x, nxt);
       KFB_FOR(k, m) a[k] = nxt[k];
       KFB_FOR(idx, m * m) {
-        int i = idx / m, j = idx - i * m;
+        int i = x.div_m(idx), j = idx - i * m;
         if (j < i) { const int s = i; i = j; j = s; }
         P[idx] = nxt[m + i * m - (i * (i - 1)) / 2 + (j - i)];
       }
@@ -265,7 +265,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
     }
     // ---- adjoint of  a' = T a + c + Kp v ,  P' = sym(L P L^T + Kp H Kp^T + C)
     KFB_FOR(idx, m * m) {
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       Ps[idx] = 0.5 * (Pb[idx] + Pb[j * m + i]);
       S4[idx] = P[idx] + P[j * m + i];
     }
@@ -277,7 +277,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
     gemm<false, false, 0>(x, tmp.S1, Ps, tmp.Lm, m, m, m);   // Ps L
     gemm<true, false, 0>(x, Pb, tmp.Lm, tmp.S1, m, m, m);    // Pb = L^T Ps L
     KFB_FOR(idx, m * m) {                                    // Tb += ab a^T + Lb
-      const int i = idx / m, j = idx - i * m;
+      const int i = x.div_m(idx), j = idx - i * m;
       Tb[idx] += kf_fma(ab[i], a[j], Lb[idx]);
     }
     KFB_FOR(i, m) {                                          // abn = T^T ab
@@ -289,13 +289,13 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
     x.sync();
     if (observed) {
       KFB_FOR(idx, p * p) {
-        const int i = idx / p, j = idx - i * p;
+        const int i = x.div_p(idx), j = idx - i * p;
         Q1[idx] = prm.H[idx] + prm.H[j * p + i];
       }
       gemm<false, false, 0>(x, PK, Ps, tmp.Kp, m, m, p);       // Ps Kp
       gemm<false, false, 0>(x, Kb, PK, Q1, m, p, p);           // Kb = Ps Kp (H + H^T)
       KFB_FOR(idx, m * p) {
-        const int i = idx / p, j = idx - i * p;
+        const int i = x.div_p(idx), j = idx - i * p;
         double s = kf_fma(ab[i], tmp.v[j], Kb[idx]);           // + ab v^T
 #pragma unroll
         for (int k = 0; k < m; ++k) s = kf_fma(-Lb[i * m + k], prm.Z[j * m + k], s);  // - Lb Z^T
@@ -314,7 +314,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
         }
         gemm<true, false, 1>(x, Gb, tmp.TM, Kb, p, m, p);      // Gssb += TM^T Kb
         KFB_FOR(idx, p * p) {
-          const int i = idx / p, j = idx - i * p;
+          const int i = x.div_p(idx), j = idx - i * p;
           Gb[idx] = kf_fma(-0.5 * lb * tmp.v[i], tmp.v[j], Gb[idx]);
           Fb[idx] = -0.5 * lb * tmp.Fi[j * p + i];
         }
@@ -329,7 +329,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
         }
         gemm<true, false, 0>(x, Q1, tmp.Kp, Kb, p, m, p);      // Kp^T Kb
         KFB_FOR(idx, p * p) {
-          const int i = idx / p, j = idx - i * p;
+          const int i = x.div_p(idx), j = idx - i * p;
           double s = -0.5 * lb * (tmp.Fi[j * p + i] - tmp.w[i] * tmp.w[j]);
 #pragma unroll
           for (int k = 0; k < p; ++k) s = kf_fma(-Q1[i * p + k], tmp.Fi[j * p + k], s);
@@ -342,7 +342,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       gemm<true, false, 0>(x, Mb, prm.T, TMb, m, m, p);        // Mb = T^T TMb
       gemm<true, false, 1>(x, Mb, prm.Z, Fb, m, p, p);         //    + Z^T Fb
       KFB_FOR(idx, p * m) {                                    // Zb += Fb Mm^T + Mb^T P - vb a^T
-        const int i = idx / m, j = idx - i * m;
+        const int i = x.div_m(idx), j = idx - i * m;
         double s = kf_fma(-vb[i], a[j], Zb[idx]);
 #pragma unroll
         for (int k = 0; k < p; ++k) s = kf_fma(Fb[i * p + k], tmp.Mm[j * p + k], s);

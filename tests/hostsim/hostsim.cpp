@@ -73,7 +73,7 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   const int cap = coop_arena_doubles(m, p, true) + coop_arena_doubles(m, p, false);
   std::vector<double> arena((size_t)cap);
   CoopCtx x;
-  x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false;
+  x.set_dims(m, p); x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false;
   x.off = 0;
   run_kind(x, A, 0);
   const int fwd_used = x.off;
@@ -99,7 +99,7 @@ extern "C" int hostsim_dare(int m, int p, const double* T, const double* Z, cons
   const int cap = dare_arena_doubles(m, p);
   std::vector<double> arena((size_t)cap);
   CoopCtx x;
-  x.m_ = m; x.p_ = p; x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false; x.off = 0;
+  x.set_dims(m, p); x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false; x.off = 0;
   x.red = x.bump(34);
   int info = dare_unit(x, T, Z, H, C, Pss, Gss);
   if (x.overflow) return 5;
