@@ -109,20 +109,16 @@ struct CoopCtx {
   int off, cap;
   bool overflow;
   double* red;  // 34 doubles of scratch for cross-lane reductions (CTA mode)
-  unsigned magic_m, magic_p;  // ceil(2^32 / m), ceil(2^32 / p): i / m == umulhi(i, magic) for 0 <= i < 65536
 
   KFB_HD void set_dims(int m, int p) {
     m_ = m;
     p_ = p;
-    magic_m = (unsigned)((0x100000000ull + (unsigned)m - 1) / (unsigned)m);
-    magic_p = (unsigned)((0x100000000ull + (unsigned)p - 1) / (unsigned)p);
   }
-  KFB_HD int div_m(int i) const {
-    return m_ == 1 ? i : (int)(((unsigned long long)(unsigned)i * magic_m) >> 32);
-  }
-  KFB_HD int div_p(int i) const {
-    return p_ == 1 ? i : (int)(((unsigned long long)(unsigned)i * magic_p) >> 32);
-  }
+  // NOTE: a multiply-high ("magic number") division was tried here; nvcc 12.9 then mis-compiled the unrolled
+  // P - K K^T F loop of univariate_inner for k_states = 30 (compute-sanitizer racecheck: cross-thread RAW hazard,
+  // wrong results; the division itself was verified exact on the device).  Plain division is kept.
+  KFB_HD int div_m(int i) const { return i / m_; }
+  KFB_HD int div_p(int i) const { return i / p_; }
 
   KFB_HD int size_of(int sz) const {
     return sz == SZ_M ? m_ : sz == SZ_P ? p_ : sz == SZ_MM ? m_ * m_ : sz == SZ_MP ? m_ * p_ : sz == SZ_PP ? p_ * p_ : tape_width(m_);
