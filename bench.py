@@ -104,25 +104,57 @@ def reference_arm(a):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML in-process, every ~10 ms;
+    falls back to one long-running `nvidia-smi -lms 50`)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.sm, self.smmax, self.reasons = index, [], None, set()
+        self.stop = threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         while not self.stop.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            self.reasons |= {n for bit, n in names.items() if r & bit}
+            self.stop.wait(0.01)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                 "-lms", "50"], stdout=subprocess.PIPE, text=True)
+        try:
+            while not self.stop.is_set():
+                row = [x.strip() for x in proc.stdout.readline().split(",")]
+                if len(row) >= 6 and row[0].replace(".", "").isdigit():
+                    self.sm.append(float(row[0]))
+                    self.smmax = float(row[1])
+                    self.reasons |= {n for n, v in zip(names, row[2:6]) if v.lower().startswith("active")}
+        finally:
+            proc.kill()
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in o.strip().split(",")])
+                self._run_smi()
             except Exception:
                 pass
-            self.stop.wait(0.1)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *exc):
@@ -130,12 +162,8 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smmax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------------------------- GPU side
@@ -296,6 +324,16 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} draws x T={n}, {reps} timed repeats ({ms:.0f} ms each), "
                                               "oracle/kalman_c.c forward+adjoint, OpenMP over draws"}
+            # context only: the per-step Python restatement (closest analogue of the reference's PyTensor scan VM,
+            # which BASELINE.md estimates at 7e3-3e4 steps/s/core) on one draw, forward + torch-autograd backward
+            try:
+                from oracle import models as om
+
+                t0 = time.perf_counter()
+                om.logp_and_grad_theta(lambda t: om.arma_matrices(t, (1, 1), True), ths[0], ys[:, :, None])
+                line["cpu_baseline"]["python_oracle_steps_per_s_1core"] = n / (time.perf_counter() - t0)
+            except Exception:
+                pass
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

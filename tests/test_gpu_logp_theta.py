@@ -122,3 +122,60 @@ def test_full_size_properties_arma11():
     fd = (model.logp(th + eps * direction) - model.logp(th - eps * direction)) / (2 * eps)
     an = (grad * direction).sum(1)
     assert float(((fd - an).abs() / (an.abs() + 1e-3 * grad.abs().amax(1))).median()) < 1e-5
+
+
+def test_full_size_properties_varmax():
+    """BASELINE.json configs[2] at full size (262,144 draws x T=1000, k_states=6, k_endog=3, 10 % missing rows):
+    sub-batch invariance, sampled draws vs the oracle, univariate == corrected cholesky (diagonal H identity)."""
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.synthetic import varmax20_workload
+
+    B, n = 262144, 1000
+    spec, y, theta = varmax20_workload(B, n)
+    th = torch.as_tensor(theta, device="cuda")
+    fn = lambda t: om.varmax_matrices(t, 3, (2, 0), True, True)  # noqa: E731
+    model = KalmanLogp(spec, y, n_draws=B, filter_type="univariate")
+    logp, grad = model.logp_and_grad(th)
+    assert int((model.info != 0).sum()) == 0
+    assert bool(torch.isfinite(logp).all()) and bool(torch.isfinite(grad).all())
+    sub = KalmanLogp(spec, y, n_draws=256, filter_type="univariate")
+    lp2, g2 = sub.logp_and_grad(th[5000:5256].contiguous())
+    assert torch.equal(lp2, logp[5000:5256]) and torch.equal(g2, grad[5000:5256])
+    _compare(fn, y[:, :, None], theta, logp.cpu().numpy(), grad.cpu().numpy(), (0, 262143), "univariate")
+    chol = KalmanLogp(spec, y, n_draws=256, filter_type="cholesky", strict_reference=False)
+    lp3, g3 = chol.logp_and_grad(th[5000:5256].contiguous())
+    assert float(((lp3 - lp2).abs() / lp2.abs()).max()) < 1e-9
+    sl = spec.param_slices["state_cov"]
+    sym = lambda g: 0.5 * (g[:, sl].reshape(-1, 3, 3) + g[:, sl].reshape(-1, 3, 3).transpose(1, 2))  # noqa: E731
+    assert float(((sym(g3) - sym(g2)).abs().amax((1, 2)) / g2.abs().amax(1)).max()) < 1e-7
+    other = [i for i in range(spec.n_theta) if not (sl.start <= i < sl.stop)]
+    assert float(((g3[:, other] - g2[:, other]).abs().amax(1) / g2.abs().amax(1)).max()) < 1e-7
+
+
+def test_trend_seasonal_k30_steady_vs_standard():
+    """BASELINE.json configs[3]: k_states = 30, T = 2000.  Both filters against the oracle on sampled draws; the two
+    filters legitimately differ (P_t has not converged to P_ss by t = 2000)."""
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.models import trend_seasonal_spec
+    from pymc_statespace_b200.synthetic import trend_seasonal_workload
+
+    spec, y, theta = trend_seasonal_workload(n_draws=64, n=300)
+    th = torch.as_tensor(theta, device="cuda")
+
+    def mats(t):
+        m = spec.matrices(t.detach().numpy())
+        T, Z, R = (torch.tensor(m[k]) for k in ("T", "Z", "R"))
+        Q = torch.zeros(3, 3, dtype=torch.float64)
+        Q[0, 0], Q[1, 1], Q[2, 2] = t[0], t[1], t[2]
+        H = t[3].reshape(1, 1)
+        return torch.zeros(30, 1, dtype=torch.float64), torch.eye(30, dtype=torch.float64), T, Z, R, H, Q
+
+    for kind, gtol in (("standard", 1e-8), ("steady_state", 1e-6)):
+        model = KalmanLogp(spec, y, n_draws=64, filter_type=kind)
+        logp, grad = model.logp_and_grad(th)
+        assert int((model.info != 0).sum()) == 0
+        lp, g = logp.cpu().numpy(), grad.cpu().numpy()
+        for b in (0, 63):
+            ll, gr = om.logp_and_grad_theta(mats, theta[b], y[:, :, None], kind)
+            assert abs(lp[b] - ll) <= 1e-8 * abs(ll)
+            assert np.abs(g[b] - gr).max() <= gtol * np.abs(gr).max(), (kind, g[b], gr)
