@@ -21,6 +21,7 @@ struct RegBuf {
 template <int M, int P>
 struct ThreadCtx {
   static constexpr bool TV = false;
+  static constexpr bool PIPELINE = false;  // adjoint: overlap gain(t-1) with adjoint(t)
   template <int SZ>
   using Buf = RegBuf<(SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : M + (M * (M + 1)) / 2)>;
   const double* y_smem;  // observations staged in shared memory (shared y) or nullptr
@@ -104,6 +105,7 @@ struct ThreadCtx {
 // ---------------------------------------------------------------------------
 struct CoopCtx {
   static constexpr bool TV = true;
+  static constexpr bool PIPELINE = false;
   int m_, p_, lane_, G_;
   double* arena;
   int off, cap;
@@ -243,6 +245,7 @@ KFB_HD void gemm(CoopCtx& x, TC& C, const TAa& A, const TBb& B, int r, int kk, i
 template <int M, int P, int G_>
 struct CoopCtxT {
   static constexpr bool TV = false;
+  static constexpr bool PIPELINE = false;
   static constexpr int KT = M + (M * (M + 1)) / 2;
   int lane_;
   unsigned mask_;

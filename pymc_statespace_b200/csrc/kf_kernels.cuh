@@ -62,6 +62,8 @@ __device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
   }
 }
 
+// 65,536 units (the headline batch) need 443 resident threads per SM for a single wave: the pipelined adjoint of the
+// k_states <= 2 kernels is capped at 7 CTAs x 64 threads per SM (<= 144 registers) instead of spilling into a 2nd wave.
 template <int M, int P, int MK, int MODE>
 __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     kf_thread_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(128) kf_coopT_kernel(const __grid_constant__ K
   x.arena = kf_dyn_smem + (size_t)group * arena_doubles;
   x.off = 0;
   run_unit<MK, MODE>(x, A, u);
+  if (x.off > arena_doubles) __trap();  // arena accounting (coop_arena_doubles + slack) out of date
 }
 
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----

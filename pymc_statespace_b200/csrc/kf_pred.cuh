@@ -199,17 +199,30 @@ KFB_HD void forward_unit_pred(X& x, const KfArgs& A, long long u) {
 // ------------------------------------------------------------------------------------------------
 // adjoint
 // ------------------------------------------------------------------------------------------------
+// One step's inputs for the adjoint: predicted moments of step t and everything that depends only on them
+// (innovation, gain, closed-loop matrix).  None of it depends on the adjoint state, so with X::PIPELINE the set of
+// step t-1 is computed while the adjoint of step t is in flight (two independent dependency chains per thread).
+template <class X>
+struct StepSet {
+  typename X::template Buf<SZ_M> a;
+  typename X::template Buf<SZ_MM> P;
+  PredTmp<X> g;
+  bool observed;
+  KFB_HD explicit StepSet(X& x) : a(x), P(x), g(x), observed(false) {}
+};
+
 template <int MK, class X>
 KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
   const int m = x.m(), p = x.p(), n = A.n;
   const long long draw = u / A.n_series, series = u - draw * A.n_series;
   Params<X> prm(x);
-  typename X::template Buf<SZ_MM> P(x), Pb(x), Tb(x), Cb(x), Ps(x), S4(x), Lb(x);
-  typename X::template Buf<SZ_M> a(x), ab(x), abn(x), cb(x);
+  typename X::template Buf<SZ_MM> Pb(x), Tb(x), Cb(x), Ps(x), S4(x), Lb(x);
+  typename X::template Buf<SZ_M> ab(x), abn(x), cb(x);
   typename X::template Buf<SZ_MP> Zb(x), Kb(x), Mb(x), PK(x), TMb(x);
   typename X::template Buf<SZ_PP> Hb(x), Fb(x), Gb(x), Q1(x);
   typename X::template Buf<SZ_P> db(x), vb(x);
-  PredTmp<X> tmp(x);
+  StepSet<X> S0(x);
+  StepSet<X> S1(X::PIPELINE ? StepSet<X>(x) : S0);
 
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
@@ -232,7 +245,8 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
   typename X::template Buf<SZ_TAPE> nxt(x);
   typename X::TapeReader rd(x, A, u);
 
-  for (int t = n - 1; t >= 0; --t) {
+  // ---- inputs of step t (tape entries are consumed in strictly descending order)
+  auto prepare = [&](int t, StepSet<X>& S) {
     if (X::TV) {
       if (A.T.ts) load_or_zero(x, prm.T, Tp + t * A.T.ts, m * m);
       if (A.Z.ts) load_or_zero(x, prm.Z, Zp + t * A.Z.ts, p * m);
@@ -241,28 +255,36 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       x.sync();
     }
     if (t == 0) {
-      load_or_zero(x, a, A.a0.p + draw * A.a0.bs, m);
-      if (MK == MK_STEADY) load_or_zero(x, P, A.Pss.p + draw * A.Pss.bs, m * m);
-      else load_or_zero(x, P, A.P0.p + draw * A.P0.bs, m * m);
+      load_or_zero(x, S.a, A.a0.p + draw * A.a0.bs, m);
+      if (MK == MK_STEADY) load_or_zero(x, S.P, A.Pss.p + draw * A.Pss.bs, m * m);
+      else load_or_zero(x, S.P, A.P0.p + draw * A.P0.bs, m * m);
     } else {
       rd.get(x, nxt);
-      KFB_FOR(k, m) a[k] = nxt[k];
+      KFB_FOR(k, m) S.a[k] = nxt[k];
       KFB_FOR(idx, m * m) {
         int i = x.div_m(idx), j = idx - i * m;
-        if (j < i) { const int s = i; i = j; j = s; }
-        P[idx] = nxt[m + i * m - (i * (i - 1)) / 2 + (j - i)];
+        if (j < i) { const int sw = i; i = j; j = sw; }
+        S.P[idx] = nxt[m + i * m - (i * (i - 1)) / 2 + (j - i)];
       }
     }
     x.sync();
     const double* yt = y + (long long)t * p;
-    const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
-    const bool observed = (count_missing(x, yt) == 0);
-    if (observed) {
-      pred_gain<MK>(x, prm, yt, A.d_sign, a, P, tmp, (LogAcc*)nullptr, false);
+    S.observed = (count_missing(x, yt) == 0);
+    if (S.observed) {
+      pred_gain<MK>(x, prm, yt, A.d_sign, S.a, S.P, S.g, (LogAcc*)nullptr, false);
     } else {
-      KFB_FOR(i, m * m) tmp.Lm[i] = prm.T[i];  // L = T, Kp = 0
+      KFB_FOR(i, m * m) S.g.Lm[i] = prm.T[i];  // L = T, Kp = 0
       x.sync();
     }
+  };
+
+  // ---- adjoint of step t
+  auto adjoint = [&](int t, StepSet<X>& S) {
+    auto& a = S.a;
+    auto& P = S.P;
+    auto& tmp = S.g;
+    const bool observed = S.observed;
+    const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
     // ---- adjoint of  a' = T a + c + Kp v ,  P' = sym(L P L^T + Kp H Kp^T + C)
     KFB_FOR(idx, m * m) {
       const int i = x.div_m(idx), j = idx - i * m;
@@ -372,6 +394,23 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       if (A.H.ts && A.gH) { KFB_FOR(i, p * p) { A.gH[(u * n + t) * p * p + i] = Hb[i]; Hb[i] = 0.0; } }
       if (A.d.ts && A.gd) { KFB_FOR(i, p) { A.gd[(u * n + t) * p + i] = db[i]; db[i] = 0.0; } }
       x.sync();
+    }
+  };
+
+  if (!X::PIPELINE) {
+    for (int t = n - 1; t >= 0; --t) {
+      prepare(t, S0);
+      adjoint(t, S0);
+    }
+  } else {
+    prepare(n - 1, S0);
+    for (int t = n - 1; t >= 0; t -= 2) {
+      if (t >= 1) prepare(t - 1, S1);
+      adjoint(t, S0);
+      if (t >= 1) {
+        if (t >= 2) prepare(t - 2, S0);
+        adjoint(t - 1, S1);
+      }
     }
   }
   if (A.ga0) KFB_FOR(i, m) A.ga0[u * m + i] = ab[i];

@@ -2,6 +2,9 @@
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
+import os
+from pymc_statespace_b200 import _lib
+if os.environ.get('KFB_LIB'): _lib.LIB_PATH=os.environ['KFB_LIB']
 from pymc_statespace_b200 import BatchedKalman, fp64_peak_tflops
 
 def arma11(B, n, seed=1):
