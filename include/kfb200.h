@@ -123,6 +123,15 @@ kfb_status kfb_backward(const kfb_desc *desc, const kfb_inputs *in, const kfb_co
                         const kfb_grads *grads, void *workspace, size_t workspace_bytes,
                         void *stream);
 
+/* RTS smoother (next row f2, not on the logp/grad path): reference KalmanSmoother.build_graph,
+ * pymc_statespace/filters/kalman_smoother.py:56-104, static T, R, Q.  filtered_states[U,n,m], filtered_covs[U,n,m,m]
+ * (outputs of kfb_forward) -> smoothed_states[U,n,m], smoothed_covs[U,n,m,m].  workspace: n_draws*m*m doubles
+ * (m*m if R and Q are shared). */
+kfb_status kfb_smoother(int64_t n_draws, int64_t n_series, int32_t n, int32_t m, int32_t r, const double *T,
+                        int64_t T_bs, const double *R, int64_t R_bs, const double *Q, int64_t Q_bs,
+                        const double *filtered_states, const double *filtered_covs, double *smoothed_states,
+                        double *smoothed_covs, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Stationary initial covariance: X = A X A^T + C with C = R Q R^T
  * (reference models/SARIMAX.py:100-107, models/VARMAX.py:143-150:
  *  solve_discrete_lyapunov(T, R Q R^T, method="bilinear")).  X[B,m,m]; info[B] (0 ok, 1 = no

@@ -312,3 +312,29 @@ def dense_gaussian_loglik(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
     L = np.linalg.cholesky(S)
     w = scipy.linalg.solve_triangular(L, yv, lower=True)
     return float(-0.5 * (n * p * LOG_2PI + w @ w) - np.log(np.diag(L)).sum())
+
+
+# ----------------------------------------------------------------------------
+# RTS smoother (SURVEY.md section 8(f) row f2 - not on the logp/grad path)
+# ----------------------------------------------------------------------------
+def kalman_smoother(T, R, Q, filtered_states, filtered_covariances):
+    """KalmanSmoother.build_graph / smoother_step, reference filters/kalman_smoother.py:56-104 (static T, R, Q).
+
+    Backwards scan from the last filtered moment; the gain uses ``pinv(P_hat)`` (:92) and ``predict`` here has no
+    intercept and no symmetrisation (:99-104).  Returns (smoothed_states[n,m,1], smoothed_covariances[n,m,m])."""
+    T, R, Q = (np.asarray(x, dtype=np.float64) for x in (T, R, Q))
+    fs = np.asarray(filtered_states, dtype=np.float64)
+    fc = np.asarray(filtered_covariances, dtype=np.float64)
+    n = fs.shape[0]
+    a_smooth, P_smooth = fs[-1], fc[-1]
+    out_a, out_P = [a_smooth], [P_smooth]
+    for t in range(n - 2, -1, -1):
+        a, P = fs[t], fc[t]
+        a_hat = T.dot(a)
+        P_hat = T.dot(P).dot(T.T) + R.dot(Q).dot(R.T)
+        smoother_gain = np.linalg.pinv(P_hat).dot(T).dot(P).T
+        a_smooth = a + smoother_gain @ (a_smooth - a_hat)
+        P_smooth = P + smoother_gain.dot(P_smooth - P_hat).dot(smoother_gain.T)
+        out_a.append(a_smooth)
+        out_P.append(P_smooth)
+    return np.stack(out_a[::-1]), np.stack(out_P[::-1])

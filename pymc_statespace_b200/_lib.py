@@ -62,6 +62,8 @@ EXPORTS = {
                              ctypes.c_size_t, _c_i32, _vp]),
     "kfb_backward": (_c_i32, [ctypes.POINTER(KfbDesc), ctypes.POINTER(KfbInputs), ctypes.POINTER(KfbCotangents),
                               ctypes.POINTER(KfbGrads), _vp, ctypes.c_size_t, _vp]),
+    "kfb_smoother": (_c_i32, [_c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp, _vp,
+                              _vp, ctypes.c_size_t, _vp]),
     "kfb_lyapunov_forward": (_c_i32, [_c_i64, _c_i32, _c_i32, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
     "kfb_lyapunov_backward": (_c_i32, [_c_i64, _c_i32, _c_i32, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp,
                                        _vp, _vp, _vp]),

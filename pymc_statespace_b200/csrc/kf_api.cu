@@ -266,6 +266,30 @@ kfb_status kfb_backward(const kfb_desc* desc, const kfb_inputs* in, const kfb_co
   return KFB_OK;
 }
 
+kfb_status kfb_smoother(int64_t n_draws, int64_t n_series, int32_t n, int32_t m, int32_t r, const double* T, int64_t T_bs,
+                        const double* R, int64_t R_bs, const double* Q, int64_t Q_bs, const double* filtered_states,
+                        const double* filtered_covs, double* smoothed_states, double* smoothed_covs, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (n_draws <= 0 || n_series <= 0 || n <= 0 || m <= 0 || r <= 0 || !T || !R || !Q || !filtered_states || !filtered_covs ||
+      !smoothed_states || !smoothed_covs)
+    return KFB_ERR_INVALID_ARG;
+  const bool C_batched = R_bs || Q_bs;
+  const long long nDC = C_batched ? n_draws : 1;
+  const size_t need = (size_t)nDC * m * m * sizeof(double);
+  if (!workspace || workspace_bytes < need) return KFB_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = launch_rqr_forward(nDC, 1, m, r, MatArg{R, R_bs, 0}, MatArg{Q, Q_bs, 0}, (double*)workspace, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  SmoothArgs S;
+  S.U = n_draws * n_series; S.n_series = n_series; S.n = n; S.m = m;
+  S.T = MatArg{T, T_bs, 0};
+  S.C = MatArg{(const double*)workspace, C_batched ? (long long)m * m : 0, 0};
+  S.fs = filtered_states; S.fc = filtered_covs; S.ss = smoothed_states; S.sc = smoothed_covs;
+  e = launch_smoother(S, s);
+  if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
 kfb_status kfb_lyapunov_forward(int64_t B, int32_t m, int32_t r, const double* A, int64_t A_bs, const double* R,
                                 int64_t R_bs, const double* Q, int64_t Q_bs, double* X, int32_t* info, void* stream) {
   if (B <= 0 || m <= 0 || r <= 0 || !A || !R || !Q || !X) return KFB_ERR_INVALID_ARG;

@@ -55,6 +55,24 @@ cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s) {
   return launch_coop_mode<false>(A, bwd, arena, block, (unsigned)A.U, arena_bytes, s);
 }
 
+cudaError_t launch_smoother(const SmoothArgs& S, cudaStream_t s) {
+  const int arena = (smoother_arena_doubles(S.m) + 1) & ~1;
+  const size_t arena_bytes = (size_t)arena * sizeof(double);
+  const size_t smem_max = 227 * 1024;
+  if (arena_bytes > smem_max) return cudaErrorInvalidConfiguration;
+  if (arena_bytes * 4 <= smem_max && S.m < 16) {
+    const int warps = 4;
+    const size_t smem = arena_bytes * warps;
+    cudaFuncSetAttribute(kf_smoother_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kf_smoother_kernel<true><<<(unsigned)((S.U + warps - 1) / warps), warps * 32, smem, s>>>(S, arena);
+  } else {
+    cudaFuncSetAttribute(kf_smoother_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)arena_bytes);
+    kf_smoother_kernel<false><<<(unsigned)S.U, 256, arena_bytes, s>>>(S, arena);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s) {
   int arena = (dare_arena_doubles(D.m, D.p) + 1) & ~1;
   const size_t arena_bytes = (size_t)arena * sizeof(double);

@@ -5,6 +5,7 @@
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
 #include "kf_pred.cuh"
+#include "kf_smooth.cuh"
 
 namespace kfb {
 
@@ -173,6 +174,34 @@ __global__ void kf_dare_kernel(const __grid_constant__ DareArgs D, int arena_dou
   if (x.overflow) __trap();
 }
 cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s);
+
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 128 : 256) kf_smoother_kernel(const __grid_constant__ SmoothArgs S, int arena_doubles) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  CoopCtx x;
+  x.set_dims(S.m, 1);
+  x.off = 0;
+  x.cap = arena_doubles;
+  x.overflow = false;
+  long long u;
+  if (WARP) {
+    const int warp = threadIdx.x >> 5;
+    x.lane_ = threadIdx.x & 31;
+    x.G_ = 32;
+    x.arena = kf_dyn_smem + (size_t)warp * arena_doubles;
+    u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (u >= S.U) return;
+  } else {
+    x.lane_ = threadIdx.x;
+    x.G_ = blockDim.x;
+    x.arena = kf_dyn_smem;
+    u = blockIdx.x;
+  }
+  x.red = x.bump(34);
+  smoother_unit(x, S, u);
+  if (x.overflow) __trap();
+}
+cudaError_t launch_smoother(const SmoothArgs& S, cudaStream_t s);
 
 // launchers implemented in kf_thread_m*.cu / kf_coop.cu
 typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);

@@ -197,6 +197,28 @@ class BatchedKalman:
         return grads
 
 
+def rts_smoother(T, R, Q, filtered_states, filtered_covs, n_series: int = 1):
+    """Batched RTS smoother (reference filters/kalman_smoother.py:56-104).
+    T:[B,m,m]|[m,m], R:[B,m,r]|[m,r], Q:[B,r,r]|[r,r] static; filtered_states [U,n,m], filtered_covs [U,n,m,m]
+    (outputs of BatchedKalman.forward).  Returns (smoothed_states [U,n,m], smoothed_covs [U,n,m,m])."""
+    lib = load()
+    fs, fc = filtered_states.contiguous(), filtered_covs.contiguous()
+    U, n, m = fs.shape
+    r = R.shape[-1]
+    T, R, Q = T.contiguous(), R.contiguous(), Q.contiguous()
+    n_draws = U // n_series
+    for name, t, nd in (("T", T, 2), ("R", R, 2), ("Q", Q, 2)):
+        if t.ndim == nd + 1 and t.shape[0] != n_draws:
+            raise ValueError(f"{name}: leading dimension {t.shape[0]} != n_draws {n_draws}")
+    ss, sc = torch.empty_like(fs), torch.empty_like(fc)
+    ws = torch.empty(max(n_draws, 1) * m * m, dtype=torch.float64, device=fs.device)
+    with torch.cuda.device(fs.device):
+        check(lib.kfb_smoother(n_draws, n_series, n, m, r, _ptr(T), m * m if T.ndim == 3 else 0, _ptr(R),
+                               m * r if R.ndim == 3 else 0, _ptr(Q), r * r if Q.ndim == 3 else 0, _ptr(fs), _ptr(fc),
+                               _ptr(ss), _ptr(sc), _ptr(ws), ws.numel() * 8, _stream_ptr(fs.device)), "kfb_smoother")
+    return ss, sc
+
+
 def lyapunov_forward(A: torch.Tensor, R: torch.Tensor, Q: torch.Tensor):
     """X = A X A^T + R Q R^T per draw (reference models/SARIMAX.py:100-107).  A:[B,m,m], R:[B,m,r]|[m,r],
     Q:[B,r,r]|[r,r].  Returns (X[B,m,m], info[B])."""

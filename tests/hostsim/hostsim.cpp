@@ -9,6 +9,7 @@
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
 #include "kf_pred.cuh"
+#include "kf_smooth.cuh"
 
 using namespace kfb;
 
@@ -109,4 +110,18 @@ extern "C" int hostsim_dare(int m, int p, const double* T, const double* Z, cons
     if (x.overflow) return 6;
   }
   return info;
+}
+
+extern "C" int hostsim_smoother(int n, int m, const double* T, const double* C, const double* fs, const double* fc, double* ss,
+                                double* sc) {
+  SmoothArgs S;
+  S.U = 1; S.n_series = 1; S.n = n; S.m = m;
+  S.T = {T, 0, 0}; S.C = {C, 0, 0}; S.fs = fs; S.fc = fc; S.ss = ss; S.sc = sc;
+  const int cap = smoother_arena_doubles(m);
+  std::vector<double> arena((size_t)cap);
+  CoopCtx x;
+  x.set_dims(m, 1); x.lane_ = 0; x.G_ = 1; x.arena = arena.data(); x.cap = cap; x.overflow = false; x.off = 0;
+  x.red = x.bump(34);
+  smoother_unit(x, S, 0);
+  return x.overflow ? 5 : 0;
 }

@@ -153,3 +153,48 @@ def test_steady_state_rejects_time_varying():
     data, a0, P0, T, Z, R, H, Q = make_test_inputs(1, 2, 2, 10)
     with pytest.raises(ValueError, match="time-invariant"):
         SteadyStateFilter().build_graph(data, a0, P0, np.stack([T] * 10), Z, R, H, Q)
+
+
+@pytest.mark.parametrize("filter_name", filter_names)
+def test_last_smoother_is_last_filtered_and_matches_oracle(filter_name):
+    # reference tests/test_kalman_filter.py:212-222 + smoothed outputs of :226-241
+    from pymc_statespace_b200.filters import KalmanSmoother
+
+    p, m, r, n = 1, 5, 1, 10
+    inputs = make_test_inputs(p, m, r, n)
+    outs = _filters()[filter_name]().build_graph(*inputs)
+    ss, sc = KalmanSmoother().build_graph(inputs[3], inputs[5], inputs[7], outs[0], outs[2])
+    assert ss.shape == (n, m, 1) and sc.shape == (n, m, m)
+    np.testing.assert_allclose(outs[0][-1], ss[-1])
+    np.testing.assert_allclose(outs[2][-1], sc[-1])
+    rs, rc = kn.kalman_smoother(inputs[3], inputs[5], inputs[7], outs[0], outs[2])
+    np.testing.assert_allclose(ss, rs, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(sc, rc, rtol=1e-8, atol=1e-10)
+
+
+def test_smoother_nile_and_batched():
+    from pymc_statespace_b200 import BatchedKalman, rts_smoother
+    from pymc_statespace_b200.filters import KalmanSmoother, StandardFilter
+
+    inputs = nile_inputs(5)
+    outs = StandardFilter().build_graph(*inputs)
+    ss, sc = KalmanSmoother().build_graph(inputs[3], inputs[5], inputs[7], outs[0], outs[2])
+    rs, rc = kn.kalman_smoother(inputs[3], inputs[5], inputs[7], outs[0], outs[2])
+    np.testing.assert_allclose(ss, rs, rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(sc[5:], rc[5:], rtol=1e-7, atol=1e-7)  # reference skips the first 5 as well (:236-238)
+    # batched, k_states = 6 (warp mode) and 30 (CTA mode)
+    rng = np.random.default_rng(2)
+    for m, pdim, r, B in ((6, 3, 3, 9), (30, 1, 3, 3)):
+        n = 20
+        systems = [random_system(rng, m, pdim, r, n, scale_T=0.2) for _ in range(B)]
+        y = systems[0][0]
+        dev = lambda i: torch.as_tensor(np.stack([s[i] for s in systems]), device="cuda")  # noqa: E731
+        bk = BatchedKalman("standard", n, m, pdim, r, n_draws=B)
+        out = bk.forward(torch.as_tensor(y[..., 0], device="cuda"), dev(1), dev(2), dev(3), dev(4), dev(5), dev(6), dev(7),
+                         outputs=("filtered_states", "filtered_covs"))
+        ss, sc = rts_smoother(dev(3), dev(5), dev(7), out["filtered_states"], out["filtered_covs"])
+        for b in (0, B - 1):
+            o = kn.kalman_filter("standard", y, *systems[b][1:])
+            rs, rc = kn.kalman_smoother(systems[b][3], systems[b][5], systems[b][7], o[0], o[2])
+            assert rel_err(ss[b].cpu().numpy(), rs[..., 0]) < 1e-8
+            assert rel_err(sc[b].cpu().numpy(), rc) < 1e-8

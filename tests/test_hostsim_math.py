@@ -157,3 +157,28 @@ def test_predictor_form_steady_state_and_time_varying():
     _, gt = kt.loglik_and_grads("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d)
     for k in gt:
         assert rel_err(g[k], gt[k]) < 1e-9, k
+
+
+def test_rts_smoother_on_host():
+    import ctypes
+
+    lib = hostsim.build()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rng = np.random.default_rng(0)
+    from tests.helpers import make_test_inputs
+
+    for args, skip in ((nile_inputs(0), 5), (make_test_inputs(1, 5, 1, 10), 0),
+                       (make_test_inputs(1, 5, 2, 10, missing_data=1), 0), (random_system(rng, 6, 3, 3, 30, n_missing=2), 0)):
+        o = kn.kalman_filter("standard", *args)
+        T, R, Q = (np.ascontiguousarray(args[i]) for i in (3, 5, 7))
+        n, m = o[0].shape[0], T.shape[0]
+        fs, fc = np.ascontiguousarray(o[0][..., 0]), np.ascontiguousarray(o[2])
+        ss, sc = np.zeros_like(fs), np.zeros_like(fc)
+        C = np.ascontiguousarray(R @ Q @ R.T)
+        assert lib.hostsim_smoother(n, m, vp(T), vp(C), vp(fs), vp(fc), vp(ss), vp(sc)) == 0
+        rs, rc = kn.kalman_smoother(T, R, Q, o[0], o[2])
+        assert rel_err(ss, rs[..., 0]) < 1e-10
+        # reference tests/test_kalman_filter.py:236-238: the first few smoothed covariances of the P0 = 1e6 fixture are
+        # ill-conditioned (pinv of cond ~3e6 followed by a 1e6-sized cancellation) and are skipped there as well
+        assert rel_err(sc[skip:], rc[skip:]) < 1e-10
+        np.testing.assert_allclose(ss[-1], fs[-1])
