@@ -280,3 +280,77 @@ def test_subwarp_kernels_many_units_not_multiple_of_group():
             assert abs(ll[b] - ref) < RTOL * abs(ref)
             assert rel_err(g["T"][b].cpu().numpy(), gref["T"]) < RTOL
             assert rel_err(g["Q"][b].cpu().numpy(), gref["Q"]) < RTOL
+
+
+@pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_very_short_series(n, force_coop):
+    # n = 1: no tape at all; n = 2: one tape entry; the ring read-ahead must not run past the start
+    rng = np.random.default_rng(n)
+    for kind, (m, p, r) in (("standard", (2, 1, 1)), ("univariate", (3, 2, 2)), ("steady_state", (2, 1, 1))):
+        args = random_system(rng, m, p, r, n)
+        check_against_oracle(kind, args, force_coop=force_coop, grad_rtol=1e-7 if kind == "steady_state" else RTOL)
+
+
+def test_all_rows_missing_and_first_last_missing():
+    rng = np.random.default_rng(2)
+    args = list(random_system(rng, 2, 1, 1, 12))
+    y = args[0].copy()
+    y[[0, 11]] = np.nan
+    args[0] = y
+    for kind in ("standard", "univariate", "single"):
+        check_against_oracle(kind, args)
+    args[0] = np.full_like(y, np.nan)
+    res, grads, info = run_single("standard", args)
+    ref = kn.kalman_filter("standard", *args)
+    assert info == 0 and res[4] == 0.0 and ref[4] == 0.0
+    for a, b in zip(res[:4], ref[:4]):
+        assert rel_err(a, b) < RTOL
+    assert all(np.all(np.isfinite(g)) for g in grads.values())
+
+
+def test_more_observables_than_states_and_wide_p():
+    # k_endog > k_states and k_endog = 5 have no compile-time instantiation: generic cooperative kernels
+    rng = np.random.default_rng(9)
+    for (m, p, r) in ((1, 2, 1), (2, 5, 2), (3, 4, 1)):
+        args = random_system(rng, m, p, r, 20, n_missing=2)
+        check_against_oracle("standard", args)
+        check_against_oracle("univariate", args)
+
+
+def test_units_not_multiple_of_block_and_per_series_y():
+    from pymc_statespace_b200 import BatchedKalman
+
+    rng = np.random.default_rng(33)
+    B, S, n, m, p, r = 67, 2, 30, 2, 1, 1  # 134 units: 2 full 64-thread CTAs + 6 threads
+    systems = [random_system(rng, m, p, r, n) for _ in range(B)]
+    ys = np.stack([random_system(rng, m, p, r, n, n_missing=2)[0][..., 0] for _ in range(S)])
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    for force in (False, True):
+        bk = BatchedKalman("standard", n, m, p, r, n_draws=B, n_series=S, force_coop=force)
+        out = bk.forward(_dev(ys), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                         outputs=("loglik",), save_for_backward=True)
+        g = bk.backward(wrt=("T", "a0"))
+        ll = out["loglik"].cpu().numpy().reshape(B, S)
+        for b, s in ((0, 0), (66, 1), (31, 1)):
+            args = (ys[s][..., None],) + tuple(systems[b][1:])
+            ref, gref = kt.loglik_and_grads("standard", *args)
+            assert abs(ll[b, s] - ref) < RTOL * abs(ref)
+            assert rel_err(g["T"].cpu().numpy().reshape(B, S, m, m)[b, s], gref["T"]) < RTOL
+
+
+def test_invalid_requests_raise():
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KfbError
+
+    bk = BatchedKalman("standard", 10, 2, 1, 1, n_draws=4)
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device="cuda")  # noqa: E731
+    with pytest.raises(ValueError):
+        bk.forward(z(10, 1), z(3, 2), z(4, 2, 2), z(2, 2), z(1, 2), z(2, 1), z(1, 1), z(1, 1))  # a0 batch 3 != 4
+    with pytest.raises(TypeError):
+        bk.forward(z(10, 1).float(), z(2), z(2, 2), z(2, 2), z(1, 2), z(2, 1), z(1, 1), z(1, 1))
+    with pytest.raises(RuntimeError, match="save_for_backward"):
+        bk.backward()
+    with pytest.raises(KfbError, match="invalid argument"):
+        BatchedKalman("single", 10, 2, 2, 1, n_draws=1).forward(z(10, 2), z(2), z(2, 2), z(2, 2), z(2, 2), z(2, 1),
+                                                                z(2, 2), z(1, 1))
