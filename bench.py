@@ -210,7 +210,10 @@ def main():
         logp, grad = model.logp_and_grad(th)
         packed = pack_logp_grad(logp, grad)
         full = gather_logp_grad(packed, n_total) if world > 1 else packed
-        out_h.copy_(full, non_blocking=True)
+        if rank == 0:
+            out_h.copy_(full, non_blocking=True)          # the job's result: every draw's (logp, grad) on the host
+        else:
+            out_h[:B].copy_(packed, non_blocking=True)    # other ranks only read back their own shard
         torch.cuda.current_stream().synchronize()  # the caller needs the numbers on the host
         return out_h
 
@@ -296,7 +299,8 @@ def main():
                        "parallelism": f"draws sharded x{world}, all-gather of [B,{1 + spec.n_theta}] f64" if world > 1 else "1 GPU",
                        "draws_with_info": bad},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(theta_h.numel() * 8 * world), "d2h_bytes_per_step": int(out_h.numel() * 8)},
+                    "h2d_bytes_per_step": int(theta_h.numel() * 8 * world),
+                    "d2h_bytes_per_step": int(out_h.numel() * 8 + (world - 1) * B * (1 + spec.n_theta) * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,MK_STD,2> (adjoint recursion; the longest kernel)",
