@@ -59,9 +59,10 @@ class KalmanFilterOp(Op):
     def make_node(self, *inputs):
         _require()
         inputs = [pt.as_tensor_variable(x) for x in inputs]
-        f64 = "float64"
-        outs = [pt.tensor(dtype=f64, shape=(None, None, None)) for _ in range(4)]
-        outs += [pt.tensor(dtype=f64, shape=()), pt.tensor(dtype=f64, shape=(None,))]
+        from pytensor.tensor.type import TensorType
+
+        outs = [TensorType("float64", shape=(None, None, None))() for _ in range(4)]
+        outs += [TensorType("float64", shape=())(), TensorType("float64", shape=(None,))()]
         return Apply(self, inputs, outs)
 
     def infer_shape(self, fgraph, node, shapes):
