@@ -179,3 +179,16 @@ def test_trend_seasonal_k30_steady_vs_standard():
             ll, gr = om.logp_and_grad_theta(mats, theta[b], y[:, :, None], kind)
             assert abs(lp[b] - ll) <= 1e-8 * abs(ll)
             assert np.abs(g[b] - gr).max() <= gtol * np.abs(gr).max(), (kind, g[b], gr)
+
+
+def test_waves_match_single_pass():
+    from pymc_statespace_b200.logp import KalmanLogp, logp_and_grad_in_waves
+    from pymc_statespace_b200.synthetic import arma11_workload
+
+    B, n = 1000, 200
+    spec, y, theta = arma11_workload(B, n)
+    th = torch.as_tensor(theta, device="cuda")
+    lp, g = KalmanLogp(spec, y, n_draws=B).logp_and_grad(th)
+    per_draw = ((n - 1) * 5 + 16 + 64) * 8
+    lp2, g2, info = logp_and_grad_in_waves(spec, y, th, max_workspace_bytes=per_draw * 300)  # 4 waves (300,300,300,100)
+    assert torch.equal(lp, lp2) and torch.equal(g, g2) and int(info.abs().sum()) == 0
