@@ -21,6 +21,7 @@ coopT_launch_fn coopT_launcher_m5(int p, int mk);
 coopT_launch_fn coopT_launcher_m6(int p, int mk);
 coopT_launch_fn coopT_launcher_m7(int p, int mk);
 coopT_launch_fn coopT_launcher_m8(int p, int mk);
+coopT_launch_fn coopT_launcher_m30(int p, int mk);
 
 coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
   switch (m) {
@@ -28,6 +29,7 @@ coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
     case 6: return coopT_launcher_m6(p, mk);
     case 7: return coopT_launcher_m7(p, mk);
     case 8: return coopT_launcher_m8(p, mk);
+    case 30: return coopT_launcher_m30(p, mk);
     default: return nullptr;
   }
 }

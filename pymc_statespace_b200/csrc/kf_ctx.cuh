@@ -251,6 +251,7 @@ struct CoopCtxT {
   unsigned mask_;
   double* arena;
   int off;
+  double* red;  // G_ > 32 only: 34 doubles of scratch for block-wide reductions
   template <int SZ>
   KFB_HD static constexpr int size_of() {
     return SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : KT;
@@ -270,19 +271,35 @@ struct CoopCtxT {
   KFB_HD int lane() const { return lane_; }
   KFB_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    __syncwarp(mask_);
+    if (G_ <= 32) __syncwarp(mask_);
+    else __syncthreads();
 #endif
   }
   KFB_HD double reduce_max(double v) const {
 #if defined(__CUDA_ARCH__)
+    if (G_ <= 32) {
 #pragma unroll
-    for (int o = G_ / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask_, v, o, G_));
+      for (int o = G_ / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask_, v, o, G_));
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      __syncthreads();
+      if ((lane_ & 31) == 0) red[lane_ >> 5] = v;
+      __syncthreads();
+      v = red[0];
+#pragma unroll
+      for (int w = 1; w < (G_ >> 5); ++w) v = fmax(v, red[w]);
+    }
 #endif
     return v;
   }
   KFB_HD bool all_ok(bool v) const {
 #if defined(__CUDA_ARCH__)
-    return __shfl_sync(mask_, (int)v, 0, G_) != 0;
+    if (G_ <= 32) return __shfl_sync(mask_, (int)v, 0, G_) != 0;
+    __syncthreads();
+    if (lane_ == 0) red[33] = v ? 1.0 : 0.0;
+    __syncthreads();
+    return red[33] != 0.0;
 #else
     return v;
 #endif
@@ -310,7 +327,58 @@ struct CoopCtxT {
 template <bool TA, bool TB, int MODE, int M, int P, int G_, class TC, class TAa, class TBb>
 KFB_HD void gemm(CoopCtxT<M, P, G_>& x, TC& C, const TAa& A, const TBb& B, int r, int kk, int c) {
   constexpr int CMAX = (M > P ? M : P);
-  if (r <= G_) {
+  if (G_ > 32) {
+    // one CTA per unit: 2x2 register tiles, fully unrolled k loop with constant shared-memory offsets
+    const int tr = (r + 1) >> 1, tc = (c + 1) >> 1;
+    const double* Ap = &A[0];
+    const double* Bp = &B[0];
+#pragma unroll
+    for (int tile = x.lane(); tile < tr * tc; tile += G_) {
+      const int ti = tile / tc, tj = tile - ti * tc;
+      const int i0 = 2 * ti, j0 = 2 * tj;
+      const bool i1 = (i0 + 1 < r), j1 = (j0 + 1 < c);
+      const int i1x = i1 ? i0 + 1 : i0, j1x = j1 ? j0 + 1 : j0;
+      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+      if (MODE != 0) {
+        s00 = C[i0 * c + j0];
+        s01 = C[i0 * c + j1x];
+        s10 = C[i1x * c + j0];
+        s11 = C[i1x * c + j1x];
+      }
+      const double* a0p = Ap + (TA ? i0 : i0 * kk);
+      const double* a1p = Ap + (TA ? i1x : i1x * kk);
+      const double* b0p = Bp + (TB ? j0 * kk : j0);
+      const double* b1p = Bp + (TB ? j1x * kk : j1x);
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < kk) {
+          double a0 = a0p[TA ? k * r : k];
+          double a1 = a1p[TA ? k * r : k];
+          if (MODE == 2) { a0 = -a0; a1 = -a1; }
+          double b0, b1;
+#if defined(__CUDA_ARCH__)
+          if (!TB && (c % 2 == 0)) {
+            const double2 t = *reinterpret_cast<const double2*>(b0p + k * c);
+            b0 = t.x;
+            b1 = t.y;
+          } else
+#endif
+          {
+            b0 = b0p[TB ? k : k * c];
+            b1 = b1p[TB ? k : k * c];
+          }
+          s00 = kf_fma(a0, b0, s00);
+          s01 = kf_fma(a0, b1, s01);
+          s10 = kf_fma(a1, b0, s10);
+          s11 = kf_fma(a1, b1, s11);
+        }
+      }
+      C[i0 * c + j0] = s00;
+      if (j1) C[i0 * c + j0 + 1] = s01;
+      if (i1) C[(i0 + 1) * c + j0] = s10;
+      if (i1 && j1) C[(i0 + 1) * c + j0 + 1] = s11;
+    }
+  } else if (r <= G_) {
     const int i = x.lane();
     if (i < r) {
       double acc[CMAX];

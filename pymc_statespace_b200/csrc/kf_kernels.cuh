@@ -111,16 +111,23 @@ __global__ void __launch_bounds__(WARP ? 128 : 256, WARP ? 4 : 2) kf_coop_kernel
 
 // Sub-warp cooperative kernel with compile-time dims: G lanes per unit, 128 threads per CTA.
 template <int M, int P, int G, int MK, int MODE>
-__global__ void __launch_bounds__(128) kf_coopT_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
+__global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
+    kf_coopT_kernel(const __grid_constant__ KfArgs A, int arena_doubles) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int BLOCK = G > 128 ? G : 128;
   const int group = threadIdx.x / G;
-  const long long u = (long long)blockIdx.x * (128 / G) + group;
+  const long long u = (long long)blockIdx.x * (BLOCK / G) + group;
   if (u >= A.U) return;
   CoopCtxT<M, P, G> x;
   x.lane_ = threadIdx.x % G;
   x.mask_ = __activemask();
   x.arena = kf_dyn_smem + (size_t)group * arena_doubles;
   x.off = 0;
+  x.red = nullptr;
+  if (G > 32) {
+    x.red = x.arena;
+    x.off = 34;
+  }
   run_unit<MK, MODE>(x, A, u);
   if (x.off > arena_doubles) __trap();  // arena accounting (coop_arena_doubles + slack) out of date
 }
