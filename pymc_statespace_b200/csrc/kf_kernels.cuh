@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
   x.arena = kf_dyn_smem + (size_t)group * arena_doubles;
   x.off = 0;
   x.red = nullptr;
+  x.group_ = group;
   if (G > 32) {
     x.red = x.arena;
     x.off = 34;
