@@ -1,6 +1,4 @@
 // kf_coop.cu - cooperative (shared-memory) kernels: any (k_states, k_endog), time-varying matrices.
-#include <cstdlib>
-
 #include "kf_kernels.cuh"
 
 namespace kfb {
@@ -42,16 +40,14 @@ cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s) {
   const size_t arena_bytes = (size_t)arena * sizeof(double);
   const size_t smem_max = 227 * 1024;
   if (arena_bytes > smem_max) return cudaErrorInvalidConfiguration;
-  const char* dbg = std::getenv("KFB_DEBUG_COOP");  // debugging aid: "warp" | "cta128"
-  const bool force_warp = dbg && dbg[0] == 'w' && arena_bytes * 4 <= smem_max;
-  if (force_warp || (arena_bytes * 4 <= smem_max && A.m < 16)) {
+  if (arena_bytes * 4 <= smem_max && A.m < 16) {
     int warps = 4;
     // more warps per CTA only helps when the arena is tiny; keep CTAs small so many are resident
     const int block = warps * 32;
     const unsigned grid = (unsigned)((A.U + warps - 1) / warps);
     return launch_coop_mode<true>(A, bwd, arena, block, grid, arena_bytes * warps, s);
   }
-  const int block = (dbg && dbg[0] == 'c') ? 128 : 256;
+  const int block = 256;
   return launch_coop_mode<false>(A, bwd, arena, block, (unsigned)A.U, arena_bytes, s);
 }
 

@@ -80,9 +80,7 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   const int fwd_used = x.off;
   if (fwd_used > coop_arena_doubles(m, p, false)) return 3;
   if (do_bwd) {
-    // run forward again (tape) + backward from a fresh arena
-    x.off = 0;
-    std::vector<double> arena2((size_t)cap);
+    x.off = 0;  // the adjoint re-uses the arena; the tape written by the forward pass lives in A.tape
     KfArgs B = A;
     B.loglik = nullptr; B.ll_obs = nullptr; B.fs = B.ps = B.fc = B.pc = nullptr; B.info = nullptr;
     if (A.math_kind == MK_STD) { if (g_pred) backward_unit_pred<MK_STD>(x, B, 0); else backward_unit<MK_STD>(x, B, 0); }

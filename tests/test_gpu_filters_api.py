@@ -201,3 +201,37 @@ def test_smoother_nile_and_batched():
             tol = 1e-8 if m < 10 else 1e-6
             assert rel_err(ss[b].cpu().numpy(), rs[..., 0]) < tol
             assert rel_err(sc[b].cpu().numpy(), rc) < tol
+
+
+def test_pytensor_op_perform_paths_without_pytensor():
+    """PyTensor is not installable here, but the numeric halves of the adapter (KalmanFilterOp.perform and
+    KalmanFilterGradOp.perform: numpy in, numpy out, argument wiring incl. optional c / d) need no PyTensor at all."""
+    from pymc_statespace_b200.pytensor_op import KalmanFilterGradOp, KalmanFilterOp
+
+    rng = np.random.default_rng(17)
+    args = random_system(rng, 3, 2, 2, 15, n_missing=2)
+    c, d = rng.normal(size=(3, 1)), rng.normal(size=(2, 1))
+    for kind, has_c, has_d in (("standard", True, True), ("univariate", False, True), ("cholesky", False, False)):
+        strict = kind != "cholesky"
+        inputs = list(args) + ([c] if has_c else []) + ([d] if has_d else [])
+        op = KalmanFilterOp(kind, strict, has_c, has_d)
+        storage = [[None] for _ in range(6)]
+        op.perform(None, inputs, storage)
+        ref = kn.kalman_filter(kind, *args, c=c if has_c else None, d=d if has_d else None, strict_reference=strict)
+        for s, want in zip(storage, ref):
+            np.testing.assert_allclose(s[0], want, rtol=1e-8, atol=1e-10)
+        assert storage[4][0].shape == () and storage[5][0].shape == (15,)
+        w = rng.normal(size=15)
+        gop = KalmanFilterGradOp(kind, strict, has_c, has_d)
+        gstorage = [[None] for _ in range(len(inputs) - 1)]
+        gop.perform(None, inputs + [np.asarray(0.5), w], gstorage)
+        _, g1 = kt.loglik_and_grads(kind, *args, c=c if has_c else None, d=d if has_d else None, strict_reference=strict)
+        _, g2 = kt.loglik_and_grads(kind, *args, c=c if has_c else None, d=d if has_d else None, strict_reference=strict,
+                                    g_ll_obs=w)
+        names = ["a0", "P0", "T", "Z", "R", "H", "Q"] + (["c"] if has_c else []) + (["d"] if has_d else [])
+        for s, name, x in zip(gstorage, names, inputs[1:]):
+            want = 0.5 * g1[name] + g2[name]
+            assert s[0].shape == np.shape(x)
+            if kind == "cholesky" and name in ("P0", "H"):
+                continue  # gauge of the symmetric inputs differs for the Cholesky-based filter (DESIGN.md)
+            assert rel_err(s[0], want) < 1e-8, (kind, name)
