@@ -157,6 +157,22 @@ kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32
                                 const double *gdst, const int32_t *src_idx, const int32_t *dst_idx,
                                 double *gtheta, void *stream);
 
+/* Batched simulation helpers (next row f4, not on the logp/grad path): reference pymc_statespace/utils/simulation.py.
+ * The standard-normal draws are INPUTS (z_*), so the kernels are deterministic.
+ * kfb_simulate = simulate_statespace (:29-62) for n_draws * sims_per_draw trajectories: z_state[S,n,r], z_obs[S,n,p]
+ *   -> states[S,n,m], obs[S,n,p] (S = n_draws*sims_per_draw; x0[n_draws,m] may be NULL; info[S] = 1 if Q or H is
+ *   not positive definite; H identically zero = no observation noise, as in the reference).
+ * kfb_mvn_draws = conditional_simulation / numba_mvn_draws (:8-26): out[s,t,:] = mus[u,t,:] + chol(covs[u,t] +
+ *   jitter[s] I) z[s,t,:], u = s / sims_per_unit; info[S] must be zero-initialised (receives t+1 of a failing block). */
+kfb_status kfb_simulate(int64_t n_draws, int64_t sims_per_draw, int32_t n, int32_t m, int32_t p, int32_t r,
+                        const double *T, int64_t T_bs, const double *Z, int64_t Z_bs, const double *R, int64_t R_bs,
+                        const double *H, int64_t H_bs, const double *Q, int64_t Q_bs, const double *x0, int64_t x0_bs,
+                        const double *z_state, const double *z_obs, double *states, double *obs, int32_t *info,
+                        void *stream);
+kfb_status kfb_mvn_draws(int64_t n_units, int64_t sims_per_unit, int32_t n, int32_t k, const double *mus,
+                         const double *covs, const double *z, const double *jitter, double *out, int32_t *info,
+                         void *stream);
+
 /* FP64 roofline denominator: `iters` dependent-chain DFMA rounds on every SM.  Returns through
  * h_flops the number of floating-point operations the launch executes (2 per FMA); the caller
  * times it with CUDA events.  sink[>= 1] receives a checksum so the work cannot be elided. */

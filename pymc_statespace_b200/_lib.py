@@ -69,6 +69,9 @@ EXPORTS = {
                                        _vp, _vp, _vp]),
     "kfb_scatter_forward": (_c_i32, [_c_i64, _c_i32, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kfb_scatter_backward": (_c_i32, [_c_i64, _c_i32, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp]),
+    "kfb_simulate": (_c_i32, [_c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64,
+                              _vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kfb_mvn_draws": (_c_i32, [_c_i64, _c_i64, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kfb_fp64_peak": (_c_i32, [_c_i32, _c_i32, _c_i32, _vp, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

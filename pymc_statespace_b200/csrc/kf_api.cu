@@ -330,6 +330,30 @@ kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);
 }
 
+kfb_status kfb_simulate(int64_t n_draws, int64_t sims_per_draw, int32_t n, int32_t m, int32_t p, int32_t r, const double* T,
+                        int64_t T_bs, const double* Z, int64_t Z_bs, const double* R, int64_t R_bs, const double* H,
+                        int64_t H_bs, const double* Q, int64_t Q_bs, const double* x0, int64_t x0_bs,
+                        const double* z_state, const double* z_obs, double* states, double* obs, int32_t* info,
+                        void* stream) {
+  if (n_draws <= 0 || sims_per_draw <= 0 || n <= 0 || m <= 0 || p <= 0 || r <= 0 || !T || !Z || !R || !H || !Q || !z_state ||
+      !z_obs || !states || !obs)
+    return KFB_ERR_INVALID_ARG;
+  if (m > 32 || p > 32 || r > 32) return KFB_ERR_UNSUPPORTED;
+  cudaError_t e = launch_simulate(n_draws * sims_per_draw, sims_per_draw, n, m, p, r, MatArg{T, T_bs, 0}, MatArg{Z, Z_bs, 0},
+                                  MatArg{R, R_bs, 0}, MatArg{H, H_bs, 0}, MatArg{Q, Q_bs, 0}, x0, x0_bs, z_state, z_obs,
+                                  states, obs, info, (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_mvn_draws(int64_t n_units, int64_t sims_per_unit, int32_t n, int32_t k, const double* mus, const double* covs,
+                         const double* z, const double* jitter, double* out, int32_t* info, void* stream) {
+  if (n_units <= 0 || sims_per_unit <= 0 || n <= 0 || k <= 0 || !mus || !covs || !z || !out) return KFB_ERR_INVALID_ARG;
+  if (k > 32) return KFB_ERR_UNSUPPORTED;
+  cudaError_t e = launch_mvn_draws(n_units * sims_per_unit, sims_per_unit, n, k, mus, covs, z, jitter, out, info,
+                                   (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
 kfb_status kfb_fp64_peak(int32_t iters, int32_t blocks, int32_t threads, double* sink, double* h_flops, void* stream) {
   if (iters <= 0 || blocks <= 0 || threads <= 0 || threads > 1024 || !sink) return KFB_ERR_INVALID_ARG;
   cudaError_t e = launch_fp64_peak(iters, blocks, threads, sink, (cudaStream_t)stream);

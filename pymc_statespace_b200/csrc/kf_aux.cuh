@@ -18,5 +18,10 @@ cudaError_t launch_scatter_forward(long long B, int n_theta, int block, int n_ma
                                    cudaStream_t s);
 cudaError_t launch_scatter_backward(long long B, int n_theta, int block, int n_map, const double* gdst,
                                     const int* src_idx, const int* dst_idx, double* gtheta, cudaStream_t s);
+cudaError_t launch_simulate(long long n_sims, long long sims_per_draw, int n, int m, int p, int r, MatArg T, MatArg Z,
+                            MatArg R, MatArg H, MatArg Q, const double* x0, long long x0_bs, const double* z_state,
+                            const double* z_obs, double* states, double* obs, int* info, cudaStream_t s);
+cudaError_t launch_mvn_draws(long long n_sims, long long sims_per_unit, int n, int k, const double* mus, const double* covs,
+                             const double* z, const double* jitter, double* out, int* info, cudaStream_t s);
 cudaError_t launch_fp64_peak(int iters, int blocks, int threads, double* sink, cudaStream_t s);
 }  // namespace kfb
