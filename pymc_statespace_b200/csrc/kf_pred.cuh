@@ -244,6 +244,9 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
   typename X::template Buf<SZ_TAPE> nxt(x);
   typename X::TapeReader rd(x, A, u);
+  // Cotangents nobody asked for are not accumulated (every reference model has a constant design matrix, so Z-bar -
+  // 2 m^2 p + m p^2 multiply-adds per step - is never needed at theta level).  Uniform run-time branches.
+  const bool need_Z = (A.gZ != nullptr), need_H = (A.gH != nullptr) || (MK == MK_STEADY);
 
   // ---- inputs of step t (tape entries are consumed in strictly descending order)
   auto prepare = [&](int t, StepSet<X>& S) {
@@ -323,8 +326,9 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
         for (int k = 0; k < m; ++k) s = kf_fma(-Lb[i * m + k], prm.Z[j * m + k], s);  // - Lb Z^T
         Kb[idx] = s;
       }
-      gemm<true, false, 1>(x, Hb, tmp.Kp, PK, p, m, p);        // Hb += Kp^T Ps Kp
-      gemm<true, false, 2>(x, Zb, tmp.Kp, Lb, p, m, m);        // Zb -= Kp^T Lb
+      x.sync();  // Kb is read across lanes below
+      if (need_H) gemm<true, false, 1>(x, Hb, tmp.Kp, PK, p, m, p);  // Hb += Kp^T Ps Kp
+      if (need_Z) gemm<true, false, 2>(x, Zb, tmp.Kp, Lb, p, m, m);  // Zb -= Kp^T Lb
       if (MK == MK_STEADY) {
         KFB_FOR(i, p) {
           double s = 0.0;
@@ -363,7 +367,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       gemm<false, true, 1>(x, Tb, TMb, tmp.Mm, m, p, m);       // Tb += TMb Mm^T
       gemm<true, false, 0>(x, Mb, prm.T, TMb, m, m, p);        // Mb = T^T TMb
       gemm<true, false, 1>(x, Mb, prm.Z, Fb, m, p, p);         //    + Z^T Fb
-      KFB_FOR(idx, p * m) {                                    // Zb += Fb Mm^T + Mb^T P - vb a^T
+      if (need_Z) KFB_FOR(idx, p * m) {                        // Zb += Fb Mm^T + Mb^T P - vb a^T
         const int i = x.div_m(idx), j = idx - i * m;
         double s = kf_fma(-vb[i], a[j], Zb[idx]);
 #pragma unroll
@@ -372,7 +376,7 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
         for (int k = 0; k < m; ++k) s = kf_fma(Mb[k * p + i], P[k * m + j], s);
         Zb[idx] = s;
       }
-      KFB_FOR(idx, p * p) Hb[idx] += Fb[idx];
+      if (need_H) KFB_FOR(idx, p * p) Hb[idx] += Fb[idx];
       gemm<false, false, 1>(x, Pb, Mb, prm.Z, m, p, m);        // Pb += Mb Z
       KFB_FOR(i, m) {                                          // ab = T^T ab - Z^T vb
         double s = abn[i];
