@@ -278,6 +278,7 @@ def main():
             pass
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp64_peak = fp64_peak_tflops(dev)
+        fp64_peak_distinct = fp64_peak_tflops(dev, distinct_operands=True)
         traffic = {}
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this exact workload
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -313,7 +314,7 @@ def main():
                                  "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak,
                                  "traffic": traffic.get("forward"), "ms_per_launch": ms_fwd,
                                  "algorithmic_bytes_per_launch": tape_bytes},
-            "fp64": {"peak_tflops_measured": fp64_peak, "achieved_tflops": ALG_FLOPS_PER_STEP * steps_per_eval /
+            "fp64": {"peak_tflops_measured": fp64_peak, "peak_tflops_distinct_operands": fp64_peak_distinct, "achieved_tflops": ALG_FLOPS_PER_STEP * steps_per_eval /
                      ((ms_fwd + ms_bwd) * 1e-3) / 1e12,
                      "frac": ALG_FLOPS_PER_STEP * steps_per_eval / ((ms_fwd + ms_bwd) * 1e-3) / 1e12 / fp64_peak,
                      "flops_per_step": ALG_FLOPS_PER_STEP},

@@ -179,6 +179,11 @@ kfb_status kfb_mvn_draws(int64_t n_units, int64_t sims_per_unit, int32_t n, int3
 kfb_status kfb_fp64_peak(int32_t iters, int32_t blocks, int32_t threads, double *sink,
                          double *h_flops, void *stream);
 
+/* Same probe, but every FMA reads three DISTINCT registers (no operand reuse) - the rate dense small-matrix code can
+ * actually sustain through the register file. */
+kfb_status kfb_fp64_peak_distinct(int32_t iters, int32_t blocks, int32_t threads, double *sink, double *h_flops,
+                                  void *stream);
+
 /* How many kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t kfb_launch_count(void);
 

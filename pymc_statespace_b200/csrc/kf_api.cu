@@ -354,6 +354,14 @@ kfb_status kfb_mvn_draws(int64_t n_units, int64_t sims_per_unit, int32_t n, int3
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);
 }
 
+kfb_status kfb_fp64_peak_distinct(int32_t iters, int32_t blocks, int32_t threads, double* sink, double* h_flops,
+                                  void* stream) {
+  if (iters <= 0 || blocks <= 0 || threads <= 0 || threads > 1024 || !sink) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_fp64_peak_distinct(iters, blocks, threads, sink, (cudaStream_t)stream);
+  if (h_flops) *h_flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
 kfb_status kfb_fp64_peak(int32_t iters, int32_t blocks, int32_t threads, double* sink, double* h_flops, void* stream) {
   if (iters <= 0 || blocks <= 0 || threads <= 0 || threads > 1024 || !sink) return KFB_ERR_INVALID_ARG;
   cudaError_t e = launch_fp64_peak(iters, blocks, threads, sink, (cudaStream_t)stream);

@@ -538,6 +538,35 @@ __global__ void fp64_peak_kernel(int iters, double* __restrict__ sink) {
   if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
 }
 
+// Same probe with three DISTINCT register operands per FMA (no operand-reuse): what real matrix code looks like to
+// the register file.  8 accumulators x (own multiplier, own addend).
+__global__ void fp64_peak_distinct_kernel(int iters, double* __restrict__ sink) {
+  double a[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = threadIdx.x * 1e-9 + i;
+    b[i] = 1.0 + 1e-7 * (i + 1);
+    c[i] = 1e-9 * (i + 1);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b[(i + k) & 7], c[(i + 3 * k) & 7]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_fp64_peak_distinct(int iters, int blocks, int threads, double* sink, cudaStream_t s) {
+  fp64_peak_distinct_kernel<<<blocks, threads, 0, s>>>(iters, sink);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fp64_peak(int iters, int blocks, int threads, double* sink, cudaStream_t s) {
   fp64_peak_kernel<<<blocks, threads, 0, s>>>(iters, sink);
   count_launch();

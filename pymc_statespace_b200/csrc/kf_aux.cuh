@@ -23,5 +23,6 @@ cudaError_t launch_simulate(long long n_sims, long long sims_per_draw, int n, in
                             const double* z_obs, double* states, double* obs, int* info, cudaStream_t s);
 cudaError_t launch_mvn_draws(long long n_sims, long long sims_per_unit, int n, int k, const double* mus, const double* covs,
                              const double* z, const double* jitter, double* out, int* info, cudaStream_t s);
+cudaError_t launch_fp64_peak_distinct(int iters, int blocks, int threads, double* sink, cudaStream_t s);
 cudaError_t launch_fp64_peak(int iters, int blocks, int threads, double* sink, cudaStream_t s);
 }  // namespace kfb

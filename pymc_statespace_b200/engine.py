@@ -248,9 +248,11 @@ def lyapunov_backward(A, R, Q, X, Xbar, Abar, Rbar, Qbar):
               "kfb_lyapunov_backward")
 
 
-def fp64_peak_tflops(device="cuda", iters=4096, repeats=5):
-    """Measured FP64 FMA throughput (TFLOP/s) of this GPU: the "FP64 roofline" denominator."""
+def fp64_peak_tflops(device="cuda", iters=4096, repeats=5, distinct_operands=False, warps_per_smsp=16):
+    """Measured FP64 FMA throughput (TFLOP/s) of this GPU: the "FP64 roofline" denominator.
+    ``distinct_operands=True``: every FMA reads three different registers (no operand reuse)."""
     lib = load()
+    fn = lib.kfb_fp64_peak_distinct if distinct_operands else lib.kfb_fp64_peak
     dev = torch.device(device)
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     flops = ctypes.c_double(0)
@@ -260,8 +262,8 @@ def fp64_peak_tflops(device="cuda", iters=4096, repeats=5):
         for i in range(repeats + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            check(lib.kfb_fp64_peak(iters, sms * 8, 256, _ptr(sink), ctypes.byref(flops), _stream_ptr(dev)),
-                  "kfb_fp64_peak")
+            blocks = max(1, (sms * 4 * warps_per_smsp * 32) // 256)
+            check(fn(iters, blocks, 256, _ptr(sink), ctypes.byref(flops), _stream_ptr(dev)), "kfb_fp64_peak")
             e1.record()
             e1.synchronize()
             if i:
