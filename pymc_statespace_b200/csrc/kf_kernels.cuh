@@ -5,6 +5,7 @@
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
 #include "kf_pred.cuh"
+#include "kf_rows.cuh"
 #include "kf_smooth.cuh"
 
 namespace kfb {
@@ -131,6 +132,20 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
   }
   run_unit<MK, MODE>(x, A, u);
   if (x.off > arena_doubles) __trap();  // arena accounting (coop_arena_doubles + slack) out of date
+}
+
+// Fused row-per-lane programs (kf_rows.cuh): 8 lanes per unit, 16 units per 128-thread CTA.  BWD = adjoint.
+template <int M, int P, bool BWD>
+__global__ void __launch_bounds__(128) kf_rows_kernel(const __grid_constant__ KfArgs A) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int per_unit = BWD ? RowsLayout<M, P>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
+  const int group = threadIdx.x >> 3;
+  const long long u = (long long)blockIdx.x * 16 + group;
+  if (u >= A.U) return;
+  const unsigned mask = __activemask();
+  double* sm = kf_dyn_smem + (size_t)group * per_unit;
+  if (BWD) rows_backward<M, P>(A, u, sm, threadIdx.x & 7, mask);
+  else rows_forward<M, P>(A, u, sm, threadIdx.x & 7, mask);
 }
 
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----
