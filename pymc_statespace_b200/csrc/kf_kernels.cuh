@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
 
 // Fused row-per-lane programs (kf_rows.cuh): 8 lanes per unit, 16 units per 128-thread CTA.  BWD = adjoint.
 template <int M, int P, bool BWD>
-__global__ void __launch_bounds__(128) kf_rows_kernel(const __grid_constant__ KfArgs A) {
+__global__ void __launch_bounds__(128, BWD ? 3 : 4) kf_rows_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   constexpr int per_unit = BWD ? RowsLayout<M, P>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
   const int group = threadIdx.x >> 3;
