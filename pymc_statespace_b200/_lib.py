@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkfb200.so")
+LIB_PATH = os.environ.get("KFB_LIB") or os.path.join(_HERE, "libkfb200.so")  # KFB_LIB: developer override (A/B builds)
 
 KFB_STANDARD, KFB_UNIVARIATE, KFB_STEADY_STATE, KFB_SINGLE, KFB_CHOLESKY = range(5)
 FILTER_KIND = {

@@ -134,18 +134,26 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
   if (x.off > arena_doubles) __trap();  // arena accounting (coop_arena_doubles + slack) out of date
 }
 
-// Fused row-per-lane programs (kf_rows.cuh): 8 lanes per unit, 16 units per 128-thread CTA.  BWD = adjoint.
-template <int M, int P, bool BWD>
-__global__ void __launch_bounds__(128, BWD ? 3 : 4) kf_rows_kernel(const __grid_constant__ KfArgs A) {
+// Fused row-block-per-lane programs (kf_rows.cuh): G lanes per unit, 32/G units per warp, blockDim.x/32 warps per CTA.
+// BWD = adjoint.  Lanes beyond the last whole group of a warp shadow the warp's first unit without owning rows.
+template <int M, int P, int G, bool BWD>
+__global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? 3 : 4)) kf_rows_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   constexpr int per_unit = BWD ? RowsLayout<M, P>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
-  const int group = threadIdx.x >> 3;
-  const long long u = (long long)blockIdx.x * 16 + group;
+  constexpr int UPW = RowsCfg<M, P, G>::UPW;
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int grp = lane32 / G, l = lane32 - grp * G;
+  if (grp >= UPW) {
+    grp = 0;
+    l = G;
+  }
+  const int slot = warp * UPW + grp;
+  const long long u = (long long)blockIdx.x * ((blockDim.x >> 5) * UPW) + slot;
   if (u >= A.U) return;
   const unsigned mask = __activemask();
-  double* sm = kf_dyn_smem + (size_t)group * per_unit;
-  if (BWD) rows_backward<M, P>(A, u, sm, threadIdx.x & 7, mask);
-  else rows_forward<M, P>(A, u, sm, threadIdx.x & 7, mask);
+  double* sm = kf_dyn_smem + (size_t)slot * per_unit;
+  if (BWD) rows_backward<M, P, G>(A, u, sm, l, mask);
+  else rows_forward<M, P, G>(A, u, sm, l, mask);
 }
 
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----

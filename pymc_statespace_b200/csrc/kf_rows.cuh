@@ -1,82 +1,139 @@
-// kf_rows.cuh - fused "row per lane" programs for mid-size systems (k_states 5..8, k_endog <= 3, MK_STD).
+// kf_rows.cuh - fused "row block per lane" programs for mid-size systems (k_states 5..8, k_endog <= 3, MK_STD).
 //
-// Same mathematics as kf_pred.cuh (one-step-predictor form and its adjoint) but written directly for the sub-warp
-// mapping instead of through the generic primitive-per-phase abstraction: 8 lanes per unit, lane i owns ROW i of every
-// m x m / m x p quantity.  Everything a lane can compute from its own rows stays in registers; only what OTHER lanes
-// must read goes through shared memory, and the p x p inverse, w = F^-1 v, K^T Kb, v-bar, F-bar are computed redundantly
-// by every lane in registers.  The generic CoopCtxT path needs ~14 (forward) / ~40 (adjoint) warp-synchronised phases
-// per filter step, each paying shared-memory + 32-cycle DFMA latency with only 8-12 warps per SM to hide it; this
-// version needs 5 / 8, uses ~4 KB instead of ~6.4 KB of shared memory per unit (3 instead of 2 CTAs per SM in the
-// adjoint) and keeps the gradient accumulators in registers.
+// Same mathematics as kf_pred.cuh (one-step-predictor form and its adjoint) but written directly for a sub-warp
+// mapping instead of through the generic primitive-per-phase abstraction: G lanes per unit, lane l owns the
+// R = ceil(M / G) ROWS l*R .. l*R+R-1 of every m x m / m x p quantity.  Everything a lane can compute from its own rows
+// stays in registers; only what OTHER lanes must read goes through shared memory, and the p x p inverse, w = F^-1 v,
+// K^T Kb, v-bar, F-bar are computed redundantly by every lane in registers.  The generic CoopCtxT path needs ~14 (forward)
+// / ~40 (adjoint) warp-synchronised phases per filter step; this version needs 5 / 8.
+//
+// Why R > 1: with one row per lane every multiply-add needs one shared-memory operand (the other comes from the lane's
+// registers), and ncu shows the kernels bound by shared-memory wavefronts (90 % / 80 % of the LSU peak, fp64 pipe 32 %,
+// profiles/r1_ncu_rows.md).  With R rows per lane every broadcast operand feeds R multiply-adds and a warp holds 32/G
+// units, so the wavefronts per multiply-add drop by ~R * (8/G).
 // Units of a warp must take identical control flow: shared observation stream, static matrices (enforced by the launcher).
 #pragma once
 #include "kf_core.cuh"
 
 namespace kfb {
 
+template <int M, int P, int G>
+struct RowsCfg {
+  static constexpr int R = (M + G - 1) / G;  // rows per lane
+  static constexpr int UPW = 32 / G;         // units per warp (lanes >= UPW*G idle)
+  static_assert(G >= P && G <= 32, "lanes 0..P-1 own the rows of v, F, Zb, Hb");
+};
+
 template <int M, int P>
 struct RowsLayout {
   static constexpr int MM = M * M, MP = M * P, PP = P * P;
+  static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
   // forward + adjoint share the first block
   static constexpr int T = 0, Z = T + MM, H = Z + MP, Pm = H + PP + (PP & 1), Mm = Pm + MM, Kp = Mm + MP, Lm = Kp + MP,
                        F = Lm + MM, a = F + PP + (PP & 1), v = a + M + (M & 1), END_COMMON = v + P + (P & 1);
   // forward only
-  static constexpr int C = END_COMMON, S2 = C + MM, END_FWD = S2 + MM;
-  // adjoint only
-  static constexpr int Pb = END_COMMON, Ps = Pb + MM, X = Ps + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MP,
-                       Mb = TMb + MP, PK = Mb + MP, ab = PK + MP, tp = ab + M + (M & 1),
-                       END_BWD = tp + M + (M * (M + 1)) / 2 + 1;
-  static constexpr int fwd_doubles = (END_FWD + 1) & ~1, bwd_doubles = (END_BWD + 1) & ~1;
+  static constexpr int S2 = END_COMMON, END_FWD = S2 + MM;
+  // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
+  static constexpr int Pb = END_COMMON, X = Pb + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MP,
+                       Mb = TMb + MP, PK = Mb + MP, ab = PK + MP, tp = ab + M + (M & 1), END_BWD = tp + 2 * KTP;
+  // unit stride == 2 (mod 4) doubles: consecutive units start 16 bytes apart modulo the 128-byte bank row, so the 32/G
+  // units of a warp spread per-lane row / column accesses evenly over the banks (a stride == 0 mod 4 gave 8-way replays)
+  static constexpr int stride(int n) { return ((n + 1) & ~1) + ((((n + 1) & ~1) & 2) ? 0 : 2); }
+  static constexpr int fwd_doubles = stride(END_FWD), bwd_doubles = stride(END_BWD);
 };
+
+// rows owned by lane l: r[q] (may be >= M: inactive), c[q] = clamped index that is always safe to read
+template <int M, int R>
+struct RowIdx {
+  int r[R], c[R];
+  bool a[R];
+  __device__ __forceinline__ explicit RowIdx(int l) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      r[q] = l * R + q;
+      a[q] = r[q] < M;
+      c[q] = a[q] ? r[q] : 0;
+    }
+  }
+};
+
+// out[q] = p[c[q]]: the lane's R consecutive elements of a length-M vector (its block of a COLUMN-indexed access).
+// Two rows per lane and even M: one aligned 16-byte load instead of two 8-byte loads that replay on the same banks.
+template <int M, int R>
+__device__ __forceinline__ void lane_block(const double* p, const RowIdx<M, R>& rw, double (&out)[R]) {
+  if constexpr (R == 2 && (M % 2) == 0) {
+    const double2 v2 = *reinterpret_cast<const double2*>(p + rw.c[0]);
+    out[0] = v2.x;
+    out[1] = v2.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < R; ++q) out[q] = p[rw.c[q]];
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 // Phases A, B, D of a step for an observed row: v, Mm, F | TM | (F^-1, w, quad) Kp, Lm.   Leaves in shared memory:
-// v, Mm, F, Kp, Lm; in registers of lane i: TM row, Kp row, Lm row, and (every lane) Fi, w.
-template <int M, int P>
+// v, Mm, F, Kp, Lm; in registers of the lane: its TM, Kp, Lm rows, and (every lane) Fi, w.
+template <int M, int P, int R>
 struct RowGain {
-  double TM[P], Kp[P], Lm[M], Fi[P * P], w[P], piv[P], quad;
+  double TM[R][P], Kp[R][P], Lm[R][M], Fi[P * P], w[P], piv[P], quad;
   bool ok;
 };
 
-template <int M, int P>
-__device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, double di, int lane, unsigned mask,
-                                          RowGain<M, P>& g) {
+// tr(q, k) = T[row q of this lane][k] (registers in the forward kernel, shared memory in the adjoint)
+// Pr = the lane's rows of the predicted covariance (registers).
+template <int M, int P, int R, class TR>
+__device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, double di, int l, unsigned mask,
+                                          const RowIdx<M, R>& rw, TR tr, const double (&Pr)[R][M], RowGain<M, P, R>& g) {
   using L = RowsLayout<M, P>;
-  const bool act = lane < M;
-  const int i = act ? lane : 0;
-  // ---- phase A: v (lanes < P), Mm row
-  if (lane < P) {
-    double s = yt[lane] - d_sign * di;
+  // ---- phase A: v (lanes < P), Mm rows
+  if (l < P) {
+    double s = yt[l] - d_sign * di;
 #pragma unroll
-    for (int k = 0; k < M; ++k) s = fma(-sm[L::Z + lane * M + k], sm[L::a + k], s);
-    sm[L::v + lane] = s;
+    for (int k = 0; k < M; ++k) s = fma(-sm[L::Z + l * M + k], sm[L::a + k], s);
+    sm[L::v + l] = s;
   }
-  if (act) {
+  {
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      double s = 0.0;
+      double s[R];
 #pragma unroll
-      for (int k = 0; k < M; ++k) s = fma(sm[L::Pm + i * M + k], sm[L::Z + j * M + k], s);
-      sm[L::Mm + i * P + j] = s;
+      for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double z = sm[L::Z + j * M + k];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = fma(Pr[q][k], z, s[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        if (rw.a[q]) sm[L::Mm + rw.r[q] * P + j] = s[q];
     }
   }
   __syncwarp(mask);
-  // ---- phase B: F rows (lanes < P), TM row (registers)
-  if (lane < P) {
+  // ---- phase B: F rows (lanes < P), TM rows (registers)
+  if (l < P) {
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      double s = sm[L::H + lane * P + j];
+      double s = sm[L::H + l * P + j];
 #pragma unroll
-      for (int k = 0; k < M; ++k) s = fma(sm[L::Z + lane * M + k], sm[L::Mm + k * P + j], s);
-      sm[L::F + lane * P + j] = s;
+      for (int k = 0; k < M; ++k) s = fma(sm[L::Z + l * M + k], sm[L::Mm + k * P + j], s);
+      sm[L::F + l * P + j] = s;
     }
   }
 #pragma unroll
   for (int j = 0; j < P; ++j) {
-    double s = 0.0;
+    double s[R];
 #pragma unroll
-    for (int k = 0; k < M; ++k) s = fma(sm[L::T + i * M + k], sm[L::Mm + k * P + j], s);
-    g.TM[j] = s;
+    for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double b = sm[L::Mm + k * P + j];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = fma(tr(q, k), b, s[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) g.TM[q][j] = s[q];
   }
   __syncwarp(mask);
   // ---- phase D: every lane inverts F in registers; Kp, Lm rows
@@ -84,36 +141,47 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
 #pragma unroll
   for (int k = 0; k < P * P; ++k) Fr[k] = sm[L::F + k];
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
-  double q = 0.0;
+  double qd = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], sm[L::v + k], s);
     g.w[j] = s;
-    q = fma(sm[L::v + j], s, q);
+    qd = fma(sm[L::v + j], s, qd);
   }
-  g.quad = q;
+  g.quad = qd;
 #pragma unroll
-  for (int j = 0; j < P; ++j) {
-    double s = 0.0;
+  for (int q = 0; q < R; ++q)
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(g.TM[k], g.Fi[k * P + j], s);
-    g.Kp[j] = s;
-  }
+    for (int j = 0; j < P; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) s = fma(g.TM[q][k], g.Fi[k * P + j], s);
+      g.Kp[q][j] = s;
+    }
 #pragma unroll
   for (int j = 0; j < M; ++j) {
-    double s = sm[L::T + i * M + j];
+    double s[R];
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(-g.Kp[k], sm[L::Z + k * M + j], s);
-    g.Lm[j] = s;
+    for (int q = 0; q < R; ++q) s[q] = tr(q, j);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const double z = sm[L::Z + k * M + j];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = fma(-g.Kp[q][k], z, s[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) g.Lm[q][j] = s[q];
   }
-  if (act) {
 #pragma unroll
-    for (int j = 0; j < P; ++j) sm[L::Kp + i * P + j] = g.Kp[j];
+  for (int q = 0; q < R; ++q)
+    if (rw.a[q]) {
 #pragma unroll
-    for (int j = 0; j < M; ++j) sm[L::Lm + i * M + j] = g.Lm[j];
-  }
+      for (int j = 0; j < P; ++j) sm[L::Kp + rw.r[q] * P + j] = g.Kp[q][j];
+#pragma unroll
+      for (int j = 0; j < M; ++j) sm[L::Lm + rw.r[q] * M + j] = g.Lm[q][j];
+    }
   __syncwarp(mask);
 }
 
@@ -126,122 +194,191 @@ __device__ __forceinline__ int rows_count_missing(const double* yt) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int M, int P>
-__device__ void rows_forward(const KfArgs& A, long long u, double* sm, int lane, unsigned mask) {
+template <int M, int P, int G>
+__device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
   using L = RowsLayout<M, P>;
-  constexpr int KT = M + (M * (M + 1)) / 2;
+  constexpr int R = RowsCfg<M, P, G>::R;
+  constexpr int KT = L::KT;
   const int n = A.n;
   const long long draw = u / A.n_series;
-  const bool act = lane < M;
-  const int i = act ? lane : 0;
+  const RowIdx<M, R> rw(l);
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
   const double* Cp = A.C.p + draw * A.C.bs;
   const double* P0p = A.P0.p + draw * A.P0.bs;
   const double* a0p = A.a0.p + draw * A.a0.bs;
-  for (int k = lane; k < M * M; k += 8) {
-    sm[L::T + k] = Tp[k];
-    sm[L::C + k] = Cp[k];
-    sm[L::Pm + k] = P0p[k];
+  if (l < G) {  // idle lanes of the warp (l == G) shadow a unit without owning anything
+    for (int k = l; k < M * M; k += G) {
+      sm[L::T + k] = Tp[k];
+      sm[L::Pm + k] = P0p[k];
+    }
+    for (int k = l; k < P * M; k += G) sm[L::Z + k] = Zp[k];
+    for (int k = l; k < P * P; k += G) sm[L::H + k] = Hp[k];
   }
-  for (int k = lane; k < P * M; k += 8) sm[L::Z + k] = Zp[k];
-  for (int k = lane; k < P * P; k += 8) sm[L::H + k] = Hp[k];
-  if (act) sm[L::a + i] = a0p[i];
-  const double ci = (act && A.c.p) ? A.c.p[draw * A.c.bs + i] : 0.0;
-  const double di = (lane < P && A.d.p) ? A.d.p[draw * A.d.bs + lane] : 0.0;
+  // static rows the lane owns: registers
+  double Tr[R][M], Cr[R][M], Pr[R][M], ci[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      Tr[q][j] = Tp[rw.c[q] * M + j];
+      Cr[q][j] = Cp[rw.c[q] * M + j];
+      Pr[q][j] = P0p[rw.c[q] * M + j];
+    }
+    ci[q] = (rw.a[q] && A.c.p) ? A.c.p[draw * A.c.bs + rw.r[q]] : 0.0;
+    if (rw.a[q]) sm[L::a + rw.r[q]] = a0p[rw.r[q]];
+  }
+  const double di = (l < P && A.d.p) ? A.d.p[draw * A.d.bs + l] : 0.0;
   __syncwarp(mask);
+  auto tr = [&](int q, int k) { return Tr[q][k]; };
 
   const double* y = A.y.p;
   LogAcc acc;
   double llsum = 0.0;
   int info = 0;
   double* tp = A.tape ? A.tape + u * (long long)(n - 1) * KT : nullptr;
-  RowGain<M, P> g;
+  RowGain<M, P, R> g;
 
   for (int t = 0; t < n; ++t) {
     const double* yt = y + (long long)t * P;
     const int nm = rows_count_missing<P>(yt);
-    double an = ci, S1[M], S2[M];
+    double an[R], S1[R][M], S2[R][M];
+#pragma unroll
+    for (int q = 0; q < R; ++q) an[q] = ci[q];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double ak = sm[L::a + k];
+#pragma unroll
+      for (int q = 0; q < R; ++q) an[q] = fma(Tr[q][k], ak, an[q]);
+    }
     if (nm == 0) {
-      rows_gain<M, P>(sm, yt, A.d_sign, di, lane, mask, g);
+      rows_gain<M, P, R>(sm, yt, A.d_sign, di, l, mask, rw, tr, Pr, g);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll
         for (int k = 0; k < P; ++k) acc.mul(g.piv[k]);
       }
       llsum += -0.5 * (A.ll_const + g.quad);
-      // ---- phase E: a' row, S2 row = C + (L P) L^T + (Kp H) Kp^T
+      // ---- phase E: a' rows, S2 rows = C + (L P) L^T + (Kp H) Kp^T
 #pragma unroll
-      for (int k = 0; k < M; ++k) an = fma(sm[L::T + i * M + k], sm[L::a + k], an);
+      for (int k = 0; k < P; ++k) {
+        const double vk = sm[L::v + k];
 #pragma unroll
-      for (int k = 0; k < P; ++k) an = fma(g.Kp[k], sm[L::v + k], an);
+        for (int q = 0; q < R; ++q) an[q] = fma(g.Kp[q][k], vk, an[q]);
+      }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        double s = 0.0;
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(g.Lm[k], sm[L::Pm + k * M + j], s);
-        S1[j] = s;
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Pm + k * M + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) S1[q][j] = s[q];
       }
-      double KH[P];
+      double KH[R][P];
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        double s = 0.0;
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(g.Kp[k], sm[L::H + k * P + j], s);
-        KH[j] = s;
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::H + k * P + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(g.Kp[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) KH[q][j] = s[q];
       }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        double s = sm[L::C + i * M + j];
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(S1[k], sm[L::Lm + j * M + k], s);
+        for (int q = 0; q < R; ++q) s[q] = Cr[q][j];
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(KH[k], sm[L::Kp + j * P + k], s);
-        S2[j] = s;
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Lm + j * M + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(S1[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::Kp + j * P + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(KH[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) S2[q][j] = s[q];
       }
     } else {
       if (nm != P && info == 0) info = -(t + 1);
 #pragma unroll
-      for (int k = 0; k < M; ++k) an = fma(sm[L::T + i * M + k], sm[L::a + k], an);
-#pragma unroll
       for (int j = 0; j < M; ++j) {
-        double s = 0.0;
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(sm[L::T + i * M + k], sm[L::Pm + k * M + j], s);
-        S1[j] = s;
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Pm + k * M + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(Tr[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) S1[q][j] = s[q];
       }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        double s = sm[L::C + i * M + j];
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(S1[k], sm[L::T + j * M + k], s);
-        S2[j] = s;
+        for (int q = 0; q < R; ++q) s[q] = Cr[q][j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::T + j * M + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(S1[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) S2[q][j] = s[q];
       }
     }
-    if (act) {
 #pragma unroll
-      for (int j = 0; j < M; ++j) sm[L::S2 + i * M + j] = S2[j];
-    }
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) sm[L::S2 + rw.r[q] * M + j] = S2[q][j];
+      }
     __syncwarp(mask);
     // ---- phase F: P' = sym(S2), a' ; tape
-    if (act) {
+    const bool taped = tp && t + 1 < n;
 #pragma unroll
-      for (int j = 0; j < M; ++j) sm[L::Pm + i * M + j] = 0.5 * (S2[j] + sm[L::S2 + j * M + i]);
-      sm[L::a + i] = an;
+    for (int j = 0; j < M; ++j) {
+      double col[R];
+      lane_block<M, R>(sm + L::S2 + j * M, rw, col);
+#pragma unroll
+      for (int q = 0; q < R; ++q) Pr[q][j] = 0.5 * (S2[q][j] + col[q]);
     }
-    __syncwarp(mask);
-    if (tp && t + 1 < n) {
-      if (act) {
-        tp[i] = an;
 #pragma unroll
-        for (int j = 0; j < M; ++j)
-          if (j >= i) tp[M + i * M - (i * (i - 1)) / 2 + (j - i)] = sm[L::Pm + i * M + j];
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+        const int i = rw.r[q];
+        if (taped) tp[i] = an[q];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          sm[L::Pm + i * M + j] = Pr[q][j];
+          if (taped && j >= i) tp[M + i * M - (i * (i - 1)) / 2 + (j - i)] = Pr[q][j];
+        }
+        sm[L::a + i] = an[q];
       }
-      tp += KT;
-    }
+    if (taped) tp += KT;
+    __syncwarp(mask);
   }
-  if (lane == 0) {
+  if (l == 0) {
     double ll = llsum - 0.5 * acc.value();
     if (info != 0) ll = nan("");
     if (A.loglik) A.loglik[u] = ll;
@@ -250,145 +387,270 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int lane,
 }
 
 // ------------------------------------------------------------------------------------------------ adjoint
-template <int M, int P>
-__device__ void rows_backward(const KfArgs& A, long long u, double* sm, int lane, unsigned mask) {
+// Asynchronous copy of one packed tape entry (KT doubles) into shared memory, G lanes cooperating (LDGSTS).
+template <int KT, int G>
+__device__ __forceinline__ void rows_tape_prefetch(double* dst, const double* src, int l) {
+#ifdef __CUDA_ARCH__
+  if (l < G) {
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+    for (int k0 = 0; k0 < KT; k0 += G) {
+      const int k = k0 + l;
+      if (k < KT) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + (unsigned)(k * 8)), "l"(src + k) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+  if (l < G)
+    for (int k = l; k < KT; k += G) dst[k] = src[k];
+#endif
+}
+
+__device__ __forceinline__ void rows_tape_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+template <int M, int P, int G>
+__device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
   using L = RowsLayout<M, P>;
-  constexpr int KT = M + (M * (M + 1)) / 2;
+  constexpr int R = RowsCfg<M, P, G>::R;
+  constexpr int KT = L::KT;
   const int n = A.n;
   const long long draw = u / A.n_series;
-  const bool act = lane < M;
-  const int i = act ? lane : 0;
+  const RowIdx<M, R> rw(l);
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
-  for (int k = lane; k < M * M; k += 8) {
-    sm[L::T + k] = Tp[k];
-    sm[L::Pb + k] = 0.0;
+  const double* tape = A.tape + u * (long long)(n - 1) * KT;  // entry t-1 = predicted moments of step t
+  if (n >= 2) rows_tape_prefetch<KT, G>(sm + L::tp + ((n - 1) & 1) * L::KTP, tape + (long long)(n - 2) * KT, l);
+  if (l < G) {
+    for (int k = l; k < M * M; k += G) {
+      sm[L::T + k] = Tp[k];
+      sm[L::Pb + k] = 0.0;
+    }
+    for (int k = l; k < P * M; k += G) sm[L::Z + k] = Zp[k];
+    for (int k = l; k < P * P; k += G) sm[L::H + k] = Hp[k];
   }
-  for (int k = lane; k < P * M; k += 8) sm[L::Z + k] = Zp[k];
-  for (int k = lane; k < P * P; k += 8) sm[L::H + k] = Hp[k];
-  if (act) sm[L::ab + i] = 0.0;
-  const double di = (lane < P && A.d.p) ? A.d.p[draw * A.d.bs + lane] : 0.0;
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+    if (rw.a[q]) sm[L::ab + rw.r[q]] = 0.0;
+  const double di = (l < P && A.d.p) ? A.d.p[draw * A.d.bs + l] : 0.0;
   __syncwarp(mask);
+  auto tr = [&](int q, int k) { return sm[L::T + rw.c[q] * M + k]; };
 
   const double* y = A.y.p;
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
   const bool need_Z = (A.gZ != nullptr), need_H = (A.gH != nullptr);
-  // gradient accumulators: lane i holds row i (Tb, Cb), lanes < P hold rows of Zb, Hb; element i of cb, db
-  double Tb[M], Cb[M], Zb[M], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
+  // gradient accumulators: the lane's rows of Tb, Cb; lanes < P hold rows of Zb, Hb; elements of cb (rows), db (lane)
+  double Tb[R][M], Cb[R][M], Zb[M], Hb[P], cb[R], db = 0.0;
 #pragma unroll
-  for (int j = 0; j < M; ++j) Tb[j] = Cb[j] = Zb[j] = 0.0;
+  for (int q = 0; q < R; ++q) {
+    cb[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) Tb[q][j] = Cb[q][j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) Zb[j] = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) Hb[j] = 0.0;
-  const double* tp = A.tape + u * (long long)(n - 1) * KT + (long long)(n - 2) * KT;
-  RowGain<M, P> g;
+  RowGain<M, P, R> g;
+  double Pr[R][M];
 
   for (int t = n - 1; t >= 0; --t) {
-    // ---- predicted moments of step t -> shared memory
+    // ---- predicted moments of step t -> shared memory (and the lane's rows of P in registers)
     if (t == 0) {
       const double* P0p = A.P0.p + draw * A.P0.bs;
-      for (int k = lane; k < M * M; k += 8) sm[L::Pm + k] = P0p[k];
-      if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) Pr[q][j] = P0p[rw.c[q] * M + j];
+        if (rw.a[q]) {
+#pragma unroll
+          for (int j = 0; j < M; ++j) sm[L::Pm + rw.r[q] * M + j] = Pr[q][j];
+          sm[L::a + rw.r[q]] = A.a0.p[draw * A.a0.bs + rw.r[q]];
+        }
+      }
     } else {
-      for (int k = lane; k < KT; k += 8) sm[L::tp + k] = tp[k];
-      tp -= KT;
+      rows_tape_wait();
       __syncwarp(mask);
-      if (act) {
-        sm[L::a + i] = sm[L::tp + i];
+      const double* tq = sm + L::tp + (t & 1) * L::KTP;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int i = rw.c[q];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
           const int lo = i < j ? i : j, hi = i < j ? j : i;
-          sm[L::Pm + i * M + j] = sm[L::tp + M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
+          Pr[q][j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
+        }
+        if (rw.a[q]) {
+          sm[L::a + i] = tq[i];
+#pragma unroll
+          for (int j = 0; j < M; ++j) sm[L::Pm + i * M + j] = Pr[q][j];
         }
       }
+      if (t >= 2) rows_tape_prefetch<KT, G>(sm + L::tp + ((t - 1) & 1) * L::KTP, tape + (long long)(t - 2) * KT, l);
     }
     __syncwarp(mask);
     const double* yt = y + (long long)t * P;
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
     const bool observed = (rows_count_missing<P>(yt) == 0);
     if (observed) {
-      rows_gain<M, P>(sm, yt, A.d_sign, di, lane, mask, g);
+      rows_gain<M, P, R>(sm, yt, A.d_sign, di, l, mask, rw, tr, Pr, g);
     } else {
 #pragma unroll
-      for (int j = 0; j < M; ++j) g.Lm[j] = sm[L::T + i * M + j];
-      if (act) {
+      for (int q = 0; q < R; ++q) {
 #pragma unroll
-        for (int j = 0; j < M; ++j) sm[L::Lm + i * M + j] = g.Lm[j];
+        for (int j = 0; j < M; ++j) g.Lm[q][j] = sm[L::T + rw.c[q] * M + j];
+        if (rw.a[q]) {
+#pragma unroll
+          for (int j = 0; j < M; ++j) sm[L::Lm + rw.r[q] * M + j] = g.Lm[q][j];
+        }
       }
       __syncwarp(mask);
     }
-    // ---- phase 1: Ps row, X = L (P + P^T) row ; Cb, cb
-    double Ps[M];
+    // ---- phase 1: Ps rows (registers), X = L (P + P^T) rows ; Cb, cb
+    double Ps[R][M], abi[R];
 #pragma unroll
-    for (int j = 0; j < M; ++j) Ps[j] = 0.5 * (sm[L::Pb + i * M + j] + sm[L::Pb + j * M + i]);
-    abi = sm[L::ab + i];
-    if (act) {
+    for (int j = 0; j < M; ++j) {
+      double col[R];
+      lane_block<M, R>(sm + L::Pb + j * M, rw, col);
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
-        sm[L::Ps + i * M + j] = Ps[j];
-        Cb[j] += Ps[j];
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(g.Lm[k], sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k], s);
-        sm[L::X + i * M + j] = s;
+      for (int q = 0; q < R; ++q) {
+        Ps[q][j] = 0.5 * (sm[L::Pb + rw.c[q] * M + j] + col[q]);
+        Cb[q][j] += Ps[q][j];
       }
-      cb += abi;
+    }
+    lane_block<M, R>(sm + L::ab, rw, abi);
+#pragma unroll
+    for (int q = 0; q < R; ++q) cb[q] += abi[q];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double b = sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        if (rw.a[q]) sm[L::X + rw.r[q] * M + j] = s[q];
     }
     __syncwarp(mask);
     // ---- phase 2: Lb = Ps X, W = Ps L, T^T ab, (observed) PK = Ps Kp, Kb
-    double Lb[M], PK[P], Kb[P], abn = 0.0;
+    double Lb[R][M], PK[R][P], Kb[R][P], abn[R];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      double s = 0.0, s2 = 0.0;
+      double s[R], s2[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = s2[q] = 0.0;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        s = fma(Ps[k], sm[L::X + k * M + j], s);
-        s2 = fma(Ps[k], sm[L::Lm + k * M + j], s2);
+        const double bx = sm[L::X + k * M + j], bl = sm[L::Lm + k * M + j];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          s[q] = fma(Ps[q][k], bx, s[q]);
+          s2[q] = fma(Ps[q][k], bl, s2[q]);
+        }
       }
-      Lb[j] = s;
-      Tb[j] += fma(abi, sm[L::a + j], s);  // Tb += ab a^T + Lb
-      if (act) sm[L::W + i * M + j] = s2;
+      const double aj = sm[L::a + j];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        Lb[q][j] = s[q];
+        Tb[q][j] += fma(abi[q], aj, s[q]);  // Tb += ab a^T + Lb
+        if (rw.a[q]) sm[L::W + rw.r[q] * M + j] = s2[q];
+      }
     }
 #pragma unroll
-    for (int k = 0; k < M; ++k) abn = fma(sm[L::T + k * M + i], sm[L::ab + k], abn);
+    for (int q = 0; q < R; ++q) abn[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double abk = sm[L::ab + k];
+      double tc[R];
+      lane_block<M, R>(sm + L::T + k * M, rw, tc);
+#pragma unroll
+      for (int q = 0; q < R; ++q) abn[q] = fma(tc[q], abk, abn[q]);
+    }
     if (observed) {
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        double s = 0.0;
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(Ps[k], sm[L::Kp + k * P + j], s);
-        PK[j] = s;
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Kp + k * P + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(Ps[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) PK[q][j] = s[q];
       }
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        double s = abi * sm[L::v + j];
+        double s[R];
+        const double vj = sm[L::v + j];
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(PK[k], sm[L::H + k * P + j] + sm[L::H + j * P + k], s);
+        for (int q = 0; q < R; ++q) s[q] = abi[q] * vj;
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(-Lb[k], sm[L::Z + j * M + k], s);
-        Kb[j] = s;
-      }
-      if (act) {
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::H + k * P + j] + sm[L::H + j * P + k];
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-          sm[L::Kb + i * P + j] = Kb[j];
-          if (need_H) sm[L::PK + i * P + j] = PK[j];
+          for (int q = 0; q < R; ++q) s[q] = fma(PK[q][k], b, s[q]);
         }
-        if (need_Z) {
 #pragma unroll
-          for (int j = 0; j < M; ++j) sm[L::Lb + i * M + j] = Lb[j];
+        for (int k = 0; k < M; ++k) {
+          const double z = sm[L::Z + j * M + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(-Lb[q][k], z, s[q]);
         }
+#pragma unroll
+        for (int q = 0; q < R; ++q) Kb[q][j] = s[q];
       }
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        if (rw.a[q]) {
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            sm[L::Kb + rw.r[q] * P + j] = Kb[q][j];
+            if (need_H) sm[L::PK + rw.r[q] * P + j] = PK[q][j];
+          }
+          if (need_Z) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) sm[L::Lb + rw.r[q] * M + j] = Lb[q][j];
+          }
+        }
     }
     __syncwarp(mask);
-    // ---- phase 3: Pb' = L^T W (registers) ; (observed) every lane: K^T Kb, vb, Fb ; TMb row, Tb += TMb Mm^T
-    double Pbn[M];
+    // ---- phase 3: Pb' = L^T W (registers) ; (observed) every lane: K^T Kb, vb, Fb ; TMb rows, Tb += TMb Mm^T
+    double Pbn[R][M];
+    {
+      double Lc[R][M];  // the lane's COLUMNS of L
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      double s = 0.0;
+      for (int k = 0; k < M; ++k) {
+        double col[R];
+        lane_block<M, R>(sm + L::Lm + k * M, rw, col);
 #pragma unroll
-      for (int k = 0; k < M; ++k) s = fma(sm[L::Lm + k * M + i], sm[L::W + k * M + j], s);
-      Pbn[j] = s;
+        for (int q = 0; q < R; ++q) Lc[q][k] = col[q];
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::W + k * M + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(Lc[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) Pbn[q][j] = s[q];
+      }
     }
     double vb[P], Fb[P * P];
     if (observed) {
@@ -401,10 +663,10 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int lane
         vb[a2] = s;
 #pragma unroll
         for (int b2 = 0; b2 < P; ++b2) {
-          double q = 0.0;
+          double q1 = 0.0;
 #pragma unroll
-          for (int k = 0; k < M; ++k) q = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q);
-          Q1[a2 * P + b2] = q;
+          for (int k = 0; k < M; ++k) q1 = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q1);
+          Q1[a2 * P + b2] = q1;
         }
       }
 #pragma unroll
@@ -416,85 +678,121 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int lane
           for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
           Fb[a2 * P + b2] = s;
         }
-      double TMb[P];
+      double TMb[R][P];
 #pragma unroll
-      for (int j = 0; j < P; ++j) {
-        double s = 0.0;
+      for (int q = 0; q < R; ++q)
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(Kb[k], g.Fi[j * P + k], s);
-        TMb[j] = s;
-      }
+        for (int j = 0; j < P; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < P; ++k) s = fma(Kb[q][k], g.Fi[j * P + k], s);
+          TMb[q][j] = s;
+        }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        double s = Tb[j];
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(TMb[k], sm[L::Mm + j * P + k], s);
-        Tb[j] = s;
-      }
-      if (act) {
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::Mm + j * P + k];
 #pragma unroll
-        for (int j = 0; j < P; ++j) sm[L::TMb + i * P + j] = TMb[j];
+          for (int q = 0; q < R; ++q) Tb[q][j] = fma(TMb[q][k], b, Tb[q][j]);
+        }
       }
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        if (rw.a[q]) {
+#pragma unroll
+          for (int j = 0; j < P; ++j) sm[L::TMb + rw.r[q] * P + j] = TMb[q][j];
+        }
     }
     __syncwarp(mask);
     // ---- phase 4: (observed) Mb = T^T TMb + Z^T Fb ; Pb' += Mb Z ; ab' = T^T ab - Z^T vb ; store Pb', ab'
-    double Mb[P];
     if (observed) {
+      double Mb[R][P], Zc[R][P];  // Zc: the lane's columns of Z
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        double col[R];
+        lane_block<M, R>(sm + L::Z + k * M, rw, col);
+#pragma unroll
+        for (int q = 0; q < R; ++q) Zc[q][k] = col[q];
+      }
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        double s = 0.0;
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(sm[L::T + k * M + i], sm[L::TMb + k * P + j], s);
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(sm[L::Z + k * M + i], Fb[k * P + j], s);
-        Mb[j] = s;
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::TMb + k * P + j];
+          double tc[R];
+          lane_block<M, R>(sm + L::T + k * M, rw, tc);
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(tc[q], b, s[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(Zc[q][k], Fb[k * P + j], s[q]);
+#pragma unroll
+        for (int q = 0; q < R; ++q) Mb[q][j] = s[q];
       }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
 #pragma unroll
-        for (int k = 0; k < P; ++k) Pbn[j] = fma(Mb[k], sm[L::Z + k * M + j], Pbn[j]);
+        for (int k = 0; k < P; ++k) {
+          const double z = sm[L::Z + k * M + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) Pbn[q][j] = fma(Mb[q][k], z, Pbn[q][j]);
+        }
       }
 #pragma unroll
-      for (int k = 0; k < P; ++k) abn = fma(-sm[L::Z + k * M + i], vb[k], abn);
+      for (int k = 0; k < P; ++k)
 #pragma unroll
-      for (int q = 0; q < P; ++q)
-        if (lane == q) db = fma(-A.d_sign, vb[q], db);
-      if (need_Z && act) {
+        for (int q = 0; q < R; ++q) abn[q] = fma(-Zc[q][k], vb[k], abn[q]);
 #pragma unroll
-        for (int j = 0; j < P; ++j) sm[L::Mb + i * P + j] = Mb[j];
+      for (int k = 0; k < P; ++k)
+        if (l == k) db = fma(-A.d_sign, vb[k], db);
+      if (need_Z) {
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+          if (rw.a[q]) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) sm[L::Mb + rw.r[q] * P + j] = Mb[q][j];
+          }
       }
     }
     __syncwarp(mask);  // every lane has finished reading Pb, ab, Lm, W of this step
-    if (act) {
 #pragma unroll
-      for (int j = 0; j < M; ++j) sm[L::Pb + i * M + j] = Pbn[j];
-      sm[L::ab + i] = abn;
-    }
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) sm[L::Pb + rw.r[q] * M + j] = Pbn[q][j];
+        sm[L::ab + rw.r[q]] = abn[q];
+      }
     // ---- optional cotangents that need cross-row reductions (lanes < P own the rows of Zb, Hb)
     if (observed && (need_Z || need_H)) {
 #pragma unroll
-      for (int q = 0; q < P; ++q) {  // static index q instead of vb[lane] / Fb[lane * P + k]: keeps both in registers
-        if (lane != q) continue;
+      for (int e = 0; e < P; ++e) {  // static index e instead of vb[l] / Fb[l * P + k]: keeps both in registers
+        if (l != e) continue;
         if (need_Z) {
 #pragma unroll
           for (int j = 0; j < M; ++j) {
-            double s = fma(-vb[q], sm[L::a + j], Zb[j]);
+            double s = fma(-vb[e], sm[L::a + j], Zb[j]);
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-              s = fma(-sm[L::Kp + k * P + q], sm[L::Lb + k * M + j], s);   // - Kp^T Lb
-              s = fma(sm[L::Mb + k * P + q], sm[L::Pm + k * M + j], s);    // + Mb^T P
+              s = fma(-sm[L::Kp + k * P + e], sm[L::Lb + k * M + j], s);  // - Kp^T Lb
+              s = fma(sm[L::Mb + k * P + e], sm[L::Pm + k * M + j], s);   // + Mb^T P
             }
 #pragma unroll
-            for (int k = 0; k < P; ++k) s = fma(Fb[q * P + k], sm[L::Mm + j * P + k], s);  // + Fb Mm^T
+            for (int k = 0; k < P; ++k) s = fma(Fb[e * P + k], sm[L::Mm + j * P + k], s);  // + Fb Mm^T
             Zb[j] = s;
           }
         }
         if (need_H) {
 #pragma unroll
           for (int j = 0; j < P; ++j) {
-            double s = Hb[j] + Fb[q * P + j];
+            double s = Hb[j] + Fb[e * P + j];
 #pragma unroll
-            for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + q], sm[L::PK + k * P + j], s);  // + Kp^T Ps Kp
+            for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + e], sm[L::PK + k * P + j], s);  // + Kp^T Ps Kp
             Hb[j] = s;
           }
         }
@@ -502,25 +800,28 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int lane
     }
     __syncwarp(mask);
   }
-  // ---- write-out (row i by lane i)
-  if (act) {
-    if (A.ga0) A.ga0[u * M + i] = sm[L::ab + i];
+  // ---- write-out (each lane its rows)
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
-      if (A.gT) A.gT[u * M * M + i * M + j] = Tb[j];
-      if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
+  for (int q = 0; q < R; ++q)
+    if (rw.a[q]) {
+      const int i = rw.r[q];
+      if (A.ga0) A.ga0[u * M + i] = sm[L::ab + i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
+        if (A.gT) A.gT[u * M * M + i * M + j] = Tb[q][j];
+        if (A.gC) A.gC[u * M * M + i * M + j] = Cb[q][j];
+      }
+      if (A.gc) A.gc[u * M + i] = cb[q];
     }
-    if (A.gc) A.gc[u * M + i] = cb;
-  }
-  if (lane < P) {
-    if (A.gd) A.gd[u * P + lane] = db;
+  if (l < P) {
+    if (A.gd) A.gd[u * P + l] = db;
 #pragma unroll
     for (int j = 0; j < M; ++j)
-      if (A.gZ) A.gZ[u * P * M + lane * M + j] = Zb[j];
+      if (A.gZ) A.gZ[u * P * M + l * M + j] = Zb[j];
 #pragma unroll
     for (int j = 0; j < P; ++j)
-      if (A.gH) A.gH[u * P * P + lane * P + j] = Hb[j];
+      if (A.gH) A.gH[u * P * P + l * P + j] = Hb[j];
   }
 }
 

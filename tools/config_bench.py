@@ -3,6 +3,9 @@ usage: python tools/config_bench.py varmax|seasonal|arma21 [draws] [n] [filter] 
 import sys, json
 import numpy as np, torch
 sys.path.insert(0, ".")
+import os
+from pymc_statespace_b200 import _lib
+if os.environ.get("KFB_LIB"): _lib.LIB_PATH = os.environ["KFB_LIB"]
 from pymc_statespace_b200.logp import KalmanLogp
 from pymc_statespace_b200 import synthetic as syn
 
