@@ -29,13 +29,14 @@ struct RowsLayout {
   static constexpr int MM = M * M, MP = M * P, PP = P * P;
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
   // forward + adjoint share the first block
-  static constexpr int T = 0, Z = T + MM, H = Z + MP, Pm = H + PP + (PP & 1), Mm = Pm + MM, Kp = Mm + MP, Lm = Kp + MP,
-                       F = Lm + MM, a = F + PP + (PP & 1), v = a + M + (M & 1), END_COMMON = v + P + (P & 1);
+  static constexpr int T = 0, Z = T + MM, H = Z + MP, Pm = H + PP + (PP & 1), Mm = Pm + MM, Kp = Mm + MP + (MP & 1),
+                       Lm = Kp + MP + (MP & 1), a = Lm + MM, END_COMMON = a + M + (M & 1);
   // forward only
   static constexpr int S2 = END_COMMON, END_FWD = S2 + MM;
   // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
-  static constexpr int Pb = END_COMMON, X = Pb + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MP,
-                       Mb = TMb + MP, PK = Mb + MP, ab = PK + MP, tp = ab + M + (M & 1), END_BWD = tp + 2 * KTP;
+  static constexpr int MPE = MP + (MP & 1);
+  static constexpr int Pb = END_COMMON, X = Pb + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MPE,
+                       Mb = TMb + MPE, PK = Mb + MPE, ab = PK + MPE, tp = ab + M + (M & 1), END_BWD = tp + 2 * KTP;
   // unit stride == 2 (mod 4) doubles: consecutive units start 16 bytes apart modulo the 128-byte bank row, so the 32/G
   // units of a warp spread per-lane row / column accesses evenly over the banks (a stride == 0 mod 4 gave 8-way replays)
   static constexpr int stride(int n) { return ((n + 1) & ~1) + ((((n + 1) & ~1) & 2) ? 0 : 2); }
@@ -71,56 +72,85 @@ __device__ __forceinline__ void lane_block(const double* p, const RowIdx<M, R>& 
   }
 }
 
+// p[r[q]] = v[q] for the lane's active rows (inverse of lane_block)
+template <int M, int R>
+__device__ __forceinline__ void store_block(double* p, const RowIdx<M, R>& rw, const double (&v)[R]) {
+  if constexpr (R == 2 && (M % 2) == 0) {
+    if (rw.a[0]) *reinterpret_cast<double2*>(p + rw.r[0]) = make_double2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) p[rw.r[q]] = v[q];
+  }
+}
+
+// base[r[q] * W + j] = v[q][j] for the lane's active rows.  Two rows per lane and even M: the lane's block is 2W
+// contiguous doubles starting on a 16-byte boundary -> W 16-byte stores (rows of width 3 would otherwise go out as
+// 8-byte stores that replay on the banks).
+template <int M, int R, int W>
+__device__ __forceinline__ void store_rows(double* base, const RowIdx<M, R>& rw, const double (&v)[R][W]) {
+  if constexpr (R == 2 && (M % 2) == 0) {
+    if (rw.a[0]) {
+      double2* d = reinterpret_cast<double2*>(base + rw.r[0] * W);
+#pragma unroll
+      for (int e = 0; e < W; ++e) d[e] = make_double2(v[(2 * e) / W][(2 * e) % W], v[(2 * e + 1) / W][(2 * e + 1) % W]);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) base[rw.r[q] * W + j] = v[q][j];
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ shared pieces
-// Phases A, B, D of a step for an observed row: v, Mm, F | TM | (F^-1, w, quad) Kp, Lm.   Leaves in shared memory:
-// v, Mm, F, Kp, Lm; in registers of the lane: its TM, Kp, Lm rows, and (every lane) Fi, w.
+// Phases A, B of a step for an observed row: v, Mm | TM, F, F^-1, w, quad, Kp, Lm.   Leaves in shared memory: Mm, Kp, Lm;
+// in registers of the lane: its TM, Kp, Lm rows, and (every lane, redundantly: p <= 3) v, F^-1, w.  v and F cost every
+// lane 18 + 54 multiply-adds at m = 6, p = 3, but their operands (Z, a, Mm) are broadcast loads the phase needs anyway,
+// where rows of v / F owned by lanes 0..p-1 cost 8-way replayed row loads of Z, a store / sync / load round trip and a
+// third warp synchronisation.
 template <int M, int P, int R>
 struct RowGain {
-  double TM[R][P], Kp[R][P], Lm[R][M], Fi[P * P], w[P], piv[P], quad;
+  double TM[R][P], Kp[R][P], Lm[R][M], Fi[P * P], v[P], w[P], piv[P], quad;
   bool ok;
 };
 
 // tr(q, k) = T[row q of this lane][k] (registers in the forward kernel, shared memory in the adjoint)
 // Pr = the lane's rows of the predicted covariance (registers).
 template <int M, int P, int R, class TR>
-__device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, double di, int l, unsigned mask,
+__device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, const double (&dv)[P], unsigned mask,
                                           const RowIdx<M, R>& rw, TR tr, const double (&Pr)[R][M], RowGain<M, P, R>& g) {
   using L = RowsLayout<M, P>;
-  // ---- phase A: v (lanes < P), Mm rows
-  if (l < P) {
-    double s = yt[l] - d_sign * di;
-#pragma unroll
-    for (int k = 0; k < M; ++k) s = fma(-sm[L::Z + l * M + k], sm[L::a + k], s);
-    sm[L::v + l] = s;
-  }
+  // ---- phase A: v (every lane), Mm rows
   {
+    double av[M], Mr[R][P];
+#pragma unroll
+    for (int k = 0; k < M; ++k) av[k] = sm[L::a + k];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      double s[R];
+      double s[R], sv = yt[j] - d_sign * dv[j];
 #pragma unroll
       for (int q = 0; q < R; ++q) s[q] = 0.0;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
         const double z = sm[L::Z + j * M + k];
+        sv = fma(-z, av[k], sv);
 #pragma unroll
         for (int q = 0; q < R; ++q) s[q] = fma(Pr[q][k], z, s[q]);
       }
+      g.v[j] = sv;
 #pragma unroll
-      for (int q = 0; q < R; ++q)
-        if (rw.a[q]) sm[L::Mm + rw.r[q] * P + j] = s[q];
+      for (int q = 0; q < R; ++q) Mr[q][j] = s[q];
     }
+    store_rows<M, R, P>(sm + L::Mm, rw, Mr);
   }
   __syncwarp(mask);
-  // ---- phase B: F rows (lanes < P), TM rows (registers)
-  if (l < P) {
+  // ---- phase B: TM rows, F (every lane), F^-1, w, quad, Kp, Lm rows
+  double Fr[P * P], Lr[P * P], Lir[P * P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      double s = sm[L::H + l * P + j];
-#pragma unroll
-      for (int k = 0; k < M; ++k) s = fma(sm[L::Z + l * M + k], sm[L::Mm + k * P + j], s);
-      sm[L::F + l * P + j] = s;
-    }
-  }
+  for (int k = 0; k < P * P; ++k) Fr[k] = sm[L::H + k];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     double s[R];
@@ -131,24 +161,21 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
       const double b = sm[L::Mm + k * P + j];
 #pragma unroll
       for (int q = 0; q < R; ++q) s[q] = fma(tr(q, k), b, s[q]);
+#pragma unroll
+      for (int i = 0; i < P; ++i) Fr[i * P + j] = fma(sm[L::Z + i * M + k], b, Fr[i * P + j]);
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) g.TM[q][j] = s[q];
   }
-  __syncwarp(mask);
-  // ---- phase D: every lane inverts F in registers; Kp, Lm rows
-  double Fr[P * P], Lr[P * P], Lir[P * P];
-#pragma unroll
-  for (int k = 0; k < P * P; ++k) Fr[k] = sm[L::F + k];
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
   double qd = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], sm[L::v + k], s);
+    for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], g.v[k], s);
     g.w[j] = s;
-    qd = fma(sm[L::v + j], s, qd);
+    qd = fma(g.v[j], s, qd);
   }
   g.quad = qd;
 #pragma unroll
@@ -174,14 +201,8 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
 #pragma unroll
     for (int q = 0; q < R; ++q) g.Lm[q][j] = s[q];
   }
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-    if (rw.a[q]) {
-#pragma unroll
-      for (int j = 0; j < P; ++j) sm[L::Kp + rw.r[q] * P + j] = g.Kp[q][j];
-#pragma unroll
-      for (int j = 0; j < M; ++j) sm[L::Lm + rw.r[q] * M + j] = g.Lm[q][j];
-    }
+  store_rows<M, R, P>(sm + L::Kp, rw, g.Kp);
+  store_rows<M, R, M>(sm + L::Lm, rw, g.Lm);
   __syncwarp(mask);
 }
 
@@ -229,7 +250,9 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
     ci[q] = (rw.a[q] && A.c.p) ? A.c.p[draw * A.c.bs + rw.r[q]] : 0.0;
     if (rw.a[q]) sm[L::a + rw.r[q]] = a0p[rw.r[q]];
   }
-  const double di = (l < P && A.d.p) ? A.d.p[draw * A.d.bs + l] : 0.0;
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
   __syncwarp(mask);
   auto tr = [&](int q, int k) { return Tr[q][k]; };
 
@@ -253,7 +276,7 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
       for (int q = 0; q < R; ++q) an[q] = fma(Tr[q][k], ak, an[q]);
     }
     if (nm == 0) {
-      rows_gain<M, P, R>(sm, yt, A.d_sign, di, l, mask, rw, tr, Pr, g);
+      rows_gain<M, P, R>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, g);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll
@@ -263,9 +286,8 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
       // ---- phase E: a' rows, S2 rows = C + (L P) L^T + (Kp H) Kp^T
 #pragma unroll
       for (int k = 0; k < P; ++k) {
-        const double vk = sm[L::v + k];
 #pragma unroll
-        for (int q = 0; q < R; ++q) an[q] = fma(g.Kp[q][k], vk, an[q]);
+        for (int q = 0; q < R; ++q) an[q] = fma(g.Kp[q][k], g.v[k], an[q]);
       }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
@@ -347,12 +369,7 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
         for (int q = 0; q < R; ++q) S2[q][j] = s[q];
       }
     }
-#pragma unroll
-    for (int q = 0; q < R; ++q)
-      if (rw.a[q]) {
-#pragma unroll
-        for (int j = 0; j < M; ++j) sm[L::S2 + rw.r[q] * M + j] = S2[q][j];
-      }
+    store_rows<M, R, M>(sm + L::S2, rw, S2);
     __syncwarp(mask);
     // ---- phase F: P' = sym(S2), a' ; tape
     const bool taped = tp && t + 1 < n;
@@ -369,12 +386,11 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
         const int i = rw.r[q];
         if (taped) tp[i] = an[q];
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-          sm[L::Pm + i * M + j] = Pr[q][j];
+        for (int j = 0; j < M; ++j)
           if (taped && j >= i) tp[M + i * M - (i * (i - 1)) / 2 + (j - i)] = Pr[q][j];
-        }
         sm[L::a + i] = an[q];
       }
+    store_rows<M, R, M>(sm + L::Pm, rw, Pr);
     if (taped) tp += KT;
     __syncwarp(mask);
   }
@@ -436,7 +452,9 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
   for (int q = 0; q < R; ++q)
     if (rw.a[q]) sm[L::ab + rw.r[q]] = 0.0;
-  const double di = (l < P && A.d.p) ? A.d.p[draw * A.d.bs + l] : 0.0;
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
   __syncwarp(mask);
   auto tr = [&](int q, int k) { return sm[L::T + rw.c[q] * M + k]; };
 
@@ -466,12 +484,9 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       for (int q = 0; q < R; ++q) {
 #pragma unroll
         for (int j = 0; j < M; ++j) Pr[q][j] = P0p[rw.c[q] * M + j];
-        if (rw.a[q]) {
-#pragma unroll
-          for (int j = 0; j < M; ++j) sm[L::Pm + rw.r[q] * M + j] = Pr[q][j];
-          sm[L::a + rw.r[q]] = A.a0.p[draw * A.a0.bs + rw.r[q]];
-        }
+        if (rw.a[q]) sm[L::a + rw.r[q]] = A.a0.p[draw * A.a0.bs + rw.r[q]];
       }
+      store_rows<M, R, M>(sm + L::Pm, rw, Pr);
     } else {
       rows_tape_wait();
       __syncwarp(mask);
@@ -484,12 +499,9 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
           const int lo = i < j ? i : j, hi = i < j ? j : i;
           Pr[q][j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
         }
-        if (rw.a[q]) {
-          sm[L::a + i] = tq[i];
-#pragma unroll
-          for (int j = 0; j < M; ++j) sm[L::Pm + i * M + j] = Pr[q][j];
-        }
+        if (rw.a[q]) sm[L::a + i] = tq[i];
       }
+      store_rows<M, R, M>(sm + L::Pm, rw, Pr);
       if (t >= 2) rows_tape_prefetch<KT, G>(sm + L::tp + ((t - 1) & 1) * L::KTP, tape + (long long)(t - 2) * KT, l);
     }
     __syncwarp(mask);
@@ -497,17 +509,14 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
     const bool observed = (rows_count_missing<P>(yt) == 0);
     if (observed) {
-      rows_gain<M, P, R>(sm, yt, A.d_sign, di, l, mask, rw, tr, Pr, g);
+      rows_gain<M, P, R>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, g);
     } else {
 #pragma unroll
       for (int q = 0; q < R; ++q) {
 #pragma unroll
         for (int j = 0; j < M; ++j) g.Lm[q][j] = sm[L::T + rw.c[q] * M + j];
-        if (rw.a[q]) {
-#pragma unroll
-          for (int j = 0; j < M; ++j) sm[L::Lm + rw.r[q] * M + j] = g.Lm[q][j];
-        }
       }
+      store_rows<M, R, M>(sm + L::Lm, rw, g.Lm);
       __syncwarp(mask);
     }
     // ---- phase 1: Ps rows (registers), X = L (P + P^T) rows ; Cb, cb
@@ -525,24 +534,29 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     lane_block<M, R>(sm + L::ab, rw, abi);
 #pragma unroll
     for (int q = 0; q < R; ++q) cb[q] += abi[q];
+    {
+      double Xr[R][M];
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      double s[R];
+      for (int j = 0; j < M; ++j) {
+        double s[R];
 #pragma unroll
-      for (int q = 0; q < R; ++q) s[q] = 0.0;
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
 #pragma unroll
-      for (int k = 0; k < M; ++k) {
-        const double b = sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k];
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k];
 #pragma unroll
-        for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
+          for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) Xr[q][j] = s[q];
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-        if (rw.a[q]) sm[L::X + rw.r[q] * M + j] = s[q];
+      store_rows<M, R, M>(sm + L::X, rw, Xr);
     }
     __syncwarp(mask);
     // ---- phase 2: Lb = Ps X, W = Ps L, T^T ab, (observed) PK = Ps Kp, Kb
     double Lb[R][M], PK[R][P], Kb[R][P], abn[R];
+    {
+    double Wr[R][M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       double s[R], s2[R];
@@ -562,8 +576,10 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       for (int q = 0; q < R; ++q) {
         Lb[q][j] = s[q];
         Tb[q][j] += fma(abi[q], aj, s[q]);  // Tb += ab a^T + Lb
-        if (rw.a[q]) sm[L::W + rw.r[q] * M + j] = s2[q];
+        Wr[q][j] = s2[q];
       }
+    }
+    store_rows<M, R, M>(sm + L::W, rw, Wr);
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) abn[q] = 0.0;
@@ -593,9 +609,8 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
       for (int j = 0; j < P; ++j) {
         double s[R];
-        const double vj = sm[L::v + j];
 #pragma unroll
-        for (int q = 0; q < R; ++q) s[q] = abi[q] * vj;
+        for (int q = 0; q < R; ++q) s[q] = abi[q] * g.v[j];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const double b = sm[L::H + k * P + j] + sm[L::H + j * P + k];
@@ -611,19 +626,9 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
         for (int q = 0; q < R; ++q) Kb[q][j] = s[q];
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-        if (rw.a[q]) {
-#pragma unroll
-          for (int j = 0; j < P; ++j) {
-            sm[L::Kb + rw.r[q] * P + j] = Kb[q][j];
-            if (need_H) sm[L::PK + rw.r[q] * P + j] = PK[q][j];
-          }
-          if (need_Z) {
-#pragma unroll
-            for (int j = 0; j < M; ++j) sm[L::Lb + rw.r[q] * M + j] = Lb[q][j];
-          }
-        }
+      store_rows<M, R, P>(sm + L::Kb, rw, Kb);
+      if (need_H) store_rows<M, R, P>(sm + L::PK, rw, PK);
+      if (need_Z) store_rows<M, R, M>(sm + L::Lb, rw, Lb);
     }
     __syncwarp(mask);
     // ---- phase 3: Pb' = L^T W (registers) ; (observed) every lane: K^T Kb, vb, Fb ; TMb rows, Tb += TMb Mm^T
@@ -697,12 +702,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
           for (int q = 0; q < R; ++q) Tb[q][j] = fma(TMb[q][k], b, Tb[q][j]);
         }
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-        if (rw.a[q]) {
-#pragma unroll
-          for (int j = 0; j < P; ++j) sm[L::TMb + rw.r[q] * P + j] = TMb[q][j];
-        }
+      store_rows<M, R, P>(sm + L::TMb, rw, TMb);
     }
     __syncwarp(mask);
     // ---- phase 4: (observed) Mb = T^T TMb + Z^T Fb ; Pb' += Mb Z ; ab' = T^T ab - Z^T vb ; store Pb', ab'
@@ -751,23 +751,11 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
       for (int k = 0; k < P; ++k)
         if (l == k) db = fma(-A.d_sign, vb[k], db);
-      if (need_Z) {
-#pragma unroll
-        for (int q = 0; q < R; ++q)
-          if (rw.a[q]) {
-#pragma unroll
-            for (int j = 0; j < P; ++j) sm[L::Mb + rw.r[q] * P + j] = Mb[q][j];
-          }
-      }
+      if (need_Z) store_rows<M, R, P>(sm + L::Mb, rw, Mb);
     }
     __syncwarp(mask);  // every lane has finished reading Pb, ab, Lm, W of this step
-#pragma unroll
-    for (int q = 0; q < R; ++q)
-      if (rw.a[q]) {
-#pragma unroll
-        for (int j = 0; j < M; ++j) sm[L::Pb + rw.r[q] * M + j] = Pbn[q][j];
-        sm[L::ab + rw.r[q]] = abn[q];
-      }
+    store_rows<M, R, M>(sm + L::Pb, rw, Pbn);
+    store_block<M, R>(sm + L::ab, rw, abn);
     // ---- optional cotangents that need cross-row reductions (lanes < P own the rows of Zb, Hb)
     if (observed && (need_Z || need_H)) {
 #pragma unroll
