@@ -36,7 +36,7 @@ struct RowsLayout {
   // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
   static constexpr int MPE = MP + (MP & 1);
   static constexpr int Pb = END_COMMON, X = Pb + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MPE,
-                       Mb = TMb + MPE, PK = Mb + MPE, ab = PK + MPE, tp = ab + M + (M & 1), END_BWD = tp + 2 * KTP;
+                       Mb = TMb + MPE, PK = Mb + MPE, ab = PK + MPE, Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
   // unit stride == 2 (mod 4) doubles: consecutive units start 16 bytes apart modulo the 128-byte bank row, so the 32/G
   // units of a warp spread per-lane row / column accesses evenly over the banks (a stride == 0 mod 4 gave 8-way replays)
   static constexpr int stride(int n) { return ((n + 1) & ~1) + ((((n + 1) & ~1) & 2) ? 0 : 2); }
@@ -69,6 +69,30 @@ __device__ __forceinline__ void lane_block(const double* p, const RowIdx<M, R>& 
   } else {
 #pragma unroll
     for (int q = 0; q < R; ++q) out[q] = p[rw.c[q]];
+  }
+}
+
+// base[c[q] * W + j] += v[q][j] on the lane's own rows (an accumulator the lane keeps in shared memory, not registers)
+template <int M, int R, int W>
+__device__ __forceinline__ void accumulate_rows(double* base, const RowIdx<M, R>& rw, const double (&v)[R][W]) {
+  if constexpr (R == 2 && (M % 2) == 0) {
+    if (rw.a[0]) {
+      double2* d = reinterpret_cast<double2*>(base + rw.r[0] * W);
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        double2 c = d[e];
+        c.x += v[(2 * e) / W][(2 * e) % W];
+        c.y += v[(2 * e + 1) / W][(2 * e + 1) % W];
+        d[e] = c;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) base[rw.r[q] * W + j] += v[q][j];
+      }
   }
 }
 
@@ -263,8 +287,15 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
   double* tp = A.tape ? A.tape + u * (long long)(n - 1) * KT : nullptr;
   RowGain<M, P, R> g;
 
+  double yt[P], ynx[P];  // y[t] and, loaded one step ahead so its latency hides behind a whole step, y[t+1]
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[j];
   for (int t = 0; t < n; ++t) {
-    const double* yt = y + (long long)t * P;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t + 1 < n ? t + 1 : t) * P + j];
+    }
     const int nm = rows_count_missing<P>(yt);
     double an[R], S1[R][M], S2[R][M];
 #pragma unroll
@@ -428,7 +459,9 @@ __device__ __forceinline__ void rows_tape_wait() {
 #endif
 }
 
-template <int M, int P, int G>
+// NEED_Z: the caller wants Z-bar (never the case for the reference's models, whose design matrix is constant): the
+// Z-bar accumulators and the Lb / Mb exchanges exist only in that instantiation.
+template <int M, int P, int G, bool NEED_Z>
 __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
   using L = RowsLayout<M, P>;
   constexpr int R = RowsCfg<M, P, G>::R;
@@ -445,6 +478,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     for (int k = l; k < M * M; k += G) {
       sm[L::T + k] = Tp[k];
       sm[L::Pb + k] = 0.0;
+      sm[L::Cb + k] = 0.0;
     }
     for (int k = l; k < P * M; k += G) sm[L::Z + k] = Zp[k];
     for (int k = l; k < P * P; k += G) sm[L::H + k] = Hp[k];
@@ -460,21 +494,26 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 
   const double* y = A.y.p;
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
-  const bool need_Z = (A.gZ != nullptr), need_H = (A.gH != nullptr);
-  // gradient accumulators: the lane's rows of Tb, Cb; lanes < P hold rows of Zb, Hb; elements of cb (rows), db (lane)
-  double Tb[R][M], Cb[R][M], Zb[M], Hb[P], cb[R], db = 0.0;
+  constexpr bool need_Z = NEED_Z;
+  const bool need_H = (A.gH != nullptr);
+  // gradient accumulators: the lane's rows of Tb (registers) and Cb (shared memory: touched once per step, and the
+  // registers are all taken); lanes < P hold rows of Zb, Hb; elements of cb (rows), db (lane)
+  double Tb[R][M], Zb[NEED_Z ? M : 1], Hb[P], cb[R], db = 0.0;
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     cb[q] = 0.0;
 #pragma unroll
-    for (int j = 0; j < M; ++j) Tb[q][j] = Cb[q][j] = 0.0;
+    for (int j = 0; j < M; ++j) Tb[q][j] = 0.0;
   }
 #pragma unroll
-  for (int j = 0; j < M; ++j) Zb[j] = 0.0;
+  for (int j = 0; j < (NEED_Z ? M : 1); ++j) Zb[j] = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) Hb[j] = 0.0;
   RowGain<M, P, R> g;
   double Pr[R][M];
+  double yt[P], ynx[P];  // y[t] and, loaded one step ahead, y[t-1]
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[(long long)(n - 1) * P + j];
 
   for (int t = n - 1; t >= 0; --t) {
     // ---- predicted moments of step t -> shared memory (and the lane's rows of P in registers)
@@ -505,7 +544,11 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       if (t >= 2) rows_tape_prefetch<KT, G>(sm + L::tp + ((t - 1) & 1) * L::KTP, tape + (long long)(t - 2) * KT, l);
     }
     __syncwarp(mask);
-    const double* yt = y + (long long)t * P;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t > 0 ? t - 1 : 0) * P + j];
+    }
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
     const bool observed = (rows_count_missing<P>(yt) == 0);
     if (observed) {
@@ -526,11 +569,9 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       double col[R];
       lane_block<M, R>(sm + L::Pb + j * M, rw, col);
 #pragma unroll
-      for (int q = 0; q < R; ++q) {
-        Ps[q][j] = 0.5 * (sm[L::Pb + rw.c[q] * M + j] + col[q]);
-        Cb[q][j] += Ps[q][j];
-      }
+      for (int q = 0; q < R; ++q) Ps[q][j] = 0.5 * (sm[L::Pb + rw.c[q] * M + j] + col[q]);
     }
+    accumulate_rows<M, R, M>(sm + L::Cb, rw, Ps);
     lane_block<M, R>(sm + L::ab, rw, abi);
 #pragma unroll
     for (int q = 0; q < R; ++q) cb[q] += abi[q];
@@ -761,7 +802,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
       for (int e = 0; e < P; ++e) {  // static index e instead of vb[l] / Fb[l * P + k]: keeps both in registers
         if (l != e) continue;
-        if (need_Z) {
+        if constexpr (NEED_Z) {
 #pragma unroll
           for (int j = 0; j < M; ++j) {
             double s = fma(-vb[e], sm[L::a + j], Zb[j]);
@@ -798,15 +839,14 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       for (int j = 0; j < M; ++j) {
         if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
         if (A.gT) A.gT[u * M * M + i * M + j] = Tb[q][j];
-        if (A.gC) A.gC[u * M * M + i * M + j] = Cb[q][j];
+        if (A.gC) A.gC[u * M * M + i * M + j] = sm[L::Cb + i * M + j];
       }
       if (A.gc) A.gc[u * M + i] = cb[q];
     }
   if (l < P) {
     if (A.gd) A.gd[u * P + l] = db;
 #pragma unroll
-    for (int j = 0; j < M; ++j)
-      if (A.gZ) A.gZ[u * P * M + l * M + j] = Zb[j];
+    for (int j = 0; j < (NEED_Z ? M : 0); ++j) A.gZ[u * P * M + l * M + j] = Zb[j];
 #pragma unroll
     for (int j = 0; j < P; ++j)
       if (A.gH) A.gH[u * P * P + l * P + j] = Hb[j];
