@@ -24,19 +24,22 @@ struct RowsCfg {
   static_assert(G >= P && G <= 32, "lanes 0..P-1 own the rows of v, F, Zb, Hb");
 };
 
-template <int M, int P>
+// NZ = the adjoint also produces Z-bar.  Without it Lb / Mb are never exchanged and nothing reads Pm after phase 1, so
+// W lives in Pm's slot; TMb (written in phase 3) always reuses X's slot (last read in phase 2).  At m = 6, p = 3 that
+// is 422 doubles per unit = 8 resident units-of-8 per SM instead of 6.
+template <int M, int P, bool NZ = true>
 struct RowsLayout {
-  static constexpr int MM = M * M, MP = M * P, PP = P * P;
+  static constexpr int MM = M * M, MP = M * P, PP = P * P, MPE = MP + (MP & 1);
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
   // forward + adjoint share the first block
-  static constexpr int T = 0, Z = T + MM, H = Z + MP, Pm = H + PP + (PP & 1), Mm = Pm + MM, Kp = Mm + MP + (MP & 1),
-                       Lm = Kp + MP + (MP & 1), a = Lm + MM, END_COMMON = a + M + (M & 1);
+  static constexpr int T = 0, Z = T + MM, H = Z + MP, Pm = H + PP + (PP & 1), Mm = Pm + MM, Kp = Mm + MPE,
+                       Lm = Kp + MPE, a = Lm + MM, END_COMMON = a + M + (M & 1);
   // forward only
   static constexpr int S2 = END_COMMON, END_FWD = S2 + MM;
   // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
-  static constexpr int MPE = MP + (MP & 1);
-  static constexpr int Pb = END_COMMON, X = Pb + MM, W = X + MM, Lb = W + MM, Kb = Lb + MM, TMb = Kb + MPE,
-                       Mb = TMb + MPE, PK = Mb + MPE, ab = PK + MPE, Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
+  static constexpr int Pb = END_COMMON, X = Pb + MM, TMb = X, W = NZ ? X + MM : Pm, Lb = X + 2 * MM,
+                       Kb = NZ ? Lb + MM : X + MM, Mb = Kb + MPE, PK = NZ ? Mb + MPE : Kb + MPE, ab = PK + MPE,
+                       Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
   // unit stride == 2 (mod 4) doubles: consecutive units start 16 bytes apart modulo the 128-byte bank row, so the 32/G
   // units of a warp spread per-lane row / column accesses evenly over the banks (a stride == 0 mod 4 gave 8-way replays)
   static constexpr int stride(int n) { return ((n + 1) & ~1) + ((((n + 1) & ~1) & 2) ? 0 : 2); }
@@ -463,7 +466,7 @@ __device__ __forceinline__ void rows_tape_wait() {
 // Z-bar accumulators and the Lb / Mb exchanges exist only in that instantiation.
 template <int M, int P, int G, bool NEED_Z>
 __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
-  using L = RowsLayout<M, P>;
+  using L = RowsLayout<M, P, NEED_Z>;
   constexpr int R = RowsCfg<M, P, G>::R;
   constexpr int KT = L::KT;
   const int n = A.n;
