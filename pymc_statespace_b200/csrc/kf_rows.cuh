@@ -40,9 +40,11 @@ struct RowsLayout {
   static constexpr int Pb = END_COMMON, X = Pb + MM, TMb = X, W = NZ ? X + MM : Pm, Lb = X + 2 * MM,
                        Kb = NZ ? Lb + MM : X + MM, Mb = Kb + MPE, PK = NZ ? Mb + MPE : Kb + MPE, ab = PK + MPE,
                        Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
-  // unit stride == 2 (mod 4) doubles: consecutive units start 16 bytes apart modulo the 128-byte bank row, so the 32/G
-  // units of a warp spread per-lane row / column accesses evenly over the banks (a stride == 0 mod 4 gave 8-way replays)
-  static constexpr int stride(int n) { return ((n + 1) & ~1) + ((((n + 1) & ~1) & 2) ? 0 : 2); }
+  // unit stride == 6 (mod 16) doubles = 48 bytes modulo the 128-byte bank row: with 16-byte accesses served a quarter
+  // warp (two units of 4 lanes) at a time, both the lanes' row blocks (96 bytes apart) and their column blocks (16 bytes
+  // apart) of two neighbouring units then fall on distinct bank groups.  Measured: a stride == 0 (mod 4) gave 8-way
+  // replays on row accesses, == 2 (mod 16) 2-way replays on every column access.
+  static constexpr int stride(int n) { return n + ((6 - (n % 16)) + 16) % 16; }
   static constexpr int fwd_doubles = stride(END_FWD), bwd_doubles = stride(END_BWD);
 };
 
@@ -514,6 +516,13 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
   for (int j = 0; j < P; ++j) Hb[j] = 0.0;
   RowGain<M, P, R> g;
   double Pr[R][M];
+  double Pbr[R][M], abi[R];  // the lane's rows of Pb / elements of ab as of the previous step (their columns go via shared memory)
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    abi[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) Pbr[q][j] = 0.0;
+  }
   double yt[P], ynx[P];  // y[t] and, loaded one step ahead, y[t-1]
 #pragma unroll
   for (int j = 0; j < P; ++j) ynx[j] = y[(long long)(n - 1) * P + j];
@@ -566,16 +575,15 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       __syncwarp(mask);
     }
     // ---- phase 1: Ps rows (registers), X = L (P + P^T) rows ; Cb, cb
-    double Ps[R][M], abi[R];
+    double Ps[R][M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       double col[R];
       lane_block<M, R>(sm + L::Pb + j * M, rw, col);
 #pragma unroll
-      for (int q = 0; q < R; ++q) Ps[q][j] = 0.5 * (sm[L::Pb + rw.c[q] * M + j] + col[q]);
+      for (int q = 0; q < R; ++q) Ps[q][j] = 0.5 * (Pbr[q][j] + col[q]);
     }
     accumulate_rows<M, R, M>(sm + L::Cb, rw, Ps);
-    lane_block<M, R>(sm + L::ab, rw, abi);
 #pragma unroll
     for (int q = 0; q < R; ++q) cb[q] += abi[q];
     {
@@ -800,6 +808,12 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     __syncwarp(mask);  // every lane has finished reading Pb, ab, Lm, W of this step
     store_rows<M, R, M>(sm + L::Pb, rw, Pbn);
     store_block<M, R>(sm + L::ab, rw, abn);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      abi[q] = abn[q];
+#pragma unroll
+      for (int j = 0; j < M; ++j) Pbr[q][j] = Pbn[q][j];
+    }
     // ---- optional cotangents that need cross-row reductions (lanes < P own the rows of Zb, Hb)
     if (observed && (need_Z || need_H)) {
 #pragma unroll
