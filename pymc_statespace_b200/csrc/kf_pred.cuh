@@ -247,6 +247,10 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
   // Cotangents nobody asked for are not accumulated (every reference model has a constant design matrix, so Z-bar -
   // 2 m^2 p + m p^2 multiply-adds per step - is never needed at theta level).  Uniform run-time branches.
   const bool need_Z = (A.gZ != nullptr), need_H = (A.gH != nullptr) || (MK == MK_STEADY);
+  // T-bar: structural models (local level, trend + seasonal: config 4) have a constant transition matrix.  Without T-bar
+  // and Z-bar the dense product Lb = Ps L (P + P^T) - one of the four m^3 products of the adjoint step - is only needed
+  // through Lb Z^T = Ps (L (P + P^T) Z^T): two m^2 p products instead.
+  const bool need_Lb = (A.gT != nullptr) || need_Z;
 
   // ---- inputs of step t (tape entries are consumed in strictly descending order)
   auto prepare = [&](int t, StepSet<X>& S) {
@@ -298,10 +302,14 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
     KFB_FOR(idx, m * m) Cb[idx] += Ps[idx];
     KFB_FOR(i, m) cb[i] += ab[i];
     gemm<false, false, 0>(x, tmp.S1, tmp.Lm, S4, m, m, m);   // L (P + P^T)
-    gemm<false, false, 0>(x, Lb, Ps, tmp.S1, m, m, m);       // Lb = Ps L (P + P^T)
+    if (need_Lb) {
+      gemm<false, false, 0>(x, Lb, Ps, tmp.S1, m, m, m);     // Lb = Ps L (P + P^T)
+    } else if (observed) {
+      gemm<false, true, 0>(x, tmp.KH, tmp.S1, prm.Z, m, m, p);  // L (P + P^T) Z^T   (KH is free in the adjoint)
+    }
     gemm<false, false, 0>(x, tmp.S1, Ps, tmp.Lm, m, m, m);   // Ps L
     gemm<true, false, 0>(x, Pb, tmp.Lm, tmp.S1, m, m, m);    // Pb = L^T Ps L
-    KFB_FOR(idx, m * m) {                                    // Tb += ab a^T + Lb
+    if (need_Lb) KFB_FOR(idx, m * m) {                       // Tb += ab a^T + Lb
       const int i = x.div_m(idx), j = idx - i * m;
       Tb[idx] += kf_fma(ab[i], a[j], Lb[idx]);
     }
@@ -319,12 +327,22 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
       }
       gemm<false, false, 0>(x, PK, Ps, tmp.Kp, m, m, p);       // Ps Kp
       gemm<false, false, 0>(x, Kb, PK, Q1, m, p, p);           // Kb = Ps Kp (H + H^T)
-      KFB_FOR(idx, m * p) {
-        const int i = x.div_p(idx), j = idx - i * p;
-        double s = kf_fma(ab[i], tmp.v[j], Kb[idx]);           // + ab v^T
+      if (need_Lb) {
+        KFB_FOR(idx, m * p) {
+          const int i = x.div_p(idx), j = idx - i * p;
+          double s = kf_fma(ab[i], tmp.v[j], Kb[idx]);           // + ab v^T
 #pragma unroll
-        for (int k = 0; k < m; ++k) s = kf_fma(-Lb[i * m + k], prm.Z[j * m + k], s);  // - Lb Z^T
-        Kb[idx] = s;
+          for (int k = 0; k < m; ++k) s = kf_fma(-Lb[i * m + k], prm.Z[j * m + k], s);  // - Lb Z^T
+          Kb[idx] = s;
+        }
+      } else {
+        KFB_FOR(idx, m * p) {
+          const int i = x.div_p(idx), j = idx - i * p;
+          double s = kf_fma(ab[i], tmp.v[j], Kb[idx]);           // + ab v^T
+#pragma unroll
+          for (int k = 0; k < m; ++k) s = kf_fma(-Ps[i * m + k], tmp.KH[k * p + j], s);  // - Ps (L (P + P^T) Z^T)
+          Kb[idx] = s;
+        }
       }
       x.sync();  // Kb is read across lanes below
       if (need_H) gemm<true, false, 1>(x, Hb, tmp.Kp, PK, p, m, p);  // Hb += Kp^T Ps Kp

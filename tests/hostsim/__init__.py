@@ -36,8 +36,8 @@ def _p(a):
 
 
 def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_dims=False, do_bwd=True,
-        g_loglik=None, g_ll_obs=None, full=True, pred=False):
-    """Returns (outputs6, grads dict or None, info)."""
+        g_loglik=None, g_ll_obs=None, full=True, pred=False, skip=()):
+    """Returns (outputs6, grads dict or None, info).  ``skip``: cotangents NOT requested (null pointers, left zero)."""
     lib = build()
     f8 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))  # noqa: E731
     data, a0, P0, T, Z, R, H, Q = map(f8, (data, a0, P0, T, Z, R, H, Q))
@@ -90,7 +90,8 @@ def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_d
         mk, m, p, n, _p(data), _p(a0), _p(P0), _p(T), _p(Z), _p(H), _p(C), _p(c), _p(d), _p(Pss), _p(Gss), _p(ts),
         ctypes.c_double(ll_const), ctypes.c_double(d_sign), int(static_dims) | (2 if pred else 0), _p(loglik), _p(ll_obs), _p(fs), _p(ps),
         _p(fc), _p(pc), _p(info), int(do_bwd), _p(gl), _p(glo),
-        *([_p(g[k]) for k in ("a0", "P0", "T", "Z", "H", "C", "c", "d", "Pss", "Gss")] if do_bwd else [None] * 10),
+        *([None if k in skip else _p(g[k]) for k in ("a0", "P0", "T", "Z", "H", "C", "c", "d", "Pss", "Gss")]
+          if do_bwd else [None] * 10),
     )
     if rc != 0:
         raise RuntimeError(f"hostsim_run rc={rc}")

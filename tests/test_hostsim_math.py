@@ -136,6 +136,27 @@ def test_predictor_form_hot_path(dims, static):
             assert rel_err(g[k], gt[k]) < 1e-9 or np.abs(g[k] - gt[k]).max() < 1e-13, (kind, k)
 
 
+@pytest.mark.parametrize("static", [True, False], ids=["ThreadCtx", "CoopCtx"])
+def test_predictor_form_without_T_and_Z_cotangents(static):
+    """Structural models have constant T and Z: with T-bar / Z-bar not requested the adjoint drops the dense
+    Lb = Ps L (P + P^T) product (kf_pred.cuh need_Lb).  Every other cotangent must be unchanged."""
+    rng = np.random.default_rng(5)
+    args = random_system(rng, 4, 2, 2, 20, n_missing=2)
+    c, d = rng.normal(size=(4, 1)), rng.normal(size=(2, 1))
+    for kind in ("standard", "steady_state"):
+        kw = dict(c=c, d=d) if kind == "standard" else {}
+        _, g_all, _ = hostsim.run(kind, *args, static_dims=static, full=False, pred=True, **kw)
+        _, g_few, _ = hostsim.run(kind, *args, static_dims=static, full=False, pred=True, skip=("T", "Z"), **kw)
+        _, gt = kt.loglik_and_grads(kind, *args, **kw)
+        for k in gt:
+            if k in ("T", "Z"):
+                continue
+            if kind == "steady_state" and k in ("R", "Q", "H"):
+                continue  # the DARE epilogue (numpy, in hostsim) folds T-bar / Z-bar contributions into these
+            assert rel_err(g_few[k], g_all[k]) < 1e-12 or np.abs(g_few[k] - g_all[k]).max() < 1e-14, (kind, k)
+            assert rel_err(g_few[k], gt[k]) < 1e-8 or np.abs(g_few[k] - gt[k]).max() < 1e-13, (kind, k)
+
+
 def test_predictor_form_steady_state_and_time_varying():
     rng = np.random.default_rng(77)
     args = random_system(rng, 4, 2, 2, 30)
