@@ -282,6 +282,40 @@ def test_subwarp_kernels_many_units_not_multiple_of_group():
             assert rel_err(g["Q"][b].cpu().numpy(), gref["Q"]) < RTOL
 
 
+@pytest.mark.parametrize("wrt", [("a0", "P0", "T", "R", "H", "Q", "c", "d"), ("a0", "P0", "R", "H", "Q", "c", "d"), ("H", "Q")],
+                         ids=["with_Tbar", "no_Tbar", "HQ_only"])
+@pytest.mark.parametrize("dims", [(5, 1, 2), (5, 3, 2), (6, 2, 3), (6, 3, 3), (7, 3, 2), (8, 1, 1), (8, 3, 3), (30, 1, 3)],
+                         ids=lambda d: "m%dp%dr%d" % d)
+def test_fused_row_kernels_hot_path(dims, wrt):
+    """The theta-level hot path of mid-size / large systems: loglik-only forward + adjoint WITHOUT Z-bar go through the
+    fused row kernels (kf_rows.cuh: 4 lanes x 2 rows, k_states 5..8; kf_rowsL.cuh: warp per unit, k_states 30), with and
+    without T-bar (separate instantiations / code paths).  13 units: partial last warp; shared y with missing rows."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = dims
+    rng = np.random.default_rng(1000 + 10 * m + p)
+    B, n = 13, 24
+    systems = [random_system(rng, m, p, r, n, scale_T=0.25 if m < 30 else 0.1) for _ in range(B)]
+    y = random_system(rng, m, p, r, n, n_missing=3)[0]
+    cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    bk = BatchedKalman("standard", n, m, p, r, n_draws=B)
+    out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                     c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
+    w = rng.normal(size=B)
+    g = bk.backward(g_loglik=_dev(w), wrt=wrt)
+    assert int(out["info"].abs().max()) == 0
+    ll = out["loglik"].cpu().numpy()
+    for b in (0, 7, 8, 12):
+        args = (y,) + tuple(systems[b][1:])
+        ref, gref = kt.loglik_and_grads("standard", *args, c=cs[b][:, None], d=ds[b][:, None])
+        assert abs(ll[b] - ref) < RTOL * abs(ref)
+        for k in wrt:
+            got = g[k][b].cpu().numpy().reshape(gref[k].shape)
+            scale = max(np.abs(gref[k]).max(), 1e-12)
+            assert np.abs(got - w[b] * gref[k]).max() / (abs(w[b]) * scale) < RTOL, (k, b)
+
+
 @pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
 @pytest.mark.parametrize("n", [1, 2, 3])
 def test_very_short_series(n, force_coop):
