@@ -1,0 +1,634 @@
+// kf_rowsD.cuh - large systems (16 < k_states <= 32, even; k_endog <= 3; MK_STD; static matrices; shared observation
+// stream; config 4 of BASELINE.json: trend + seasonal, k_states = 30): one WARP per unit, the m x m x m products on the
+// FP64 TENSOR CORES (mma.sync.m8n8k4.f64, "DMMA"), everything else row-per-lane as in kf_rows.cuh / kf_rowsL.cuh.
+//
+// Why: with DFMA every multiply-add needs at least one operand from shared memory and a broadcast load delivers one
+// double per wavefront, so the warp-per-unit DFMA kernel (kf_rowsL.cuh) sits at 94 % of the shared-memory wavefront
+// peak with the fp64 pipe 35 % active (profiles/r1_ncu_rowsL.md).  A DMMA consumes one A and one B element per lane for
+// eight multiply-adds per lane, and a fragment is reused for four tiles: ~0.06 shared-memory operands per multiply-add.
+// tools/dmma_probe.cu measured 37.1 TFLOP/s for register-operand DMMA on this B200 - the same as the DFMA peak - already
+// at one warp per SM sub-partition with four independent accumulator tiles.
+//
+// Matrices live in shared memory as 32 x 32 tiles-of-8 with leading dimension LD = 36 doubles (rows 16-byte aligned,
+// fragment loads at most 2-way bank-conflicted); rows / columns >= m are zero and stay zero (products of zero padding).
+// Transposed operands cost nothing: A^T / B^T just swap the two fragment access patterns.
+#pragma once
+#include "kf_core.cuh"
+#include "kf_rows.cuh"
+
+namespace kfb {
+
+template <int M, int P, bool NEED_T>
+struct RowsDLayout {
+  static_assert(M % 2 == 0 && M > 16 && M <= 32 && P <= 3, "even k_states in 18..32");
+  static constexpr int LD = 36, MS = 32 * LD;  // one padded matrix
+  static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), ME = M + (M & 1);
+  static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
+  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MPE,
+                       a = Kp + MPE, END_COMMON = a + ME;
+  // forward only: X (then S2) ; KH rows
+  static constexpr int X = END_COMMON, KH = X + MS, END_FWD = KH + MPE;
+  // adjoint only: W / X-for-lz live in Pm's slot; Lb lives in Xb's slot
+  static constexpr int Pb = END_COMMON, W = Pm, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MPE, lz = PK + MPE, ab = lz + MPE,
+                       tp = ab + ME, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0);
+  static constexpr int fwd_doubles = (END_FWD + 1) & ~1, bwd_doubles = (END_BWD + 1) & ~1;
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#endif
+}
+
+// acc (32 x 32, as 4 x 4 tiles of 8 x 8 in mma fragment layout: lane holds [8I + lane/4][8J + 2 (lane%4) + {0,1}])
+//   = op(A) op(B),  op = transpose if TA / TB.  A, B: padded row-major matrices (leading dimension LD) in shared memory.
+template <bool TA, bool TB, int LD>
+__device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, const double* B, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  const double* pa = TA ? A + c * LD + r : A + r * LD + c;  // A^T: a[row][k] = A[k][row]
+  const double* pb = TB ? B + r * LD + c : B + c * LD + r;  // B^T: b[k][col] = B[col][k]
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) af[I] = TA ? pa[(4 * kk) * LD + 8 * I] : pa[(8 * I) * LD + 4 * kk];
+#pragma unroll
+    for (int J = 0; J < 4; ++J) bf[J] = TB ? pb[(8 * J) * LD + 4 * kk] : pb[(4 * kk) * LD + 8 * J];
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J < 4; ++J) dmma884(acc[I][J][0], acc[I][J][1], af[I], bf[J]);
+  }
+}
+
+// D = alpha * acc (full 32 x 32 including the zero padding)
+template <int LD>
+__device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][2], double alpha, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int J = 0; J < 4; ++J)
+      *reinterpret_cast<double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c) = make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
+}
+
+template <int M>
+__device__ __forceinline__ void rowD_store(double* dst, const double (&v)[M]) {
+  double2* d = reinterpret_cast<double2*>(dst);
+#pragma unroll
+  for (int j = 0; j < M / 2; ++j) d[j] = make_double2(v[2 * j], v[2 * j + 1]);
+}
+template <int M>
+__device__ __forceinline__ void rowD_load(double (&v)[M], const double* src) {
+  const double2* s = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int j = 0; j < M / 2; ++j) {
+    const double2 x = s[j];
+    v[2 * j] = x.x;
+    v[2 * j + 1] = x.y;
+  }
+}
+
+template <int M, int P>
+struct RowDGain {
+  double Kp[P], Fi[P * P], v[P], w[P], piv[P], quad;
+  bool ok;
+};
+
+// v, Mm | TM, F, F^-1, w, quad, Kp, Lm for an observed step (row-per-lane).  Leaves Mm, Kp, Lm in shared memory (visible
+// after the trailing sync); returns the lane's Kp row and (every lane) v, F^-1, w.
+template <int M, int P, class L>
+__device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P], int i, bool act,
+                                           RowDGain<M, P>& g) {
+  constexpr int LD = L::LD;
+  // ---- A: Mm row (own P row x Z rows), v (every lane)
+  {
+    double Mr[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      Mr[j] = 0.0;
+      g.v[j] = yt[j] - d_sign * dv[j];
+    }
+    const double2* pr = reinterpret_cast<const double2*>(sm + L::Pm + i * LD);
+    const double2* av = reinterpret_cast<const double2*>(sm + L::a);
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) {
+      const double2 pk = pr[k], ak = av[k];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + j * M + 2 * k);
+        Mr[j] = fma(pk.x, z.x, Mr[j]);
+        Mr[j] = fma(pk.y, z.y, Mr[j]);
+        g.v[j] = fma(-z.x, ak.x, g.v[j]);
+        g.v[j] = fma(-z.y, ak.y, g.v[j]);
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) sm[L::Mm + i * P + j] = Mr[j];
+    }
+  }
+  __syncwarp();
+  // ---- B: TM row, F (every lane), inverse, w, quad, Kp row, Lm row
+  double Fr[P * P], Lr[P * P], Lir[P * P], TM[P];
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Fr[k] = sm[L::H + k];
+#pragma unroll
+  for (int j = 0; j < P; ++j) TM[j] = 0.0;
+  {
+    const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) {
+      const double2 tk = tr[k];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const double m0 = sm[L::Mm + (2 * k) * P + j], m1 = sm[L::Mm + (2 * k + 1) * P + j];
+        TM[j] = fma(tk.x, m0, TM[j]);
+        TM[j] = fma(tk.y, m1, TM[j]);
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
+          Fr[e * P + j] = fma(z.x, m0, Fr[e * P + j]);
+          Fr[e * P + j] = fma(z.y, m1, Fr[e * P + j]);
+        }
+      }
+    }
+  }
+  g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
+  double qd = 0.0;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], g.v[k], s);
+    g.w[j] = s;
+    qd = fma(g.v[j], s, qd);
+  }
+  g.quad = qd;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) s = fma(TM[k], g.Fi[k * P + j], s);
+    g.Kp[j] = s;
+  }
+  {
+    const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
+    double2* lr = reinterpret_cast<double2*>(sm + L::Lm + i * LD);
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) {
+      double2 lk = tr[k];
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
+        lk.x = fma(-g.Kp[e], z.x, lk.x);
+        lk.y = fma(-g.Kp[e], z.y, lk.y);
+      }
+      if (act) lr[k] = lk;
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) sm[L::Kp + i * P + j] = g.Kp[j];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int M, int P>
+__device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane) {
+  using L = RowsDLayout<M, P, false>;
+  constexpr int KT = L::KT, LD = L::LD;
+  const int n = A.n;
+  const long long draw = u / A.n_series;
+  const bool act = lane < M;
+  const int i = act ? lane : 0;
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* Cp = A.C.p + draw * A.C.bs;
+  const double* P0p = A.P0.p + draw * A.P0.bs;
+  for (int k = lane; k < L::fwd_doubles; k += 32) sm[k] = 0.0;  // zero padding everywhere
+  __syncwarp();
+  for (int k = lane; k < M * M; k += 32) {
+    const int rr = k / M, cc = k - rr * M;
+    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::Pm + rr * LD + cc] = P0p[k];
+  }
+  for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
+  for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
+  if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
+  double Cs[M];  // the lane's row of sym(C), C = R Q R^T (static): registers
+#pragma unroll
+  for (int j = 0; j < M; ++j) Cs[j] = 0.5 * (Cp[i * M + j] + Cp[j * M + i]);
+  const double ci = (act && A.c.p) ? A.c.p[draw * A.c.bs + i] : 0.0;
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
+  __syncwarp();
+
+  const double* y = A.y.p;
+  LogAcc acc;
+  double llsum = 0.0;
+  int info = 0;
+  double* tp = A.tape ? A.tape + u * (long long)(n - 1) * KT : nullptr;
+  RowDGain<M, P> g;
+  double yt[P], ynx[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[j];
+
+  for (int t = 0; t < n; ++t) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t + 1 < n ? t + 1 : t) * P + j];
+    }
+    int nm = 0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) nm += (yt[j] != yt[j]) ? 1 : 0;
+    const bool observed = (nm == 0);
+    // a' = T a + c (+ Kp v)
+    double an = ci;
+    {
+      const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
+      const double2* av = reinterpret_cast<const double2*>(sm + L::a);
+#pragma unroll
+      for (int k = 0; k < M / 2; ++k) {
+        const double2 tk = tr[k], ak = av[k];
+        an = fma(tk.x, ak.x, an);
+        an = fma(tk.y, ak.y, an);
+      }
+    }
+    double KH[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) KH[j] = 0.0;
+    if (observed) {
+      rowsD_gain<M, P, L>(sm, yt, A.d_sign, dv, i, act, g);
+      if (!g.ok && info == 0) info = t + 1;
+      if (g.ok) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc.mul(g.piv[k]);
+      }
+      llsum += -0.5 * (A.ll_const + g.quad);
+#pragma unroll
+      for (int k = 0; k < P; ++k) an = fma(g.Kp[k], g.v[k], an);
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) KH[j] = fma(g.Kp[k], sm[L::H + k * P + j], KH[j]);
+        if (act) sm[L::KH + i * P + j] = KH[j];
+      }
+    } else if (nm != P && info == 0) {
+      info = -(t + 1);
+    }
+    const double* Lsrc = observed ? sm + L::Lm : sm + L::T;  // L = T when nothing is observed
+    // ---- X = L P, then S2raw = X L^T (tensor cores); S2raw overwrites X (all fragment loads of X are behind its mma's)
+    {
+      double c4[4][4][2];
+      mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
+      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+      __syncwarp();
+      mm32<false, true, LD>(c4, sm + L::X, Lsrc, lane);
+      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+    }
+    __syncwarp();
+    // ---- P' = sym(C + S2raw + KH Kp^T) row, a' ; tape
+    const bool taped = tp && t + 1 < n;
+    {
+      double S[M];
+      rowD_load<M>(S, sm + L::X + i * LD);
+#pragma unroll
+      for (int j = 0; j < M; ++j) S[j] = fma(0.5, S[j] + sm[L::X + j * LD + i], Cs[j]);
+      if (observed) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+#pragma unroll
+          for (int k = 0; k < P; ++k)
+            S[j] = fma(0.5, fma(KH[k], sm[L::Kp + j * P + k], sm[L::KH + j * P + k] * g.Kp[k]), S[j]);
+        }
+      }
+      if (act) {
+        rowD_store<M>(sm + L::Pm + i * LD, S);
+        sm[L::a + i] = an;
+        if (taped) {
+          tp[i] = an;
+          double* trow = tp + M + i * M - (i * (i - 1)) / 2 - i;
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+            if (j >= i) trow[j] = S[j];
+        }
+      }
+    }
+    if (taped) tp += KT;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    double ll = llsum - 0.5 * acc.value();
+    if (info != 0) ll = nan("");
+    if (A.loglik) A.loglik[u] = ll;
+    if (A.info) A.info[u] = info;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ adjoint
+template <int M, int P, bool NEED_T>
+__device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lane) {
+  using L = RowsDLayout<M, P, NEED_T>;
+  constexpr int KT = L::KT, LD = L::LD;
+  const int n = A.n;
+  const long long draw = u / A.n_series;
+  const bool act = lane < M;
+  const int i = act ? lane : 0;
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* tape = A.tape + u * (long long)(n - 1) * KT;  // entry t-1 = predicted moments of step t
+  for (int k = lane; k < L::bwd_doubles; k += 32) sm[k] = 0.0;  // zero padding, Pb = 0, ab = 0
+  __syncwarp();
+  if (n >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(n - 2) * KT, lane);
+  for (int k = lane; k < M * M; k += 32) {
+    const int rr = k / M, cc = k - rr * M;
+    sm[L::T + rr * LD + cc] = Tp[k];
+  }
+  for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
+  for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
+  __syncwarp();
+
+  const double* y = A.y.p;
+  const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
+  const bool need_H = (A.gH != nullptr);
+  // gradient accumulators: the lane's rows of Cb (and Tb) in registers; lanes < P hold rows of Hb; cb (row), db (lane)
+  double Cb[M], Tb[NEED_T ? M : 1], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
+#pragma unroll
+  for (int j = 0; j < M; ++j) Cb[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < (NEED_T ? M : 1); ++j) Tb[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < P; ++j) Hb[j] = 0.0;
+  RowDGain<M, P> g;
+  double yt[P], ynx[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[(long long)(n - 1) * P + j];
+
+  for (int t = n - 1; t >= 0; --t) {
+    // ---- predicted moments of step t -> shared memory (Pm's slot held W: its padding is zero either way)
+    if (t == 0) {
+      const double* P0p = A.P0.p + draw * A.P0.bs;
+      for (int k = lane; k < M * M; k += 32) {
+        const int rr = k / M, cc = k - rr * M;
+        sm[L::Pm + rr * LD + cc] = P0p[k];
+      }
+      if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
+    } else {
+      rows_tape_wait();
+      __syncwarp();
+      const double* tq = sm + L::tp;
+      if (act) {
+        sm[L::a + i] = tq[i];
+        double Pr[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          const int lo = i < j ? i : j, hi = i < j ? j : i;
+          Pr[j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
+        }
+        rowD_store<M>(sm + L::Pm + i * LD, Pr);
+      }
+      __syncwarp();  // every lane has read the staging buffer: refill it for step t-1
+      if (t >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(t - 2) * KT, lane);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t > 0 ? t - 1 : 0) * P + j];
+    }
+    const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
+    bool observed = true;
+#pragma unroll
+    for (int j = 0; j < P; ++j) observed = observed && (yt[j] == yt[j]);
+    if (observed) rowsD_gain<M, P, L>(sm, yt, A.d_sign, dv, i, act, g);
+    const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
+    if (t == 0) {  // P0 may be any matrix: X needs P + P^T (for t >= 1 the taped P is symmetric: P + P^T = 2 P)
+      double S0[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) S0[j] = 0.5 * (sm[L::Pm + i * LD + j] + sm[L::Pm + j * LD + i]);
+      __syncwarp();
+      if (act) rowD_store<M>(sm + L::Pm + i * LD, S0);
+      __syncwarp();
+    }
+    // ---- 1: X = 2 L P (tensor cores) -> Xb (with T-bar) or Pm's slot (only X Z^T is needed) ; Ps = sym(Pb) in place
+    cb += abi;
+    {
+      double c4[4][4][2];
+      mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
+      mm32_store<LD>(sm + (NEED_T ? L::Xb : L::Pm), c4, 2.0, lane);  // Pm's fragment loads are behind the mma's
+    }
+    {
+      double Ps[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        Ps[j] = 0.5 * (sm[L::Pb + i * LD + j] + sm[L::Pb + j * LD + i]);
+        Cb[j] += Ps[j];
+      }
+      __syncwarp();  // every lane has read its row and column of Pb; X is visible
+      if (act) rowD_store<M>(sm + L::Pb + i * LD, Ps);
+    }
+    if (!NEED_T && observed) {  // lz = X Z^T rows
+      double Xr[M];
+      rowD_load<M>(Xr, sm + L::Pm + i * LD);
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) s = fma(Xr[j], sm[L::Z + e * M + j], s);
+        if (act) sm[L::lz + i * P + e] = s;
+      }
+    }
+    __syncwarp();  // Ps, lz visible; nobody reads X in Pm's slot any more
+    // ---- 2: W = Ps L (tensor cores) -> Pm's slot ; (T-bar) Lb = Ps X -> Xb's slot ; PK, Kb, T^T ab
+    {
+      double c4[4][4][2];
+      mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
+      mm32_store<LD>(sm + L::W, c4, 1.0, lane);
+      if (NEED_T) {
+        mm32<false, false, LD>(c4, sm + L::Pb, sm + L::Xb, lane);
+        mm32_store<LD>(sm + L::Xb, c4, 1.0, lane);
+      }
+    }
+    const double* Psr = sm + L::Pb + i * LD;  // the lane's Ps row (Pb is not written again before phase 3's store)
+    double lbz[P];
+#pragma unroll
+    for (int e = 0; e < P; ++e) lbz[e] = 0.0;
+    if (!NEED_T && observed) {
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) lbz[e] = fma(Psr[k], sm[L::lz + k * P + e], lbz[e]);
+      }
+    }
+    double abn = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) abn = fma(sm[L::T + k * LD + i], sm[L::ab + k], abn);
+    double PK[P], Kb[P];
+    if (observed) {
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(Psr[k], sm[L::Kp + k * P + e], s);
+        PK[e] = s;
+      }
+    }
+    __syncwarp();  // W (and Lb) visible
+    if (NEED_T) {
+      double Lb[M];
+      rowD_load<M>(Lb, sm + L::Xb + i * LD);
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        Tb[NEED_T ? j : 0] += fma(abi, sm[L::a + j], Lb[j]);  // Tb += ab a^T + Lb
+        if (observed) {
+#pragma unroll
+          for (int e = 0; e < P; ++e) lbz[e] = fma(Lb[j], sm[L::Z + e * M + j], lbz[e]);
+        }
+      }
+    }
+    if (observed) {
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        double s = abi * g.v[e] - lbz[e];
+#pragma unroll
+        for (int k = 0; k < P; ++k) s = fma(PK[k], sm[L::H + k * P + e] + sm[L::H + e * P + k], s);
+        Kb[e] = s;
+      }
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          sm[L::Kb + i * P + e] = Kb[e];
+          if (need_H) sm[L::PK + i * P + e] = PK[e];
+        }
+      }
+    }
+    // ---- 3: Pb' = L^T W (tensor cores) -> Pb (Ps rows were last read above, by their owners, before this point in
+    //         program order of every lane; the store follows the last mma, which all lanes execute together)
+    __syncwarp();  // Kb visible; all row reads of Ps done
+    {
+      double c4[4][4][2];
+      mm32<true, false, LD>(c4, Lsrc, sm + L::W, lane);
+      mm32_store<LD>(sm + L::Pb, c4, 1.0, lane);
+    }
+    double vb[P], Fb[P * P], TMb[P];
+    if (observed) {
+      double Q1[P * P];
+#pragma unroll
+      for (int a2 = 0; a2 < P; ++a2) {
+        double s = -lb * g.w[a2];
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
+        vb[a2] = s;
+#pragma unroll
+        for (int b2 = 0; b2 < P; ++b2) {
+          double q1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < M; ++k) q1 = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q1);
+          Q1[a2 * P + b2] = q1;
+        }
+      }
+#pragma unroll
+      for (int a2 = 0; a2 < P; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 < P; ++b2) {
+          double s = -0.5 * lb * (g.Fi[b2 * P + a2] - g.w[a2] * g.w[b2]);
+#pragma unroll
+          for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
+          Fb[a2 * P + b2] = s;
+        }
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) s = fma(Kb[k], g.Fi[e * P + k], s);
+        TMb[e] = s;
+      }
+      if (NEED_T) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) Tb[NEED_T ? j : 0] = fma(TMb[k], sm[L::Mm + j * P + k], Tb[NEED_T ? j : 0]);
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) sm[L::TMb + i * P + e] = TMb[e];
+      }
+    }
+    __syncwarp();  // Pb' and TMb visible; ab's readers are done
+    // ---- 4: (observed) Mb = T^T TMb + Z^T Fb ; Pb' row += Mb Z ; ab' = T^T ab - Z^T vb
+    if (observed) {
+      double Mb[P];
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(sm[L::T + k * LD + i], sm[L::TMb + k * P + e], s);
+#pragma unroll
+        for (int k = 0; k < P; ++k) s = fma(sm[L::Z + k * M + i], Fb[k * P + e], s);
+        Mb[e] = s;
+      }
+      double Pbn[M];
+      rowD_load<M>(Pbn, sm + L::Pb + i * LD);
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) Pbn[j] = fma(Mb[k], sm[L::Z + k * M + j], Pbn[j]);
+      }
+      if (act) rowD_store<M>(sm + L::Pb + i * LD, Pbn);
+#pragma unroll
+      for (int k = 0; k < P; ++k) abn = fma(-sm[L::Z + k * M + i], vb[k], abn);
+#pragma unroll
+      for (int k = 0; k < P; ++k)
+        if (lane == k) db = fma(-A.d_sign, vb[k], db);
+      if (need_H) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          if (lane != e) continue;
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            double s = Hb[j] + Fb[e * P + j];
+#pragma unroll
+            for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + e], sm[L::PK + k * P + j], s);  // + Kp^T Ps Kp
+            Hb[j] = s;
+          }
+        }
+      }
+    }
+    if (act) sm[L::ab + i] = abn;
+    abi = abn;
+    __syncwarp();
+  }
+  // ---- write-out (row i by lane i)
+  if (act) {
+    if (A.ga0) A.ga0[u * M + i] = abi;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+      if (NEED_T && A.gT) A.gT[u * M * M + i * M + j] = Tb[NEED_T ? j : 0];
+      if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
+    }
+    if (A.gc) A.gc[u * M + i] = cb;
+  }
+  if (lane < P) {
+    if (A.gd) A.gd[u * P + lane] = db;
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+      if (A.gH) A.gH[u * P * P + lane * P + j] = Hb[j];
+  }
+}
+
+}  // namespace kfb
