@@ -9,8 +9,10 @@
 // tools/dmma_probe.cu measured 37.1 TFLOP/s for register-operand DMMA on this B200 - the same as the DFMA peak - already
 // at one warp per SM sub-partition with four independent accumulator tiles.
 //
-// Matrices live in shared memory as 32 x 32 tiles-of-8 with leading dimension LD = 36 doubles (rows 16-byte aligned,
-// fragment loads at most 2-way bank-conflicted); rows / columns >= m are zero and stay zero (products of zero padding).
+// Matrices live in shared memory as 32 x 32 tiles-of-8 with leading dimension LD = 34 doubles: rows 16-byte aligned and
+// LD/2 odd, so the row-per-lane 16-byte accesses of a quarter warp fall on 8 distinct bank groups (LD = 36 makes the
+// fragment loads conflict-free instead but 2-way conflicts every row access: measured 357 ms vs 326 ms per evaluation of
+// config 4; LD = 38: 332 ms).  Rows / columns >= m are zero and stay zero (products of zero padding).
 // Transposed operands cost nothing: A^T / B^T just swap the two fragment access patterns.
 #pragma once
 #include "kf_core.cuh"
@@ -21,7 +23,10 @@ namespace kfb {
 template <int M, int P, bool NEED_T>
 struct RowsDLayout {
   static_assert(M % 2 == 0 && M > 16 && M <= 32 && P <= 3, "even k_states in 18..32");
-  static constexpr int LD = 36, MS = 32 * LD;  // one padded matrix
+#ifndef KFB_ROWSD_LD
+#define KFB_ROWSD_LD 34
+#endif
+  static constexpr int LD = KFB_ROWSD_LD, MS = 32 * LD;  // one padded matrix
   static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), ME = M + (M & 1);
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
   static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MPE,
