@@ -73,6 +73,9 @@ __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, co
 // D = alpha * acc (full 32 x 32 including the zero padding)
 template <int LD>
 __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][2], double alpha, int lane) {
+  // D may be one of the product's own operands (X <- X L^T, Pm's slot <- 2 L Pm, Xb <- Ps Xb): every fragment load is
+  // behind an mma.sync that consumed it, but make the ordering explicit (and visible to racecheck)
+  __syncwarp();
   const int r = lane >> 2, c = lane & 3;
 #pragma unroll
   for (int I = 0; I < 4; ++I)
