@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(128, 1) kf_rowsL_kernel(const __grid_constant_
   else rowsL_forward<M, P>(A, u, sm, threadIdx.x & 31, 0xffffffffu);
 }
 
-// Same path with the m^3 products on the FP64 tensor cores (kf_rowsD.cuh).
-template <int M, int P, bool BWD, bool NEED_T>
+// Same path with the m^3 products on the FP64 tensor cores (kf_rowsD.cuh); MK = MK_STD or MK_STEADY.
+template <int M, int P, int MK, bool BWD, bool NEED_T>
 __global__ void __launch_bounds__(128, 1) kf_rowsD_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   constexpr int per_unit = BWD ? RowsDLayout<M, P, NEED_T>::bwd_doubles : RowsDLayout<M, P, false>::fwd_doubles;
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(128, 1) kf_rowsD_kernel(const __grid_constant_
   const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (u >= A.U) return;
   double* sm = kf_dyn_smem + (size_t)warp * per_unit;
-  if (BWD) rowsD_backward<M, P, NEED_T>(A, u, sm, threadIdx.x & 31);
-  else rowsD_forward<M, P>(A, u, sm, threadIdx.x & 31);
+  if (BWD) rowsD_backward<M, P, MK, NEED_T>(A, u, sm, threadIdx.x & 31);
+  else rowsD_forward<M, P, MK>(A, u, sm, threadIdx.x & 31);
 }
 
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----

@@ -34,8 +34,8 @@ struct RowsDLayout {
   // forward only: X (then S2) ; KH rows
   static constexpr int X = END_COMMON, KH = X + MS, END_FWD = KH + MPE;
   // adjoint only: W / X-for-lz live in Pm's slot; Lb lives in Xb's slot
-  static constexpr int Pb = END_COMMON, W = Pm, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MPE, lz = PK + MPE, ab = lz + MPE,
-                       tp = ab + ME, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0);
+  static constexpr int Pb = END_COMMON, W = Pm, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MPE, lz = PK + MPE, TMs = lz + MPE,
+                       ab = TMs + MPE, tp = ab + ME, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0);
   static constexpr int fwd_doubles = (END_FWD + 1) & ~1, bwd_doubles = (END_BWD + 1) & ~1;
 };
 
@@ -103,15 +103,16 @@ __device__ __forceinline__ void rowD_load(double (&v)[M], const double* src) {
 
 template <int M, int P>
 struct RowDGain {
-  double Kp[P], Fi[P * P], v[P], w[P], piv[P], quad;
+  double Kp[P], TM[P], Fi[P * P], v[P], w[P], piv[P], quad;
   bool ok;
 };
 
 // v, Mm | TM, F, F^-1, w, quad, Kp, Lm for an observed step (row-per-lane).  Leaves Mm, Kp, Lm in shared memory (visible
 // after the trailing sync); returns the lane's Kp row and (every lane) v, F^-1, w.
-template <int M, int P, class L>
-__device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P], int i, bool act,
-                                           RowDGain<M, P>& g) {
+// MK_STEADY: the gain matrix is the fixed Gss = (Z Pss Z^T + H)^-1 instead of F^-1 (F is still factorised for log det).
+template <int M, int P, int MK, class L>
+__device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P],
+                                           const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g) {
   constexpr int LD = L::LD;
   // ---- A: Mm row (own P row x Z rows), v (every lane)
   {
@@ -172,7 +173,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], g.v[k], s);
+    for (int k = 0; k < P; ++k) s = fma(MK == MK_STEADY ? Gss[j * P + k] : g.Fi[j * P + k], g.v[k], s);
     g.w[j] = s;
     qd = fma(g.v[j], s, qd);
   }
@@ -181,8 +182,9 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(TM[k], g.Fi[k * P + j], s);
+    for (int k = 0; k < P; ++k) s = fma(TM[k], MK == MK_STEADY ? Gss[k * P + j] : g.Fi[k * P + j], s);
     g.Kp[j] = s;
+    g.TM[j] = TM[j];
   }
   {
     const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
@@ -207,7 +209,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int M, int P>
+template <int M, int P, int MK>
 __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane) {
   using L = RowsDLayout<M, P, false>;
   constexpr int KT = L::KT, LD = L::LD;
@@ -219,7 +221,10 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
   const double* Cp = A.C.p + draw * A.C.bs;
-  const double* P0p = A.P0.p + draw * A.P0.bs;
+  const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;  // steady: starts at Pss
+  double Gss[P * P];
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
   for (int k = lane; k < L::fwd_doubles; k += 32) sm[k] = 0.0;  // zero padding everywhere
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
@@ -275,7 +280,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
 #pragma unroll
     for (int j = 0; j < P; ++j) KH[j] = 0.0;
     if (observed) {
-      rowsD_gain<M, P, L>(sm, yt, A.d_sign, dv, i, act, g);
+      rowsD_gain<M, P, MK, L>(sm, yt, A.d_sign, dv, Gss, i, act, g);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll
@@ -343,7 +348,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
 }
 
 // ------------------------------------------------------------------------------------------------ adjoint
-template <int M, int P, bool NEED_T>
+template <int M, int P, int MK, bool NEED_T>
 __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lane) {
   using L = RowsDLayout<M, P, NEED_T>;
   constexpr int KT = L::KT, LD = L::LD;
@@ -371,7 +376,13 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 
   const double* y = A.y.p;
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
-  const bool need_H = (A.gH != nullptr);
+  const bool need_H = (A.gH != nullptr) || (MK == MK_STEADY);
+  double Gss[P * P], Gb[P * P];  // steady state: fixed gain matrix and its cotangent (every lane holds all of it)
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) {
+    Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
+    Gb[k] = 0.0;
+  }
   // gradient accumulators: the lane's rows of Cb (and Tb) in registers; lanes < P hold rows of Hb; cb (row), db (lane)
   double Cb[M], Tb[NEED_T ? M : 1], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
 #pragma unroll
@@ -388,7 +399,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   for (int t = n - 1; t >= 0; --t) {
     // ---- predicted moments of step t -> shared memory (Pm's slot held W: its padding is zero either way)
     if (t == 0) {
-      const double* P0p = A.P0.p + draw * A.P0.bs;
+      const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
       for (int k = lane; k < M * M; k += 32) {
         const int rr = k / M, cc = k - rr * M;
         sm[L::Pm + rr * LD + cc] = P0p[k];
@@ -421,7 +432,13 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     bool observed = true;
 #pragma unroll
     for (int j = 0; j < P; ++j) observed = observed && (yt[j] == yt[j]);
-    if (observed) rowsD_gain<M, P, L>(sm, yt, A.d_sign, dv, i, act, g);
+    if (observed) {
+      rowsD_gain<M, P, MK, L>(sm, yt, A.d_sign, dv, Gss, i, act, g);
+      if (MK == MK_STEADY && act) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) sm[L::TMs + i * P + e] = g.TM[e];  // read by every lane in phase 3 (after syncs)
+      }
+    }
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
     if (t == 0) {  // P0 may be any matrix: X needs P + P^T (for t >= 1 the taped P is symmetric: P + P^T = 2 P)
       double S0[M];
@@ -533,6 +550,33 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     double vb[P], Fb[P * P], TMb[P];
     if (observed) {
+      if (MK == MK_STEADY) {
+        // vb = Kp^T ab - lb sym(Gss) v ; Gss-bar += TM^T Kb - lb/2 v v^T ; Fb = -lb/2 F^-T ; TMb = Kb Gss^T
+#pragma unroll
+        for (int a2 = 0; a2 < P; ++a2) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) s = fma(-0.5 * lb * (Gss[a2 * P + b2] + Gss[b2 * P + a2]), g.v[b2], s);
+          vb[a2] = s;
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) {
+            double q1 = Gb[a2 * P + b2];
+#pragma unroll
+            for (int k = 0; k < M; ++k) q1 = fma(sm[L::TMs + k * P + a2], sm[L::Kb + k * P + b2], q1);
+            Gb[a2 * P + b2] = fma(-0.5 * lb * g.v[a2], g.v[b2], q1);
+            Fb[a2 * P + b2] = -0.5 * lb * g.Fi[b2 * P + a2];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < P; ++k) s = fma(Kb[k], Gss[e * P + k], s);
+          TMb[e] = s;
+        }
+      } else {
       double Q1[P * P];
 #pragma unroll
       for (int a2 = 0; a2 < P; ++a2) {
@@ -563,6 +607,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
         for (int k = 0; k < P; ++k) s = fma(Kb[k], g.Fi[e * P + k], s);
         TMb[e] = s;
+      }
       }
       if (NEED_T) {
 #pragma unroll
@@ -625,7 +670,12 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     if (A.ga0) A.ga0[u * M + i] = abi;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+      if (MK == MK_STEADY) {
+        if (A.gPss) A.gPss[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+        if (A.gP0) A.gP0[u * M * M + i * M + j] = 0.0;
+      } else if (A.gP0) {
+        A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+      }
       if (NEED_T && A.gT) A.gT[u * M * M + i * M + j] = Tb[NEED_T ? j : 0];
       if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
     }
@@ -636,6 +686,10 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
     for (int j = 0; j < P; ++j)
       if (A.gH) A.gH[u * P * P + lane * P + j] = Hb[j];
+  }
+  if (MK == MK_STEADY && lane == 0 && A.gGss) {
+#pragma unroll
+    for (int k = 0; k < P * P; ++k) A.gGss[u * P * P + k] = Gb[k];
   }
 }
 

@@ -316,6 +316,34 @@ def test_fused_row_kernels_hot_path(dims, wrt):
             assert np.abs(got - w[b] * gref[k]).max() / (abs(w[b]) * scale) < RTOL, (k, b)
 
 
+@pytest.mark.parametrize("wrt", [("a0", "T", "R", "H", "Q", "c", "d"), ("R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
+def test_fused_large_system_steady_state(wrt):
+    """SteadyStateFilter at k_states = 30 through the tensor-core row kernels (kf_rowsD.cuh, MK_STEADY) + DARE kernels."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = 30, 1, 3
+    rng = np.random.default_rng(77)
+    B, n = 5, 20
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1) for _ in range(B)]
+    y = systems[0][0]
+    cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    bk = BatchedKalman("steady_state", n, m, p, r, n_draws=B)
+    out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                     c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
+    g = bk.backward(wrt=wrt)
+    assert int(out["info"].abs().max()) == 0
+    ll = out["loglik"].cpu().numpy()
+    for b in (0, 4):
+        args = (y,) + tuple(systems[b][1:])
+        ref, gref = kt.loglik_and_grads("steady_state", *args, c=cs[b][:, None], d=ds[b][:, None])
+        assert abs(ll[b] - ref) < RTOL * abs(ref)
+        for k in wrt:
+            got = g[k][b].cpu().numpy().reshape(gref[k].shape)
+            scale = max(np.abs(gref[k]).max(), 1e-12)
+            assert np.abs(got - gref[k]).max() / scale < 1e-7, (k, b)  # DARE adjoint: 1e-7 as in the other steady tests
+
+
 @pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
 @pytest.mark.parametrize("n", [1, 2, 3])
 def test_very_short_series(n, force_coop):
