@@ -22,6 +22,7 @@ template <int M, int P>
 struct ThreadCtx {
   static constexpr bool TV = false;
   static constexpr bool PIPELINE = false;  // adjoint: overlap gain(t-1) with adjoint(t)
+  static constexpr bool SKIP_LB = false;   // adjoint without T-bar / Z-bar: keep the single code path (a run-time branch cost the m = 2 kernel 14 %)
   template <int SZ>
   using Buf = RegBuf<(SZ == SZ_M ? M : SZ == SZ_P ? P : SZ == SZ_MM ? M * M : SZ == SZ_MP ? M * P : SZ == SZ_PP ? P * P : M + (M * (M + 1)) / 2)>;
   const double* y_smem;  // observations staged in shared memory (shared y) or nullptr
@@ -106,6 +107,7 @@ struct ThreadCtx {
 struct CoopCtx {
   static constexpr bool TV = true;
   static constexpr bool PIPELINE = false;
+  static constexpr bool SKIP_LB = true;    // adjoint without T-bar / Z-bar: skip the dense Lb product (kf_pred.cuh)
   int m_, p_, lane_, G_;
   double* arena;
   int off, cap;
@@ -246,6 +248,7 @@ template <int M, int P, int G_>
 struct CoopCtxT {
   static constexpr bool TV = false;
   static constexpr bool PIPELINE = false;
+  static constexpr bool SKIP_LB = true;    // adjoint without T-bar / Z-bar: skip the dense Lb product (kf_pred.cuh)
   static constexpr int KT = M + (M * (M + 1)) / 2;
   int lane_;
   unsigned mask_;

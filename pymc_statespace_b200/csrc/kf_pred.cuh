@@ -250,7 +250,9 @@ KFB_HD void backward_unit_pred(X& x, const KfArgs& A, long long u) {
   // T-bar: structural models (local level, trend + seasonal: config 4) have a constant transition matrix.  Without T-bar
   // and Z-bar the dense product Lb = Ps L (P + P^T) - one of the four m^3 products of the adjoint step - is only needed
   // through Lb Z^T = Ps (L (P + P^T) Z^T): two m^2 p products instead.
-  const bool need_Lb = (A.gT != nullptr) || need_Z;
+  // Cooperative contexts only (X::SKIP_LB): in the thread-per-unit kernels the extra run-time branch cost the m = 2
+  // headline kernel 14 % (register allocation), and m^3 is tiny there.
+  const bool need_Lb = !X::SKIP_LB || (A.gT != nullptr) || need_Z;
 
   // ---- inputs of step t (tape entries are consumed in strictly descending order)
   auto prepare = [&](int t, StepSet<X>& S) {
