@@ -101,6 +101,21 @@ __device__ __forceinline__ void rowD_load(double (&v)[M], const double* src) {
   }
 }
 
+// init + sum_{k<N} x_k y_k with four interleaved partial sums.  With one warp per SM sub-partition nothing hides the
+// ~30-cycle dependent-issue latency of a DFMA chain: a length-30 dot product as ONE chain is ~1000 cycles, and the
+// row-wise phases of a step contain about ten of them (they were ~2/3 of the step time in the first version).
+template <int N, class F>
+__device__ __forceinline__ double dot4(double init, F f) {
+  double s[4] = {init, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double x, y;
+    f(k, x, y);
+    s[k & 3] = fma(x, y, s[k & 3]);
+  }
+  return (s[0] + s[1]) + (s[2] + s[3]);
+}
+
 template <int M, int P>
 struct RowDGain {
   double Kp[P], TM[P], Fi[P * P], v[P], w[P], piv[P], quad;
@@ -116,56 +131,68 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
   constexpr int LD = L::LD;
   // ---- A: Mm row (own P row x Z rows), v (every lane)
   {
-    double Mr[P];
+    double Mr[P][4], vr[P][4];  // four partial sums each (see dot4)
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      Mr[j] = 0.0;
-      g.v[j] = yt[j] - d_sign * dv[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Mr[j][q] = vr[j][q] = 0.0;
+      vr[j][0] = yt[j] - d_sign * dv[j];
     }
     const double2* pr = reinterpret_cast<const double2*>(sm + L::Pm + i * LD);
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
       const double2 pk = pr[k], ak = av[k];
+      const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + j * M + 2 * k);
-        Mr[j] = fma(pk.x, z.x, Mr[j]);
-        Mr[j] = fma(pk.y, z.y, Mr[j]);
-        g.v[j] = fma(-z.x, ak.x, g.v[j]);
-        g.v[j] = fma(-z.y, ak.y, g.v[j]);
+        Mr[j][q] = fma(pk.x, z.x, Mr[j][q]);
+        Mr[j][q + 1] = fma(pk.y, z.y, Mr[j][q + 1]);
+        vr[j][q] = fma(-z.x, ak.x, vr[j][q]);
+        vr[j][q + 1] = fma(-z.y, ak.y, vr[j][q + 1]);
       }
     }
-    if (act) {
 #pragma unroll
-      for (int j = 0; j < P; ++j) sm[L::Mm + i * P + j] = Mr[j];
+    for (int j = 0; j < P; ++j) {
+      g.v[j] = (vr[j][0] + vr[j][1]) + (vr[j][2] + vr[j][3]);
+      if (act) sm[L::Mm + i * P + j] = (Mr[j][0] + Mr[j][1]) + (Mr[j][2] + Mr[j][3]);
     }
   }
   __syncwarp();
   // ---- B: TM row, F (every lane), inverse, w, quad, Kp row, Lm row
   double Fr[P * P], Lr[P * P], Lir[P * P], TM[P];
-#pragma unroll
-  for (int k = 0; k < P * P; ++k) Fr[k] = sm[L::H + k];
-#pragma unroll
-  for (int j = 0; j < P; ++j) TM[j] = 0.0;
   {
+    double Fq[P * P][4], Tq[P][4];  // four partial sums each (see dot4)
+#pragma unroll
+    for (int k = 0; k < P * P; ++k) {
+      Fq[k][0] = sm[L::H + k];
+      Fq[k][1] = Fq[k][2] = Fq[k][3] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) Tq[j][0] = Tq[j][1] = Tq[j][2] = Tq[j][3] = 0.0;
     const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
       const double2 tk = tr[k];
+      const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
         const double m0 = sm[L::Mm + (2 * k) * P + j], m1 = sm[L::Mm + (2 * k + 1) * P + j];
-        TM[j] = fma(tk.x, m0, TM[j]);
-        TM[j] = fma(tk.y, m1, TM[j]);
+        Tq[j][q] = fma(tk.x, m0, Tq[j][q]);
+        Tq[j][q + 1] = fma(tk.y, m1, Tq[j][q + 1]);
 #pragma unroll
         for (int e = 0; e < P; ++e) {
           const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
-          Fr[e * P + j] = fma(z.x, m0, Fr[e * P + j]);
-          Fr[e * P + j] = fma(z.y, m1, Fr[e * P + j]);
+          Fq[e * P + j][q] = fma(z.x, m0, Fq[e * P + j][q]);
+          Fq[e * P + j][q + 1] = fma(z.y, m1, Fq[e * P + j][q + 1]);
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < P * P; ++k) Fr[k] = (Fq[k][0] + Fq[k][1]) + (Fq[k][2] + Fq[k][3]);
+#pragma unroll
+    for (int j = 0; j < P; ++j) TM[j] = (Tq[j][0] + Tq[j][1]) + (Tq[j][2] + Tq[j][3]);
   }
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
   double qd = 0.0;
@@ -265,16 +292,19 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     for (int j = 0; j < P; ++j) nm += (yt[j] != yt[j]) ? 1 : 0;
     const bool observed = (nm == 0);
     // a' = T a + c (+ Kp v)
-    double an = ci;
+    double an;
     {
+      double aq[4] = {ci, 0.0, 0.0, 0.0};
       const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
         const double2 tk = tr[k], ak = av[k];
-        an = fma(tk.x, ak.x, an);
-        an = fma(tk.y, ak.y, an);
+        const int q = (k & 1) * 2;
+        aq[q] = fma(tk.x, ak.x, aq[q]);
+        aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
       }
+      an = (aq[0] + aq[1]) + (aq[2] + aq[3]);
     }
     double KH[P];
 #pragma unroll
@@ -470,9 +500,10 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       rowD_load<M>(Xr, sm + L::Pm + i * LD);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) s = fma(Xr[j], sm[L::Z + e * M + j], s);
+        const double s = dot4<M>(0.0, [&](int j, double& x, double& y) {
+          x = Xr[j];
+          y = sm[L::Z + e * M + j];
+        });
         if (act) sm[L::lz + i * P + e] = s;
       }
     }
@@ -493,22 +524,24 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     for (int e = 0; e < P; ++e) lbz[e] = 0.0;
     if (!NEED_T && observed) {
 #pragma unroll
-      for (int k = 0; k < M; ++k) {
-#pragma unroll
-        for (int e = 0; e < P; ++e) lbz[e] = fma(Psr[k], sm[L::lz + k * P + e], lbz[e]);
-      }
+      for (int e = 0; e < P; ++e)
+        lbz[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
+          x = Psr[k];
+          y = sm[L::lz + k * P + e];
+        });
     }
-    double abn = 0.0;
-#pragma unroll
-    for (int k = 0; k < M; ++k) abn = fma(sm[L::T + k * LD + i], sm[L::ab + k], abn);
+    double abn = dot4<M>(0.0, [&](int k, double& x, double& y) {
+      x = sm[L::T + k * LD + i];
+      y = sm[L::ab + k];
+    });
     double PK[P], Kb[P];
     if (observed) {
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(Psr[k], sm[L::Kp + k * P + e], s);
-        PK[e] = s;
+        PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
+          x = Psr[k];
+          y = sm[L::Kp + k * P + e];
+        });
       }
     }
     __syncwarp();  // W (and Lb) visible
@@ -518,10 +551,14 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         Tb[NEED_T ? j : 0] += fma(abi, sm[L::a + j], Lb[j]);  // Tb += ab a^T + Lb
-        if (observed) {
+      }
+      if (observed) {
 #pragma unroll
-          for (int e = 0; e < P; ++e) lbz[e] = fma(Lb[j], sm[L::Z + e * M + j], lbz[e]);
-        }
+        for (int e = 0; e < P; ++e)
+          lbz[e] = dot4<M>(0.0, [&](int j, double& x, double& y) {
+            x = Lb[j];
+            y = sm[L::Z + e * M + j];
+          });
       }
     }
     if (observed) {
@@ -554,17 +591,19 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         // vb = Kp^T ab - lb sym(Gss) v ; Gss-bar += TM^T Kb - lb/2 v v^T ; Fb = -lb/2 F^-T ; TMb = Kb Gss^T
 #pragma unroll
         for (int a2 = 0; a2 < P; ++a2) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
+          double s = dot4<M>(0.0, [&](int k, double& x, double& y) {
+            x = sm[L::Kp + k * P + a2];
+            y = sm[L::ab + k];
+          });
 #pragma unroll
           for (int b2 = 0; b2 < P; ++b2) s = fma(-0.5 * lb * (Gss[a2 * P + b2] + Gss[b2 * P + a2]), g.v[b2], s);
           vb[a2] = s;
 #pragma unroll
           for (int b2 = 0; b2 < P; ++b2) {
-            double q1 = Gb[a2 * P + b2];
-#pragma unroll
-            for (int k = 0; k < M; ++k) q1 = fma(sm[L::TMs + k * P + a2], sm[L::Kb + k * P + b2], q1);
+            const double q1 = dot4<M>(Gb[a2 * P + b2], [&](int k, double& x, double& y) {
+              x = sm[L::TMs + k * P + a2];
+              y = sm[L::Kb + k * P + b2];
+            });
             Gb[a2 * P + b2] = fma(-0.5 * lb * g.v[a2], g.v[b2], q1);
             Fb[a2 * P + b2] = -0.5 * lb * g.Fi[b2 * P + a2];
           }
@@ -580,17 +619,16 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       double Q1[P * P];
 #pragma unroll
       for (int a2 = 0; a2 < P; ++a2) {
-        double s = -lb * g.w[a2];
+        vb[a2] = dot4<M>(-lb * g.w[a2], [&](int k, double& x, double& y) {
+          x = sm[L::Kp + k * P + a2];
+          y = sm[L::ab + k];
+        });
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
-        vb[a2] = s;
-#pragma unroll
-        for (int b2 = 0; b2 < P; ++b2) {
-          double q1 = 0.0;
-#pragma unroll
-          for (int k = 0; k < M; ++k) q1 = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q1);
-          Q1[a2 * P + b2] = q1;
-        }
+        for (int b2 = 0; b2 < P; ++b2)
+          Q1[a2 * P + b2] = dot4<M>(0.0, [&](int k, double& x, double& y) {
+            x = sm[L::Kp + k * P + a2];
+            y = sm[L::Kb + k * P + b2];
+          });
       }
 #pragma unroll
       for (int a2 = 0; a2 < P; ++a2)
@@ -627,9 +665,10 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       double Mb[P];
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(sm[L::T + k * LD + i], sm[L::TMb + k * P + e], s);
+        double s = dot4<M>(0.0, [&](int k, double& x, double& y) {
+          x = sm[L::T + k * LD + i];
+          y = sm[L::TMb + k * P + e];
+        });
 #pragma unroll
         for (int k = 0; k < P; ++k) s = fma(sm[L::Z + k * M + i], Fb[k * P + e], s);
         Mb[e] = s;
@@ -653,10 +692,10 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           if (lane != e) continue;
 #pragma unroll
           for (int j = 0; j < P; ++j) {
-            double s = Hb[j] + Fb[e * P + j];
-#pragma unroll
-            for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + e], sm[L::PK + k * P + j], s);  // + Kp^T Ps Kp
-            Hb[j] = s;
+            Hb[j] = dot4<M>(Hb[j] + Fb[e * P + j], [&](int k, double& x, double& y) {  // + Kp^T Ps Kp
+              x = sm[L::Kp + k * P + e];
+              y = sm[L::PK + k * P + j];
+            });
           }
         }
       }
