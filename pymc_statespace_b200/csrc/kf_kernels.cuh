@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
 
 // Fused row-block-per-lane programs (kf_rows.cuh): G lanes per unit, 32/G units per warp, blockDim.x/32 warps per CTA.
 // BWD = adjoint.  Lanes beyond the last whole group of a warp shadow the warp's first unit without owning rows.
-template <int M, int P, int G, bool BWD, bool NEED_Z>
+template <int M, int P, int G, int MK, bool BWD, bool NEED_Z>
 __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (NEED_Z ? 2 : 3) : 4)) kf_rows_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
-  constexpr int per_unit = BWD ? RowsLayout<M, P, NEED_Z>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
+  constexpr int per_unit = BWD ? RowsLayout<M, P, NEED_Z, MK == MK_STEADY>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
   constexpr int UPW = RowsCfg<M, P, G>::UPW;
   const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int grp = lane32 / G, l = lane32 - grp * G;
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (N
   if (u >= A.U) return;
   const unsigned mask = __activemask();
   double* sm = kf_dyn_smem + (size_t)slot * per_unit;
-  if (BWD) rows_backward<M, P, G, NEED_Z>(A, u, sm, l, mask);
-  else rows_forward<M, P, G>(A, u, sm, l, mask);
+  if (BWD) rows_backward<M, P, G, MK, NEED_Z>(A, u, sm, l, mask);
+  else rows_forward<M, P, G, MK>(A, u, sm, l, mask);
 }
 
 // Fused row-per-lane, warp-per-unit programs for large systems (kf_rowsL.cuh).  BWD = adjoint, NEED_T = with T-bar.

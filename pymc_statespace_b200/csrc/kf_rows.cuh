@@ -27,7 +27,8 @@ struct RowsCfg {
 // NZ = the adjoint also produces Z-bar.  Without it Lb / Mb are never exchanged and nothing reads Pm after phase 1, so
 // W lives in Pm's slot; TMb (written in phase 3) always reuses X's slot (last read in phase 2).  At m = 6, p = 3 that
 // is 422 doubles per unit = 8 resident units-of-8 per SM instead of 6.
-template <int M, int P, bool NZ = true>
+// ST = steady-state filter: one more m x p exchange buffer (TM rows, for Gss-bar).
+template <int M, int P, bool NZ = true, bool ST = false>
 struct RowsLayout {
   static constexpr int MM = M * M, MP = M * P, PP = P * P, MPE = MP + (MP & 1);
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
@@ -38,7 +39,8 @@ struct RowsLayout {
   static constexpr int S2 = END_COMMON, END_FWD = S2 + MM;
   // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
   static constexpr int Pb = END_COMMON, X = Pb + MM, TMb = X, W = NZ ? X + MM : Pm, Lb = X + 2 * MM,
-                       Kb = NZ ? Lb + MM : X + MM, Mb = Kb + MPE, PK = NZ ? Mb + MPE : Kb + MPE, ab = PK + MPE,
+                       Kb = NZ ? Lb + MM : X + MM, Mb = Kb + MPE, PK = NZ ? Mb + MPE : Kb + MPE, TMs = PK + MPE,
+                       ab = TMs + (ST ? MPE : 0),
                        Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
   // unit stride == 6 (mod 16) doubles = 48 bytes modulo the 128-byte bank row: with 16-byte accesses served a quarter
   // warp (two units of 4 lanes) at a time, both the lanes' row blocks (96 bytes apart) and their column blocks (16 bytes
@@ -148,9 +150,11 @@ struct RowGain {
 
 // tr(q, k) = T[row q of this lane][k] (registers in the forward kernel, shared memory in the adjoint)
 // Pr = the lane's rows of the predicted covariance (registers).
-template <int M, int P, int R, class TR>
+// MK_STEADY: the gain matrix is the fixed Gss = (Z Pss Z^T + H)^-1 instead of F^-1 (F is still factorised for log det).
+template <int M, int P, int R, int MK, class TR>
 __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, const double (&dv)[P], unsigned mask,
-                                          const RowIdx<M, R>& rw, TR tr, const double (&Pr)[R][M], RowGain<M, P, R>& g) {
+                                          const RowIdx<M, R>& rw, TR tr, const double (&Pr)[R][M], const double (&Gss)[P * P],
+                                          RowGain<M, P, R>& g) {
   using L = RowsLayout<M, P>;
   // ---- phase A: v (every lane), Mm rows
   {
@@ -202,7 +206,7 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(g.Fi[j * P + k], g.v[k], s);
+    for (int k = 0; k < P; ++k) s = fma(MK == MK_STEADY ? Gss[j * P + k] : g.Fi[j * P + k], g.v[k], s);
     g.w[j] = s;
     qd = fma(g.v[j], s, qd);
   }
@@ -213,7 +217,7 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
     for (int j = 0; j < P; ++j) {
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < P; ++k) s = fma(g.TM[q][k], g.Fi[k * P + j], s);
+      for (int k = 0; k < P; ++k) s = fma(g.TM[q][k], MK == MK_STEADY ? Gss[k * P + j] : g.Fi[k * P + j], s);
       g.Kp[q][j] = s;
     }
 #pragma unroll
@@ -244,7 +248,7 @@ __device__ __forceinline__ int rows_count_missing(const double* yt) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int M, int P, int G>
+template <int M, int P, int G, int MK>
 __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
   using L = RowsLayout<M, P>;
   constexpr int R = RowsCfg<M, P, G>::R;
@@ -256,8 +260,11 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
   const double* Cp = A.C.p + draw * A.C.bs;
-  const double* P0p = A.P0.p + draw * A.P0.bs;
+  const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;  // steady: starts at Pss
   const double* a0p = A.a0.p + draw * A.a0.bs;
+  double Gss[P * P];
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
   if (l < G) {  // idle lanes of the warp (l == G) shadow a unit without owning anything
     for (int k = l; k < M * M; k += G) {
       sm[L::T + k] = Tp[k];
@@ -312,7 +319,7 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
       for (int q = 0; q < R; ++q) an[q] = fma(Tr[q][k], ak, an[q]);
     }
     if (nm == 0) {
-      rows_gain<M, P, R>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, g);
+      rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, Gss, g);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll
@@ -466,9 +473,9 @@ __device__ __forceinline__ void rows_tape_wait() {
 
 // NEED_Z: the caller wants Z-bar (never the case for the reference's models, whose design matrix is constant): the
 // Z-bar accumulators and the Lb / Mb exchanges exist only in that instantiation.
-template <int M, int P, int G, bool NEED_Z>
+template <int M, int P, int G, int MK, bool NEED_Z>
 __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
-  using L = RowsLayout<M, P, NEED_Z>;
+  using L = RowsLayout<M, P, NEED_Z, MK == MK_STEADY>;
   constexpr int R = RowsCfg<M, P, G>::R;
   constexpr int KT = L::KT;
   const int n = A.n;
@@ -500,7 +507,13 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
   const double* y = A.y.p;
   const double gl = A.g_loglik ? A.g_loglik[u] : 1.0;
   constexpr bool need_Z = NEED_Z;
-  const bool need_H = (A.gH != nullptr);
+  const bool need_H = (A.gH != nullptr) || (MK == MK_STEADY);
+  double Gss[P * P], Gb[P * P];  // steady state: fixed gain matrix and its cotangent (every lane holds all of it)
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) {
+    Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
+    Gb[k] = 0.0;
+  }
   // gradient accumulators: the lane's rows of Tb (registers) and Cb (shared memory: touched once per step, and the
   // registers are all taken); lanes < P hold rows of Zb, Hb; elements of cb (rows), db (lane)
   double Tb[R][M], Zb[NEED_Z ? M : 1], Hb[P], cb[R], db = 0.0;
@@ -530,7 +543,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
   for (int t = n - 1; t >= 0; --t) {
     // ---- predicted moments of step t -> shared memory (and the lane's rows of P in registers)
     if (t == 0) {
-      const double* P0p = A.P0.p + draw * A.P0.bs;
+      const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
 #pragma unroll
       for (int q = 0; q < R; ++q) {
 #pragma unroll
@@ -564,7 +577,8 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     const double lb = gl + (A.g_ll_obs ? A.g_ll_obs[u * n + t] : 0.0);
     const bool observed = (rows_count_missing<P>(yt) == 0);
     if (observed) {
-      rows_gain<M, P, R>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, g);
+      rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, Gss, g);
+      if (MK == MK_STEADY) store_rows<M, R, P>(sm + L::TMs, rw, g.TM);  // read by every lane in phase 3 (after syncs)
     } else {
 #pragma unroll
       for (int q = 0; q < R; ++q) {
@@ -711,38 +725,59 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     }
     double vb[P], Fb[P * P];
     if (observed) {
-      double Q1[P * P];
+      if (MK == MK_STEADY) {
+        // vb = Kp^T ab - lb sym(Gss) v ; Gss-bar += TM^T Kb - lb/2 v v^T ; Fb = -lb/2 F^-T
 #pragma unroll
-      for (int a2 = 0; a2 < P; ++a2) {
-        double s = -lb * g.w[a2];
+        for (int a2 = 0; a2 < P; ++a2) {
+          double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
-        vb[a2] = s;
+          for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
 #pragma unroll
-        for (int b2 = 0; b2 < P; ++b2) {
-          double q1 = 0.0;
+          for (int b2 = 0; b2 < P; ++b2) s = fma(-0.5 * lb * (Gss[a2 * P + b2] + Gss[b2 * P + a2]), g.v[b2], s);
+          vb[a2] = s;
 #pragma unroll
-          for (int k = 0; k < M; ++k) q1 = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q1);
-          Q1[a2 * P + b2] = q1;
+          for (int b2 = 0; b2 < P; ++b2) {
+            double q1 = Gb[a2 * P + b2];
+#pragma unroll
+            for (int k = 0; k < M; ++k) q1 = fma(sm[L::TMs + k * P + a2], sm[L::Kb + k * P + b2], q1);
+            Gb[a2 * P + b2] = fma(-0.5 * lb * g.v[a2], g.v[b2], q1);
+            Fb[a2 * P + b2] = -0.5 * lb * g.Fi[b2 * P + a2];
+          }
         }
+      } else {
+        double Q1[P * P];
+#pragma unroll
+        for (int a2 = 0; a2 < P; ++a2) {
+          double s = -lb * g.w[a2];
+#pragma unroll
+          for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
+          vb[a2] = s;
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) {
+            double q1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) q1 = fma(sm[L::Kp + k * P + a2], sm[L::Kb + k * P + b2], q1);
+            Q1[a2 * P + b2] = q1;
+          }
+        }
+#pragma unroll
+        for (int a2 = 0; a2 < P; ++a2)
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) {
+            double s = -0.5 * lb * (g.Fi[b2 * P + a2] - g.w[a2] * g.w[b2]);
+#pragma unroll
+            for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
+            Fb[a2 * P + b2] = s;
+          }
       }
-#pragma unroll
-      for (int a2 = 0; a2 < P; ++a2)
-#pragma unroll
-        for (int b2 = 0; b2 < P; ++b2) {
-          double s = -0.5 * lb * (g.Fi[b2 * P + a2] - g.w[a2] * g.w[b2]);
-#pragma unroll
-          for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
-          Fb[a2 * P + b2] = s;
-        }
-      double TMb[R][P];
+      double TMb[R][P];  // TMb = Kb G^T, G = F^-1 or Gss
 #pragma unroll
       for (int q = 0; q < R; ++q)
 #pragma unroll
         for (int j = 0; j < P; ++j) {
           double s = 0.0;
 #pragma unroll
-          for (int k = 0; k < P; ++k) s = fma(Kb[q][k], g.Fi[j * P + k], s);
+          for (int k = 0; k < P; ++k) s = fma(Kb[q][k], MK == MK_STEADY ? Gss[j * P + k] : g.Fi[j * P + k], s);
           TMb[q][j] = s;
         }
 #pragma unroll
@@ -854,7 +889,12 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       if (A.ga0) A.ga0[u * M + i] = sm[L::ab + i];
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        if (A.gP0) A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
+        if (MK == MK_STEADY) {
+          if (A.gPss) A.gPss[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
+          if (A.gP0) A.gP0[u * M * M + i * M + j] = 0.0;
+        } else if (A.gP0) {
+          A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * M + j];
+        }
         if (A.gT) A.gT[u * M * M + i * M + j] = Tb[q][j];
         if (A.gC) A.gC[u * M * M + i * M + j] = sm[L::Cb + i * M + j];
       }
@@ -867,6 +907,10 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
 #pragma unroll
     for (int j = 0; j < P; ++j)
       if (A.gH) A.gH[u * P * P + l * P + j] = Hb[j];
+  }
+  if (MK == MK_STEADY && l == 0 && A.gGss) {
+#pragma unroll
+    for (int k = 0; k < P * P; ++k) A.gGss[u * P * P + k] = Gb[k];
   }
 }
 

@@ -317,14 +317,16 @@ def test_fused_row_kernels_hot_path(dims, wrt):
 
 
 @pytest.mark.parametrize("wrt", [("a0", "T", "R", "H", "Q", "c", "d"), ("R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
-def test_fused_large_system_steady_state(wrt):
-    """SteadyStateFilter at k_states = 30 through the tensor-core row kernels (kf_rowsD.cuh, MK_STEADY) + DARE kernels."""
+@pytest.mark.parametrize("dims", [(30, 1, 3), (6, 3, 3), (5, 1, 2), (8, 2, 2)], ids=lambda d: "m%dp%dr%d" % d)
+def test_fused_row_kernels_steady_state(dims, wrt):
+    """SteadyStateFilter through the fused row kernels (MK_STEADY instantiations of kf_rows.cuh for k_states 5..8 and of the
+    tensor-core kf_rowsD.cuh for k_states = 30) + DARE kernels; no Z-bar."""
     from pymc_statespace_b200 import BatchedKalman
 
-    m, p, r = 30, 1, 3
-    rng = np.random.default_rng(77)
-    B, n = 5, 20
-    systems = [random_system(rng, m, p, r, n, scale_T=0.1) for _ in range(B)]
+    m, p, r = dims
+    rng = np.random.default_rng(77 + m)
+    B, n = 11, 20
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m == 30 else 0.25) for _ in range(B)]
     y = systems[0][0]
     cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
     stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
@@ -334,7 +336,7 @@ def test_fused_large_system_steady_state(wrt):
     g = bk.backward(wrt=wrt)
     assert int(out["info"].abs().max()) == 0
     ll = out["loglik"].cpu().numpy()
-    for b in (0, 4):
+    for b in (0, 10):
         args = (y,) + tuple(systems[b][1:])
         ref, gref = kt.loglik_and_grads("steady_state", *args, c=cs[b][:, None], d=ds[b][:, None])
         assert abs(ll[b] - ref) < RTOL * abs(ref)
