@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1000, help="time steps T")
     ap.add_argument("--cpu-sample-draws", type=int, default=0, help="draws in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e leg: eager launches instead of the captured CUDA graph")
     return ap.parse_args()
 
 
@@ -205,7 +206,14 @@ def main():
         packed = pack_logp_grad(logp, grad)
         return gather_logp_grad(packed, n_total) if world > 1 else packed
 
+    # single GPU: the public host-to-host call, captured once as a CUDA graph (KalmanLogp.capture_host_step: H2D of theta
+    # from pinned memory, every kernel of the evaluation, D2H of (logp, grad) into pinned memory) and replayed per step;
+    # multi-GPU keeps the eager sequence (the all-gather is not captured)
+    host_step = model.capture_host_step(theta_h, out_h) if world == 1 and not a.no_graph else None
+
     def step_e2e():
+        if host_step is not None:
+            return host_step()                            # replay + stream synchronise: the numbers are on the host
         th = theta_h.to(dev, non_blocking=True)
         logp, grad = model.logp_and_grad(th)
         packed = pack_logp_grad(logp, grad)
@@ -301,7 +309,10 @@ def main():
                        "draws_with_info": bad},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 * world),
-                    "d2h_bytes_per_step": int(out_h.numel() * 8 + (world - 1) * B * (1 + spec.n_theta) * 8)},
+                    "d2h_bytes_per_step": int(out_h.numel() * 8 + (world - 1) * B * (1 + spec.n_theta) * 8),
+                    "path": ("KalmanLogp.capture_host_step: pinned H2D + evaluation + pinned D2H replayed as one CUDA graph, "
+                             "stream-synchronised every step") if host_step is not None else
+                            "eager: pinned H2D, logp_and_grad, all-gather, pinned D2H, stream-synchronised every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "kf_thread_kernel<2,1,MK_STD,2> (adjoint recursion; the longest kernel)",

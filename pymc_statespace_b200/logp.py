@@ -25,6 +25,52 @@ from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapuno
 from .models import MATRICES, StateSpaceSpec
 
 
+class HostStepGraph:
+    """ONE CUDA graph for a whole host-to-host evaluation:
+
+        pinned-host theta[B, n_theta] -> H2D -> scatter + Lyapunov/DARE + Kalman forward + adjoint + scatter^T
+            -> packed [B, 1 + n_theta] = (logp, dlogp/dtheta) -> D2H into a pinned host buffer.
+
+    A sampler that keeps theta on the host pays ~12 kernel launches + 2 copies per leapfrog step; replaying them as one
+    graph removes the per-launch CPU cost that a per-step synchronisation otherwise exposes (measured on B200, configs[1]:
+    1.66 -> 1.58 ms per step end to end).  ``theta_host`` / ``out_host`` are captured BY ADDRESS: write the next theta into
+    ``theta_host`` in place, call the object, read ``out_host``.  Single-GPU (no collective inside the graph).
+    """
+
+    def __init__(self, model: "KalmanLogp", theta_host: torch.Tensor, out_host: torch.Tensor, warmup: int = 3):
+        B, nt = model.B, model.spec.n_theta
+        for name, t, shape in (("theta_host", theta_host, (B, nt)), ("out_host", out_host, (B, 1 + nt))):
+            if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float64
+                    and t.is_contiguous() and t.is_pinned() and tuple(t.shape) == shape):
+                raise TypeError(f"{name}: expected a pinned, contiguous float64 host tensor of shape {shape}")
+        self.model, self.theta_host, self.out_host = model, theta_host, out_host
+        dev = model.device
+        self._theta_dev = torch.empty((B, nt), dtype=torch.float64, device=dev)
+
+        def body():
+            self._theta_dev.copy_(theta_host, non_blocking=True)
+            logp, grad = model.logp_and_grad(self._theta_dev)
+            out_host.copy_(torch.cat([logp[:, None], grad], dim=1), non_blocking=True)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):  # lazy initialisation (function attributes, occupancy queries) outside capture
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                body()
+            self.info = model.info  # per-draw status of the captured evaluation (device tensor, refreshed by every replay)
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        torch.cuda.current_stream(self.model.device).synchronize()
+        return self.out_host
+
+
 def logp_and_grad_in_waves(spec: StateSpaceSpec, data, theta: torch.Tensor, filter_type: str = "standard",
                            strict_reference: bool = True, max_workspace_bytes: Optional[int] = None):
     """logp+grad for an arbitrarily large batch: draws are processed in waves whose tape fits the memory budget
@@ -143,6 +189,10 @@ class KalmanLogp:
         out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",))
         self.info = out["info"]
         return out["loglik"]
+
+    def capture_host_step(self, theta_host: torch.Tensor, out_host: torch.Tensor) -> "HostStepGraph":
+        """Capture host theta -> (logp, grad) on the host as one replayable CUDA graph (see ``HostStepGraph``)."""
+        return HostStepGraph(self, theta_host, out_host)
 
     def logp_and_grad(self, theta, g_loglik: Optional[torch.Tensor] = None):
         """Returns (logp[B], dlogp/dtheta[B, n_theta]); ``self.info[B]`` holds per-draw status."""

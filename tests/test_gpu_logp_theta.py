@@ -192,3 +192,27 @@ def test_waves_match_single_pass():
     per_draw = ((n - 1) * 5 + 16 + 64) * 8
     lp2, g2, info = logp_and_grad_in_waves(spec, y, th, max_workspace_bytes=per_draw * 300)  # 4 waves (300,300,300,100)
     assert torch.equal(lp, lp2) and torch.equal(g, g2) and int(info.abs().sum()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["arma", "varmax"])
+def test_host_step_graph_matches_eager(kind):
+    """KalmanLogp.capture_host_step: pinned-host theta -> (logp, grad) on the host as ONE replayed CUDA graph; identical
+    numbers to the eager call, and a replay picks up a new theta written into the captured host buffer."""
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.synthetic import arma11_workload, varmax20_workload
+
+    spec, y, theta = arma11_workload(300, 50) if kind == "arma" else varmax20_workload(n_draws=40, n=30)
+    B = theta.shape[0]
+    model = KalmanLogp(spec, y, n_draws=B, filter_type="standard")
+    th_h = torch.from_numpy(np.ascontiguousarray(theta)).pin_memory()
+    out_h = torch.empty((B, 1 + spec.n_theta), dtype=torch.float64).pin_memory()
+    step = model.capture_host_step(th_h, out_h)
+    for scale in (1.0, 0.9):
+        th_h.copy_(torch.from_numpy(theta * scale if kind == "arma" else theta * np.where(np.arange(theta.shape[1]) < 6, scale, 1.0)))
+        got = step().clone()
+        lp, g = model.logp_and_grad(th_h.to("cuda"))
+        torch.cuda.synchronize()
+        assert torch.equal(got[:, 0], lp.cpu()) and torch.equal(got[:, 1:], g.cpu())
+    with pytest.raises(TypeError):
+        model.capture_host_step(th_h.clone(), out_h)  # not pinned
