@@ -346,6 +346,34 @@ def test_fused_row_kernels_steady_state(dims, wrt):
             assert np.abs(got - gref[k]).max() / scale < 1e-7, (k, b)  # DARE adjoint: 1e-7 as in the other steady tests
 
 
+@pytest.mark.parametrize("n", [1, 2])
+@pytest.mark.parametrize("dims", [(6, 3, 3), (30, 1, 3)], ids=lambda d: "m%dp%dr%d" % d)
+def test_fused_row_kernels_very_short_series(dims, n):
+    """n = 1: no tape at all; n = 2: a single tape entry (the prefetch / double-buffer edge cases of the fused kernels)."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = dims
+    rng = np.random.default_rng(300 + m + n)
+    B = 3
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m == 30 else 0.25) for _ in range(B)]
+    y = systems[0][0]
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    for kind in ("standard", "steady_state"):
+        bk = BatchedKalman(kind, n, m, p, r, n_draws=B)
+        out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                         outputs=("loglik",), save_for_backward=True)
+        wrt = ("a0", "P0", "T", "R", "H", "Q") if kind == "standard" else ("a0", "T", "R", "H", "Q")
+        g = bk.backward(wrt=wrt)
+        ll = out["loglik"].cpu().numpy()
+        for b in range(B):
+            ref, gref = kt.loglik_and_grads(kind, y, *systems[b][1:])
+            assert abs(ll[b] - ref) < RTOL * abs(ref)
+            for k in wrt:
+                got = g[k][b].cpu().numpy().reshape(gref[k].shape)
+                scale = max(np.abs(gref[k]).max(), 1e-12)
+                assert np.abs(got - gref[k]).max() / scale < (1e-7 if kind == "steady_state" else RTOL), (kind, k, b)
+
+
 @pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
 @pytest.mark.parametrize("n", [1, 2, 3])
 def test_very_short_series(n, force_coop):
