@@ -479,19 +479,18 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       __syncwarp();
     }
     // ---- 1: X = 2 L P (tensor cores) -> Xb (with T-bar) or Pm's slot (only X Z^T is needed) ; Ps = sym(Pb) in place
+    // (row-wise work that does not depend on a tile product sits between its last mma and its store: a DMMA issues
+    //  once per ~16 cycles, the scheduler fills the gaps with the independent loads / DFMAs)
     cb += abi;
     {
-      double c4[4][4][2];
+      double c4[4][4][2], Ps[M];
       mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
-      mm32_store<LD>(sm + (NEED_T ? L::Xb : L::Pm), c4, 2.0, lane);  // Pm's fragment loads are behind the mma's
-    }
-    {
-      double Ps[M];
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         Ps[j] = 0.5 * (sm[L::Pb + i * LD + j] + sm[L::Pb + j * LD + i]);
         Cb[j] += Ps[j];
       }
+      mm32_store<LD>(sm + (NEED_T ? L::Xb : L::Pm), c4, 2.0, lane);  // Pm's fragment loads are behind the mma's
       __syncwarp();  // every lane has read its row and column of Pb; X is visible
       if (act) rowD_store<M>(sm + L::Pb + i * LD, Ps);
     }
@@ -509,39 +508,31 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     __syncwarp();  // Ps, lz visible; nobody reads X in Pm's slot any more
     // ---- 2: W = Ps L (tensor cores) -> Pm's slot ; (T-bar) Lb = Ps X -> Xb's slot ; PK, Kb, T^T ab
+    double lbz[P], PK[P], Kb[P], abn;
     {
-      double c4[4][4][2];
+      double c4[4][4][2], Psv[M];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
+      // independent of the product (pure register results; lz / Kp are stale but unused when nothing is observed)
+      rowD_load<M>(Psv, sm + L::Pb + i * LD);  // the lane's Ps row, once, for both consumers
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        lbz[e] = NEED_T ? 0.0 : dot4<M>(0.0, [&](int k, double& x, double& y) {
+          x = Psv[k];
+          y = sm[L::lz + k * P + e];
+        });
+        PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
+          x = Psv[k];
+          y = sm[L::Kp + k * P + e];
+        });
+      }
+      abn = dot4<M>(0.0, [&](int k, double& x, double& y) {
+        x = sm[L::T + k * LD + i];
+        y = sm[L::ab + k];
+      });
       mm32_store<LD>(sm + L::W, c4, 1.0, lane);
       if (NEED_T) {
         mm32<false, false, LD>(c4, sm + L::Pb, sm + L::Xb, lane);
         mm32_store<LD>(sm + L::Xb, c4, 1.0, lane);
-      }
-    }
-    const double* Psr = sm + L::Pb + i * LD;  // the lane's Ps row (Pb is not written again before phase 3's store)
-    double lbz[P];
-#pragma unroll
-    for (int e = 0; e < P; ++e) lbz[e] = 0.0;
-    if (!NEED_T && observed) {
-#pragma unroll
-      for (int e = 0; e < P; ++e)
-        lbz[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
-          x = Psr[k];
-          y = sm[L::lz + k * P + e];
-        });
-    }
-    double abn = dot4<M>(0.0, [&](int k, double& x, double& y) {
-      x = sm[L::T + k * LD + i];
-      y = sm[L::ab + k];
-    });
-    double PK[P], Kb[P];
-    if (observed) {
-#pragma unroll
-      for (int e = 0; e < P; ++e) {
-        PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
-          x = Psr[k];
-          y = sm[L::Kp + k * P + e];
-        });
       }
     }
     __syncwarp();  // W (and Lb) visible
@@ -580,11 +571,8 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     // ---- 3: Pb' = L^T W (tensor cores) -> Pb (Ps rows were last read above, by their owners, before this point in
     //         program order of every lane; the store follows the last mma, which all lanes execute together)
     __syncwarp();  // Kb visible; all row reads of Ps done
-    {
-      double c4[4][4][2];
-      mm32<true, false, LD>(c4, Lsrc, sm + L::W, lane);
-      mm32_store<LD>(sm + L::Pb, c4, 1.0, lane);
-    }
+    double c4p[4][4][2];
+    mm32<true, false, LD>(c4p, Lsrc, sm + L::W, lane);  // stored after the row-wise block below (independent of it)
     double vb[P], Fb[P * P], TMb[P];
     if (observed) {
       if (MK == MK_STEADY) {
@@ -659,6 +647,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         for (int e = 0; e < P; ++e) sm[L::TMb + i * P + e] = TMb[e];
       }
     }
+    mm32_store<LD>(sm + L::Pb, c4p, 1.0, lane);
     __syncwarp();  // Pb' and TMb visible; ab's readers are done
     // ---- 4: (observed) Mb = T^T TMb + Z^T Fb ; Pb' row += Mb Z ; ab' = T^T ab - Z^T vb
     if (observed) {
