@@ -314,6 +314,16 @@ def test_fused_row_kernels_hot_path(dims, wrt):
             got = g[k][b].cpu().numpy().reshape(gref[k].shape)
             scale = max(np.abs(gref[k]).max(), 1e-12)
             assert np.abs(got - w[b] * gref[k]).max() / (abs(w[b]) * scale) < RTOL, (k, b)
+    # cotangent on the per-step log-likelihoods instead (g_loglik = 0): the same kernels with lb = g_ll_obs[u, t]
+    wt = rng.normal(size=(B, n))
+    g2 = bk.backward(g_loglik=_dev(np.zeros(B)), g_ll_obs=_dev(wt), wrt=wrt)
+    for b in (0, 12):
+        args = (y,) + tuple(systems[b][1:])
+        _, gref = kt.loglik_and_grads("standard", *args, c=cs[b][:, None], d=ds[b][:, None], g_ll_obs=wt[b])
+        for k in wrt:
+            got = g2[k][b].cpu().numpy().reshape(gref[k].shape)
+            scale = max(np.abs(gref[k]).max(), 1e-12)
+            assert np.abs(got - gref[k]).max() / scale < RTOL, ("g_ll_obs", k, b)
 
 
 @pytest.mark.parametrize("wrt", [("a0", "T", "R", "H", "Q", "c", "d"), ("R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
