@@ -20,13 +20,31 @@
 
 namespace kfb {
 
+// Tile layout.  Default (KFB_ROWSD_SWZ = 0): leading dimension 34 - rows 16-byte aligned and LD/2 odd, so the
+// row-per-lane 16-byte accesses are conflict free; fragment loads and tile stores are 2-way conflicted.
+// KFB_ROWSD_SWZ = 1 (kept for A/B runs): LD = 32 and the 16-byte chunks of a row XOR-swizzled,
+//     physical chunk = chunk ^ swz(row),   swz(row) = {0,4,2,6,1,5,3,7}[row & 7],
+// which makes ALL four access patterns bank-conflict free at once (row accesses: 8 consecutive rows -> 8 distinct chunk
+// groups; both mma fragment patterns: 16 distinct 8-byte slots per half warp; 16-byte tile stores) - no padding can
+// (rows need LD/2 odd, tile stores LD/2 = 4 mod 8, fragments LD = 4 mod 16).  Measured SLOWER (347 vs 318 ms per
+// evaluation of config 4): the per-lane swizzled offsets of every row access become ~15 + 40 loop-invariant registers
+// in a kernel already at the 255-register limit (spills 76 -> 316 bytes per thread).
+#ifndef KFB_ROWSD_SWZ
+#define KFB_ROWSD_SWZ 0
+#endif
+constexpr int rowsD_LD = KFB_ROWSD_SWZ ? 32 : 34;
+__host__ __device__ constexpr int rowsD_swz(int row) {
+  return KFB_ROWSD_SWZ ? (((row & 1) << 2) | (row & 2) | ((row >> 2) & 1)) : 0;
+}
+// offset of element (row, col) inside a tile matrix
+__host__ __device__ constexpr int rowsD_el(int row, int col) {
+  return row * rowsD_LD + ((((col >> 1) ^ rowsD_swz(row)) << 1) | (col & 1));
+}
+
 template <int M, int P, bool NEED_T>
 struct RowsDLayout {
   static_assert(M % 2 == 0 && M > 16 && M <= 32 && P <= 3, "even k_states in 18..32");
-#ifndef KFB_ROWSD_LD
-#define KFB_ROWSD_LD 34
-#endif
-  static constexpr int LD = KFB_ROWSD_LD, MS = 32 * LD;  // one padded matrix
+  static constexpr int LD = rowsD_LD, MS = 32 * LD;  // one padded matrix
   static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), ME = M + (M & 1);
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
   static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MPE,
@@ -50,8 +68,14 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <bool TA, bool TB, int LD>
 __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, const double* B, int lane) {
   const int r = lane >> 2, c = lane & 3;
-  const double* pa = TA ? A + c * LD + r : A + r * LD + c;  // A^T: a[row][k] = A[k][row]
-  const double* pb = TB ? B + r * LD + c : B + c * LD + r;  // B^T: b[k][col] = B[col][k]
+  // "N" pattern: element (row 8X + r, col 4kk + c) ; "T" pattern: element (row 4kk + c, col 8X + r)
+  //   A: N, A^T: T (a[row][k] = A[k][row]) ; B: T pattern on B (b[k][col] = B[k][col]), B^T: N pattern on B
+  const int sr = rowsD_swz(r);                                          // swizzle of rows 8X + r
+  const int gc = KFB_ROWSD_SWZ ? (((c & 1) << 2) | (c & 2)) : 0;        // swizzle of rows 4kk + c = gc | (kk & 1)
+  const double* nA = A + r * LD + (c & 1);
+  const double* nB = B + r * LD + (c & 1);
+  const double* tA = A + c * LD + (r & 1);
+  const double* tB = B + c * LD + (r & 1);
 #pragma unroll
   for (int I = 0; I < 4; ++I)
 #pragma unroll
@@ -59,10 +83,14 @@ __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, co
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     double af[4], bf[4];
+    const int nofs = ((2 * kk + (c >> 1)) ^ sr) << 1;  // N pattern: chunk 2kk + c/2 of the lane's row
+    const int st = gc | (KFB_ROWSD_SWZ ? (kk & 1) : 0);
 #pragma unroll
-    for (int I = 0; I < 4; ++I) af[I] = TA ? pa[(4 * kk) * LD + 8 * I] : pa[(8 * I) * LD + 4 * kk];
+    for (int I = 0; I < 4; ++I)
+      af[I] = TA ? tA[(4 * kk) * LD + (((4 * I + (r >> 1)) ^ st) << 1)] : nA[(8 * I) * LD + nofs];
 #pragma unroll
-    for (int J = 0; J < 4; ++J) bf[J] = TB ? pb[(8 * J) * LD + 4 * kk] : pb[(4 * kk) * LD + 8 * J];
+    for (int J = 0; J < 4; ++J)
+      bf[J] = TB ? nB[(8 * J) * LD + nofs] : tB[(4 * kk) * LD + (((4 * J + (r >> 1)) ^ st) << 1)];
 #pragma unroll
     for (int I = 0; I < 4; ++I)
 #pragma unroll
@@ -81,24 +109,34 @@ __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][
   for (int I = 0; I < 4; ++I)
 #pragma unroll
     for (int J = 0; J < 4; ++J)
-      *reinterpret_cast<double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c) = make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
+      *reinterpret_cast<double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1)) =
+          make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
 }
 
-template <int M>
-__device__ __forceinline__ void rowD_store(double* dst, const double (&v)[M]) {
-  double2* d = reinterpret_cast<double2*>(dst);
-#pragma unroll
-  for (int j = 0; j < M / 2; ++j) d[j] = make_double2(v[2 * j], v[2 * j + 1]);
+// row i of a tile matrix: rowp = &mat[i * LD], si = rowsD_swz(i); chunk j of the row lives at rowp + ((j ^ si) << 1)
+__device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int si, int j) {
+  return reinterpret_cast<const double2*>(rowp + ((j ^ si) << 1));
+}
+__device__ __forceinline__ double2* rowD_chunk(double* rowp, int si, int j) {
+  return reinterpret_cast<double2*>(rowp + ((j ^ si) << 1));
 }
 template <int M>
-__device__ __forceinline__ void rowD_load(double (&v)[M], const double* src) {
-  const double2* s = reinterpret_cast<const double2*>(src);
+__device__ __forceinline__ void rowD_store(double* rowp, int si, const double (&v)[M]) {
+#pragma unroll
+  for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, si, j) = make_double2(v[2 * j], v[2 * j + 1]);
+}
+template <int M>
+__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, int si) {
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
-    const double2 x = s[j];
+    const double2 x = *rowD_chunk(rowp, si, j);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
+}
+// element (row j, column i) of a tile matrix, j a compile-time constant after unrolling: the lane's COLUMN accesses
+__device__ __forceinline__ double colD(const double* mat, int j, int i) {
+  return mat[j * rowsD_LD + ((((i >> 1) ^ rowsD_swz(j)) << 1) | (i & 1))];
 }
 
 // init + sum_{k<N} x_k y_k with four interleaved partial sums.  With one warp per SM sub-partition nothing hides the
@@ -129,6 +167,7 @@ template <int M, int P, int MK, class L>
 __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P],
                                            const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g) {
   constexpr int LD = L::LD;
+  const int si = rowsD_swz(i);
   // ---- A: Mm row (own P row x Z rows), v (every lane)
   {
     double Mr[P][4], vr[P][4];  // four partial sums each (see dot4)
@@ -138,11 +177,11 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
       for (int q = 0; q < 4; ++q) Mr[j][q] = vr[j][q] = 0.0;
       vr[j][0] = yt[j] - d_sign * dv[j];
     }
-    const double2* pr = reinterpret_cast<const double2*>(sm + L::Pm + i * LD);
+    const double* pr = sm + L::Pm + i * LD;
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 pk = pr[k], ak = av[k];
+      const double2 pk = *rowD_chunk(pr, si, k), ak = av[k];
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -171,10 +210,10 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     }
 #pragma unroll
     for (int j = 0; j < P; ++j) Tq[j][0] = Tq[j][1] = Tq[j][2] = Tq[j][3] = 0.0;
-    const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
+    const double* tr = sm + L::T + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = tr[k];
+      const double2 tk = *rowD_chunk(tr, si, k);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -214,18 +253,18 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     g.TM[j] = TM[j];
   }
   {
-    const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
-    double2* lr = reinterpret_cast<double2*>(sm + L::Lm + i * LD);
+    const double* tr = sm + L::T + i * LD;
+    double* lr = sm + L::Lm + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      double2 lk = tr[k];
+      double2 lk = *rowD_chunk(tr, si, k);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
         lk.x = fma(-g.Kp[e], z.x, lk.x);
         lk.y = fma(-g.Kp[e], z.y, lk.y);
       }
-      if (act) lr[k] = lk;
+      if (act) *rowD_chunk(lr, si, k) = lk;
     }
   }
   if (act) {
@@ -244,6 +283,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   const long long draw = u / A.n_series;
   const bool act = lane < M;
   const int i = act ? lane : 0;
+  const int si = rowsD_swz(i);
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
@@ -256,8 +296,8 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
-    sm[L::Pm + rr * LD + cc] = P0p[k];
+    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
+    sm[L::Pm + rowsD_el(rr, cc)] = P0p[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -295,11 +335,11 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     double an;
     {
       double aq[4] = {ci, 0.0, 0.0, 0.0};
-      const double2* tr = reinterpret_cast<const double2*>(sm + L::T + i * LD);
+      const double* tr = sm + L::T + i * LD;
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = tr[k], ak = av[k];
+        const double2 tk = *rowD_chunk(tr, si, k), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -343,9 +383,9 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     const bool taped = tp && t + 1 < n;
     {
       double S[M];
-      rowD_load<M>(S, sm + L::X + i * LD);
+      rowD_load<M>(S, sm + L::X + i * LD, si);
 #pragma unroll
-      for (int j = 0; j < M; ++j) S[j] = fma(0.5, S[j] + sm[L::X + j * LD + i], Cs[j]);
+      for (int j = 0; j < M; ++j) S[j] = fma(0.5, S[j] + colD(sm + L::X, j, i), Cs[j]);
       if (observed) {
 #pragma unroll
         for (int j = 0; j < M; ++j) {
@@ -355,7 +395,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
         }
       }
       if (act) {
-        rowD_store<M>(sm + L::Pm + i * LD, S);
+        rowD_store<M>(sm + L::Pm + i * LD, si, S);
         sm[L::a + i] = an;
         if (taped) {
           tp[i] = an;
@@ -386,6 +426,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   const long long draw = u / A.n_series;
   const bool act = lane < M;
   const int i = act ? lane : 0;
+  const int si = rowsD_swz(i);
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
@@ -395,7 +436,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   if (n >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(n - 2) * KT, lane);
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -432,7 +473,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
       for (int k = lane; k < M * M; k += 32) {
         const int rr = k / M, cc = k - rr * M;
-        sm[L::Pm + rr * LD + cc] = P0p[k];
+        sm[L::Pm + rowsD_el(rr, cc)] = P0p[k];
       }
       if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
     } else {
@@ -447,7 +488,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           const int lo = i < j ? i : j, hi = i < j ? j : i;
           Pr[j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
         }
-        rowD_store<M>(sm + L::Pm + i * LD, Pr);
+        rowD_store<M>(sm + L::Pm + i * LD, si, Pr);
       }
       __syncwarp();  // every lane has read the staging buffer: refill it for step t-1
       if (t >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(t - 2) * KT, lane);
@@ -472,10 +513,11 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
     if (t == 0) {  // P0 may be any matrix: X needs P + P^T (for t >= 1 the taped P is symmetric: P + P^T = 2 P)
       double S0[M];
+      rowD_load<M>(S0, sm + L::Pm + i * LD, si);
 #pragma unroll
-      for (int j = 0; j < M; ++j) S0[j] = 0.5 * (sm[L::Pm + i * LD + j] + sm[L::Pm + j * LD + i]);
+      for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD(sm + L::Pm, j, i));
       __syncwarp();
-      if (act) rowD_store<M>(sm + L::Pm + i * LD, S0);
+      if (act) rowD_store<M>(sm + L::Pm + i * LD, si, S0);
       __syncwarp();
     }
     // ---- 1: X = 2 L P (tensor cores) -> Xb (with T-bar) or Pm's slot (only X Z^T is needed) ; Ps = sym(Pb) in place
@@ -485,18 +527,19 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     {
       double c4[4][4][2], Ps[M];
       mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
+      rowD_load<M>(Ps, sm + L::Pb + i * LD, si);
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        Ps[j] = 0.5 * (sm[L::Pb + i * LD + j] + sm[L::Pb + j * LD + i]);
+        Ps[j] = 0.5 * (Ps[j] + colD(sm + L::Pb, j, i));
         Cb[j] += Ps[j];
       }
       mm32_store<LD>(sm + (NEED_T ? L::Xb : L::Pm), c4, 2.0, lane);  // Pm's fragment loads are behind the mma's
       __syncwarp();  // every lane has read its row and column of Pb; X is visible
-      if (act) rowD_store<M>(sm + L::Pb + i * LD, Ps);
+      if (act) rowD_store<M>(sm + L::Pb + i * LD, si, Ps);
     }
     if (!NEED_T && observed) {  // lz = X Z^T rows
       double Xr[M];
-      rowD_load<M>(Xr, sm + L::Pm + i * LD);
+      rowD_load<M>(Xr, sm + L::Pm + i * LD, si);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double s = dot4<M>(0.0, [&](int j, double& x, double& y) {
@@ -513,7 +556,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       double c4[4][4][2], Psv[M];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
       // independent of the product (pure register results; lz / Kp are stale but unused when nothing is observed)
-      rowD_load<M>(Psv, sm + L::Pb + i * LD);  // the lane's Ps row, once, for both consumers
+      rowD_load<M>(Psv, sm + L::Pb + i * LD, si);  // the lane's Ps row, once, for both consumers
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         lbz[e] = NEED_T ? 0.0 : dot4<M>(0.0, [&](int k, double& x, double& y) {
@@ -526,7 +569,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         });
       }
       abn = dot4<M>(0.0, [&](int k, double& x, double& y) {
-        x = sm[L::T + k * LD + i];
+        x = colD(sm + L::T, k, i);
         y = sm[L::ab + k];
       });
       mm32_store<LD>(sm + L::W, c4, 1.0, lane);
@@ -538,7 +581,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     __syncwarp();  // W (and Lb) visible
     if (NEED_T) {
       double Lb[M];
-      rowD_load<M>(Lb, sm + L::Xb + i * LD);
+      rowD_load<M>(Lb, sm + L::Xb + i * LD, si);
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         Tb[NEED_T ? j : 0] += fma(abi, sm[L::a + j], Lb[j]);  // Tb += ab a^T + Lb
@@ -655,7 +698,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         double s = dot4<M>(0.0, [&](int k, double& x, double& y) {
-          x = sm[L::T + k * LD + i];
+          x = colD(sm + L::T, k, i);
           y = sm[L::TMb + k * P + e];
         });
 #pragma unroll
@@ -663,13 +706,13 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         Mb[e] = s;
       }
       double Pbn[M];
-      rowD_load<M>(Pbn, sm + L::Pb + i * LD);
+      rowD_load<M>(Pbn, sm + L::Pb + i * LD, si);
 #pragma unroll
       for (int j = 0; j < M; ++j) {
 #pragma unroll
         for (int k = 0; k < P; ++k) Pbn[j] = fma(Mb[k], sm[L::Z + k * M + j], Pbn[j]);
       }
-      if (act) rowD_store<M>(sm + L::Pb + i * LD, Pbn);
+      if (act) rowD_store<M>(sm + L::Pb + i * LD, si, Pbn);
 #pragma unroll
       for (int k = 0; k < P; ++k) abn = fma(-sm[L::Z + k * M + i], vb[k], abn);
 #pragma unroll
@@ -699,10 +742,10 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (MK == MK_STEADY) {
-        if (A.gPss) A.gPss[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+        if (A.gPss) A.gPss[u * M * M + i * M + j] = sm[L::Pb + i * LD + ((((j >> 1) ^ si) << 1) | (j & 1))];
         if (A.gP0) A.gP0[u * M * M + i * M + j] = 0.0;
       } else if (A.gP0) {
-        A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + j];
+        A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + ((((j >> 1) ^ si) << 1) | (j & 1))];
       }
       if (NEED_T && A.gT) A.gT[u * M * M + i * M + j] = Tb[NEED_T ? j : 0];
       if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
