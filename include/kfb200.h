@@ -157,6 +157,22 @@ kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32
                                 const double *gdst, const int32_t *src_idx, const int32_t *dst_idx,
                                 double *gtheta, void *stream);
 
+/* The same for SEVERAL matrices in one launch each way (an evaluation scatters theta into 3-5 matrices: one launch
+ * instead of one per matrix; the backward WRITES gtheta - no zeroing by the caller - summing over all segments). */
+#define KFB_MAX_SCATTER_SEGMENTS 8
+typedef struct kfb_scatter_seg {
+  int32_t block;           /* doubles per draw of this matrix */
+  int32_t n_map;           /* entries of src_idx / dst_idx */
+  const double *base;      /* [block] constant part (forward only) */
+  const int32_t *src_idx;  /* [n_map] theta index */
+  const int32_t *dst_idx;  /* [n_map] element index */
+  double *data;            /* forward: dst [B, block] (written); backward: gdst [B, block] (read) */
+} kfb_scatter_seg;
+kfb_status kfb_scatter_forward_multi(int64_t B, int32_t n_theta, int32_t n_seg, const kfb_scatter_seg *segs,
+                                     const double *theta, void *stream);
+kfb_status kfb_scatter_backward_multi(int64_t B, int32_t n_theta, int32_t n_seg, const kfb_scatter_seg *segs,
+                                      double *gtheta, void *stream);
+
 /* Batched simulation helpers (next row f4, not on the logp/grad path): reference pymc_statespace/utils/simulation.py.
  * The standard-normal draws are INPUTS (z_*), so the kernels are deterministic.
  * kfb_simulate = simulate_statespace (:29-62) for n_draws * sims_per_draw trajectories: z_state[S,n,r], z_obs[S,n,p]

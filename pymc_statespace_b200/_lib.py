@@ -52,6 +52,13 @@ class KfbGrads(ctypes.Structure):
     _fields_ = [(k, _vp) for k in ("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d")]
 
 
+KFB_MAX_SCATTER_SEGMENTS = 8
+
+
+class KfbScatterSeg(ctypes.Structure):
+    _fields_ = [("block", _c_i32), ("n_map", _c_i32), ("base", _vp), ("src_idx", _vp), ("dst_idx", _vp), ("data", _vp)]
+
+
 EXPORTS = {
     "kfb_version": (_c_i32, []),
     "kfb_status_string": (ctypes.c_char_p, [_c_i32]),
@@ -69,6 +76,8 @@ EXPORTS = {
                                        _vp, _vp, _vp]),
     "kfb_scatter_forward": (_c_i32, [_c_i64, _c_i32, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kfb_scatter_backward": (_c_i32, [_c_i64, _c_i32, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp]),
+    "kfb_scatter_forward_multi": (_c_i32, [_c_i64, _c_i32, _c_i32, ctypes.POINTER(KfbScatterSeg), _vp, _vp]),
+    "kfb_scatter_backward_multi": (_c_i32, [_c_i64, _c_i32, _c_i32, ctypes.POINTER(KfbScatterSeg), _vp, _vp]),
     "kfb_simulate": (_c_i32, [_c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64, _vp, _c_i64,
                               _vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kfb_mvn_draws": (_c_i32, [_c_i64, _c_i64, _c_i32, _c_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -330,6 +330,30 @@ kfb_status kfb_scatter_backward(int64_t B, int32_t n_theta, int32_t block, int32
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);
 }
 
+static bool scatter_segs_ok(int32_t n_seg, const kfb_scatter_seg* segs, bool forward) {
+  if (n_seg <= 0 || n_seg > KFB_MAX_SCATTER_SEGMENTS || !segs) return false;
+  for (int q = 0; q < n_seg; ++q) {
+    const kfb_scatter_seg& g = segs[q];
+    if (g.block <= 0 || g.n_map < 0 || !g.data || (forward && !g.base)) return false;
+    if (g.n_map > 0 && (!g.src_idx || !g.dst_idx)) return false;
+  }
+  return true;
+}
+
+kfb_status kfb_scatter_forward_multi(int64_t B, int32_t n_theta, int32_t n_seg, const kfb_scatter_seg* segs,
+                                     const double* theta, void* stream) {
+  if (B <= 0 || n_theta <= 0 || !theta || !scatter_segs_ok(n_seg, segs, true)) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_scatter_forward_multi(B, n_theta, n_seg, segs, theta, (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
+kfb_status kfb_scatter_backward_multi(int64_t B, int32_t n_theta, int32_t n_seg, const kfb_scatter_seg* segs,
+                                      double* gtheta, void* stream) {
+  if (B <= 0 || n_theta <= 0 || !gtheta || !scatter_segs_ok(n_seg, segs, false)) return KFB_ERR_INVALID_ARG;
+  cudaError_t e = launch_scatter_backward_multi(B, n_theta, n_seg, segs, gtheta, (cudaStream_t)stream);
+  return e == cudaSuccess ? KFB_OK : cuda_fail(e);
+}
+
 kfb_status kfb_simulate(int64_t n_draws, int64_t sims_per_draw, int32_t n, int32_t m, int32_t p, int32_t r, const double* T,
                         int64_t T_bs, const double* Z, int64_t Z_bs, const double* R, int64_t R_bs, const double* H,
                         int64_t H_bs, const double* Q, int64_t Q_bs, const double* x0, int64_t x0_bs,

@@ -522,6 +522,100 @@ cudaError_t launch_scatter_backward(long long B, int n_theta, int block, int n_m
   return cudaGetLastError();
 }
 
+// ---- several matrices per launch (kfb_scatter_*_multi)
+struct ScatterSegs {
+  int n;
+  kfb_scatter_seg s[KFB_MAX_SCATTER_SEGMENTS];
+};
+
+// grid.y = segment; each slice is scatter_forward_kernel for its matrix
+__global__ void scatter_forward_multi_kernel(long long B, int n_theta, const double* __restrict__ theta,
+                                             const __grid_constant__ ScatterSegs S) {
+  extern __shared__ int inv[];
+  const kfb_scatter_seg& g = S.s[blockIdx.y];
+  const int block = g.block;
+  for (int e = threadIdx.x; e < block; e += blockDim.x) inv[e] = -1;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < g.n_map; ++k) inv[g.dst_idx[k]] = g.src_idx[k];
+  __syncthreads();
+  const long long total = B * block;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % block);
+    const long long b = idx / block;
+    const int j = inv[e];
+    g.data[idx] = (j >= 0) ? theta[b * n_theta + j] : g.base[e];
+  }
+}
+
+// one thread per (draw, theta entry): sums the owning map entries of every segment and WRITES gtheta
+__global__ void scatter_backward_multi_kernel(long long B, int n_theta, double* __restrict__ gtheta,
+                                              const __grid_constant__ ScatterSegs S) {
+  extern __shared__ int inv[];  // per segment: inv[e] = map entry that owns element e (the last writer), or -1
+  int off = 0;
+  for (int q = 0; q < S.n; ++q) {
+    for (int e = threadIdx.x; e < S.s[q].block; e += blockDim.x) inv[off + e] = -1;
+    off += S.s[q].block;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    off = 0;
+    for (int q = 0; q < S.n; ++q) {
+      for (int k = 0; k < S.s[q].n_map; ++k) inv[off + S.s[q].dst_idx[k]] = k;
+      off += S.s[q].block;
+    }
+  }
+  __syncthreads();
+  const long long total = B * n_theta;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % n_theta);
+    const long long b = idx / n_theta;
+    double s = 0.0;
+    off = 0;
+    for (int q = 0; q < S.n; ++q) {
+      const kfb_scatter_seg& g = S.s[q];
+      for (int k = 0; k < g.n_map; ++k)
+        if (g.src_idx[k] == j && inv[off + g.dst_idx[k]] == k) s += g.data[b * g.block + g.dst_idx[k]];
+      off += g.block;
+    }
+    gtheta[idx] = s;
+  }
+}
+
+cudaError_t launch_scatter_forward_multi(long long B, int n_theta, int n_seg, const kfb_scatter_seg* segs,
+                                         const double* theta, cudaStream_t s) {
+  ScatterSegs S;
+  S.n = n_seg;
+  int maxblock = 1;
+  for (int q = 0; q < n_seg; ++q) {
+    S.s[q] = segs[q];
+    maxblock = max(maxblock, segs[q].block);
+  }
+  const long long total = B * maxblock;
+  const unsigned gx = (unsigned)min((total + 255) / 256, (long long)148 * 16);
+  scatter_forward_multi_kernel<<<dim3(gx, n_seg), 256, maxblock * sizeof(int), s>>>(B, n_theta, theta, S);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_backward_multi(long long B, int n_theta, int n_seg, const kfb_scatter_seg* segs,
+                                          double* gtheta, cudaStream_t s) {
+  ScatterSegs S;
+  S.n = n_seg;
+  int sum = 0;
+  for (int q = 0; q < n_seg; ++q) {
+    S.s[q] = segs[q];
+    sum += segs[q].block;
+  }
+  const long long total = B * n_theta;
+  const unsigned grid = (unsigned)min((total + 255) / 256, (long long)148 * 32);
+  scatter_backward_multi_kernel<<<grid, 256, sum * sizeof(int), s>>>(B, n_theta, gtheta, S);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ FP64 FMA peak probe
 __global__ void fp64_peak_kernel(int iters, double* __restrict__ sink) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../../include/kfb200.h"
 #include "kf_core.cuh"
 
 namespace kfb {
@@ -18,6 +19,10 @@ cudaError_t launch_scatter_forward(long long B, int n_theta, int block, int n_ma
                                    cudaStream_t s);
 cudaError_t launch_scatter_backward(long long B, int n_theta, int block, int n_map, const double* gdst,
                                     const int* src_idx, const int* dst_idx, double* gtheta, cudaStream_t s);
+cudaError_t launch_scatter_forward_multi(long long B, int n_theta, int n_seg, const kfb_scatter_seg* segs,
+                                         const double* theta, cudaStream_t s);
+cudaError_t launch_scatter_backward_multi(long long B, int n_theta, int n_seg, const kfb_scatter_seg* segs,
+                                          double* gtheta, cudaStream_t s);
 cudaError_t launch_simulate(long long n_sims, long long sims_per_draw, int n, int m, int p, int r, MatArg T, MatArg Z,
                             MatArg R, MatArg H, MatArg Q, const double* x0, long long x0_bs, const double* z_state,
                             const double* z_obs, double* states, double* obs, int* info, cudaStream_t s);

@@ -20,7 +20,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from ._lib import check, load
+from ._lib import KFB_MAX_SCATTER_SEGMENTS, KfbScatterSeg, check, load
 from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapunov_forward
 from .models import MATRICES, StateSpaceSpec
 
@@ -152,15 +152,17 @@ class KalmanLogp:
         sp = self.spec
         mats = {}
         with torch.cuda.device(self.device):
+            mapped = [k for k in MATRICES if k in self._maps]
             for k in MATRICES:
-                if k in self._maps:
-                    src, dst, nmap = self._maps[k]
-                    check(self.lib.kfb_scatter_forward(self.B, sp.n_theta, self._size(k), nmap, _ptr(theta),
-                                                       _ptr(self._base[k]), _ptr(src), _ptr(dst), _ptr(self._buf[k]),
-                                                       _stream_ptr(self.device)), "kfb_scatter_forward")
-                    mats[k] = self._buf[k]
-                else:
-                    mats[k] = self._base[k]
+                mats[k] = self._buf[k] if k in self._maps else self._base[k]
+            # one launch for all theta-dependent matrices (chunks of KFB_MAX_SCATTER_SEGMENTS)
+            for i0 in range(0, len(mapped), KFB_MAX_SCATTER_SEGMENTS):
+                ks = mapped[i0:i0 + KFB_MAX_SCATTER_SEGMENTS]
+                segs = (KfbScatterSeg * len(ks))(*[
+                    KfbScatterSeg(self._size(k), self._maps[k][2], _ptr(self._base[k]), _ptr(self._maps[k][0]),
+                                  _ptr(self._maps[k][1]), _ptr(self._buf[k])) for k in ks])
+                check(self.lib.kfb_scatter_forward_multi(self.B, sp.n_theta, len(ks), segs, _ptr(theta),
+                                                         _stream_ptr(self.device)), "kfb_scatter_forward_multi")
         if sp.stationary_initialization:
             A = mats["T"] if mats["T"].ndim == 3 else mats["T"].expand(self.B, -1, -1).contiguous()
             X, info = lyapunov_forward(A, mats["R"], mats["Q"])
@@ -209,12 +211,21 @@ class KalmanLogp:
             # P0 = Lyapunov(T, R Q R^T): push P0-bar back into T-bar, R-bar, Q-bar (only those theta reaches)
             A, X, _ = self._lyap
             lyapunov_backward(A, mats["R"], mats["Q"], X, g["P0"], g.get("T"), g.get("R"), g.get("Q"))
-        gtheta = torch.zeros((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
+        ks = [k for k in self._maps if not (sp.stationary_initialization and k == "P0")]
         with torch.cuda.device(self.device):
-            for k, (src, dst, nmap) in self._maps.items():
-                if sp.stationary_initialization and k == "P0":
-                    continue
-                check(self.lib.kfb_scatter_backward(self.B, sp.n_theta, self._size(k), nmap, _ptr(g[k]), _ptr(src),
-                                                    _ptr(dst), _ptr(gtheta), _stream_ptr(self.device)),
-                      "kfb_scatter_backward")
+            if 0 < len(ks) <= KFB_MAX_SCATTER_SEGMENTS:
+                # one launch: gtheta[b, j] = sum over matrices of the cotangents of the elements theta_j was written to
+                gtheta = torch.empty((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
+                segs = (KfbScatterSeg * len(ks))(*[
+                    KfbScatterSeg(self._size(k), self._maps[k][2], None, _ptr(self._maps[k][0]), _ptr(self._maps[k][1]),
+                                  _ptr(g[k])) for k in ks])
+                check(self.lib.kfb_scatter_backward_multi(self.B, sp.n_theta, len(ks), segs, _ptr(gtheta),
+                                                          _stream_ptr(self.device)), "kfb_scatter_backward_multi")
+            else:
+                gtheta = torch.zeros((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
+                for k in ks:
+                    src, dst, nmap = self._maps[k]
+                    check(self.lib.kfb_scatter_backward(self.B, sp.n_theta, self._size(k), nmap, _ptr(g[k]), _ptr(src),
+                                                        _ptr(dst), _ptr(gtheta), _stream_ptr(self.device)),
+                          "kfb_scatter_backward")
         return out["loglik"], gtheta
