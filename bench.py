@@ -209,7 +209,9 @@ def main():
     # single GPU: the public host-to-host call, captured once as a CUDA graph (KalmanLogp.capture_host_step: H2D of theta
     # from pinned memory, every kernel of the evaluation, D2H of (logp, grad) into pinned memory) and replayed per step;
     # multi-GPU keeps the eager sequence (the all-gather is not captured)
-    host_step = model.capture_host_step(theta_h, out_h) if world == 1 and not a.no_graph else None
+    host_step = None
+    if world == 1 and not a.no_graph:
+        host_step = model.capture_host_step(theta_h, out_h, chunks=4 if B % 4 == 0 else 1)
 
     def step_e2e():
         if host_step is not None:
@@ -310,8 +312,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 * world),
                     "d2h_bytes_per_step": int(out_h.numel() * 8 + (world - 1) * B * (1 + spec.n_theta) * 8),
-                    "path": ("KalmanLogp.capture_host_step: pinned H2D + evaluation + pinned D2H replayed as one CUDA graph, "
-                             "stream-synchronised every step") if host_step is not None else
+                    "path": ("KalmanLogp.capture_host_step: pinned H2D + evaluation + pinned D2H replayed as one CUDA graph "
+                             "(4 parallel draw-chunk branches: copies overlap kernels), stream-synchronised every step") if host_step is not None else
                             "eager: pinned H2D, logp_and_grad, all-gather, pinned D2H, stream-synchronised every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -207,13 +207,16 @@ def test_host_step_graph_matches_eager(kind):
     model = KalmanLogp(spec, y, n_draws=B, filter_type="standard")
     th_h = torch.from_numpy(np.ascontiguousarray(theta)).pin_memory()
     out_h = torch.empty((B, 1 + spec.n_theta), dtype=torch.float64).pin_memory()
-    step = model.capture_host_step(th_h, out_h)
+    step = model.capture_host_step(th_h, out_h, chunks=1 if kind == "arma" else 4)  # 4 parallel draw-chunk branches
     for scale in (1.0, 0.9):
         th_h.copy_(torch.from_numpy(theta * scale if kind == "arma" else theta * np.where(np.arange(theta.shape[1]) < 6, scale, 1.0)))
         got = step().clone()
         lp, g = model.logp_and_grad(th_h.to("cuda"))
         torch.cuda.synchronize()
         assert torch.equal(got[:, 0], lp.cpu()) and torch.equal(got[:, 1:], g.cpu())
+        assert int(step.info.abs().max()) == 0 and step.info.numel() == B
+    with pytest.raises(ValueError):
+        model.capture_host_step(th_h, out_h, chunks=7)   # must divide the number of draws
     with pytest.raises(TypeError):
         model.capture_host_step(th_h.clone(), out_h)  # not pinned
 
