@@ -17,6 +17,9 @@ thread_launch_fn thread_launcher_m2(int p, int mk);
 thread_launch_fn thread_launcher_m3(int p, int mk);
 thread_launch_fn thread_launcher_m4(int p, int mk);
 
+bool p1_adjoint_supported(int m, int p, int mk);
+cudaError_t launch_p1_adjoint(const KfArgs& A, int y_smem_doubles, int bulk_ok, cudaStream_t s);
+
 coopT_launch_fn coopT_launcher_m5(int p, int mk);
 coopT_launch_fn coopT_launcher_m6(int p, int mk);
 coopT_launch_fn coopT_launcher_m7(int p, int mk);
@@ -96,7 +99,7 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
   }
   pl->off_tape = pl->off_gC = 0;
   if (save) {
-    pl->off_tape = take((size_t)pl->U * (d->n > 1 ? d->n - 1 : 0) * tape_width(d->m));
+    pl->off_tape = take((size_t)tape_units_padded(pl->U) * (d->n > 1 ? d->n - 1 : 0) * tape_width(d->m));
     pl->off_gC = take((size_t)pl->U * pl->nTC * d->m * d->m);
     if (pl->mk == MK_STEADY) {
       pl->off_gPss = take((size_t)pl->U * d->m * d->m);
@@ -142,7 +145,12 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
       ysm = (int)ydoubles;
       bulk_ok = ((uintptr_t)A.y.p % 16 == 0) ? 1 : 0;
     }
-    e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
+    // k_endog = 1, shared observations: the specialised adjoint with the TMA tape ring (kf_p1.cu)
+    if (bwd && d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
+        p1_adjoint_supported(d->m, d->p, pl.mk))
+      e = launch_p1_adjoint(A, ysm, bulk_ok, s);
+    else
+      e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
   } else {
     // sub-warp kernels with compile-time dims need uniform control flow across the units of a warp:
     // static matrices and ONE observation stream shared by every unit

@@ -50,6 +50,8 @@ struct KfArgs {
 };
 
 KFB_HD int tape_width(int m) { return m + (m * (m + 1)) / 2; }
+// the tape holds whole warps of units (thread-per-unit layout [t-1][warp][k][32])
+KFB_HD long long tape_units_padded(long long U) { return (U + 31) & ~31LL; }
 
 KFB_HD double kf_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)

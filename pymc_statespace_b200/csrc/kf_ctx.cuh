@@ -6,7 +6,7 @@ namespace kfb {
 
 // ---------------------------------------------------------------------------
 // ThreadCtx: one unit per thread; compile-time dims; all buffers are registers.
-// Tape layout [t-1][k][U]: consecutive threads (units) touch consecutive doubles -> every tape
+// Tape layout [t-1][warp][k][32]: consecutive threads (units) touch consecutive doubles -> every tape
 // load/store of a warp is one fully-coalesced 256-byte transaction.
 // ---------------------------------------------------------------------------
 template <int N>
@@ -93,10 +93,13 @@ struct ThreadCtx {
   KFB_HD const double* y_base(const KfArgs& A, long long series) const {
     return y_smem ? y_smem : A.y.p + series * A.y.bs;
   }
-  // tape entry of step t (t >= 1) = tape_base + (t-1) * tape_step; element k at [k * tape_elem]
-  KFB_HD double* tape_base(const KfArgs& A, long long u) const { return A.tape + u; }
-  KFB_HD long long tape_step(const KfArgs& A) const { return (long long)tape_width(M) * A.U; }
-  KFB_HD long long tape_elem(const KfArgs& A) const { return A.U; }
+  // tape entry of step t (t >= 1) = tape_base + (t-1) * tape_step; element k at [k * tape_elem].
+  // Layout [t-1][warp][k][32]: the entry of one step for the 32 units of a warp is KT * 256 contiguous bytes - every
+  // tape load/store of a warp is still one fully-coalesced 256-byte transaction, and the k_endog = 1 adjoint
+  // (kf_p1.cu) fetches the whole entry with ONE TMA bulk copy per warp and step.
+  KFB_HD double* tape_base(const KfArgs& A, long long u) const { return A.tape + (u >> 5) * (KT * 32) + (u & 31); }
+  KFB_HD long long tape_step(const KfArgs& A) const { return (long long)KT * tape_units_padded(A.U); }
+  KFB_HD long long tape_elem(const KfArgs&) const { return 32; }
 };
 
 // ---------------------------------------------------------------------------

@@ -14,7 +14,7 @@ from typing import Dict, Iterable, Optional
 import torch
 
 from . import _lib
-from ._lib import (FILTER_KIND, KFB_FLAG_CORRECTED, KFB_FLAG_FORCE_COOP, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
+from ._lib import (FILTER_KIND, KFB_FLAG_CORRECTED, KFB_FLAG_FORCE_COOP, KFB_FLAG_GENERIC_ADJOINT, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
                    KfbOutputs, check, load)
 
 MATRIX_NAMES = ("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d")
@@ -47,7 +47,7 @@ class BatchedKalman:
 
     def __init__(self, kind: str, n: int, m: int, p: int, r: int, n_draws: int, n_series: int = 1,
                  strict_reference: bool = True, time_varying: Iterable[str] = (), device="cuda",
-                 force_coop: bool = False):
+                 force_coop: bool = False, generic_adjoint: bool = False):
         kind = kind.lower()
         if kind not in FILTER_KIND:
             raise NotImplementedError("The following are valid filter types: " + ", ".join(FILTER_KIND))
@@ -60,7 +60,8 @@ class BatchedKalman:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("pymc_statespace_b200 runs on CUDA devices only (no CPU fallback)")
-        self.flags = (0 if strict_reference else KFB_FLAG_CORRECTED) | (KFB_FLAG_FORCE_COOP if force_coop else 0)
+        self.flags = ((0 if strict_reference else KFB_FLAG_CORRECTED) | (KFB_FLAG_FORCE_COOP if force_coop else 0)
+                      | (KFB_FLAG_GENERIC_ADJOINT if generic_adjoint else 0))  # the last two: testing / A-B timing only
         self._base = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (p, m), "R": (m, r), "H": (p, p), "Q": (r, r),
                       "c": (m,), "d": (p,)}
         self._desc = None

@@ -22,7 +22,7 @@ MK = {"standard": 0, "single": 0, "cholesky": 0, "univariate": 1, "steady_state"
 
 def build(force=False):
     src = os.path.join(HERE, "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "pymc_statespace_b200", "csrc", f) for f in ("kf_core.cuh", "kf_ctx.cuh", "kf_dare.cuh", "kf_pred.cuh", "kf_smooth.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pymc_statespace_b200", "csrc", f) for f in ("kf_core.cuh", "kf_ctx.cuh", "kf_dare.cuh", "kf_pred.cuh", "kf_smooth.cuh", "kf_p1.cuh")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(
             ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -36,7 +36,7 @@ def _p(a):
 
 
 def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_dims=False, do_bwd=True,
-        g_loglik=None, g_ll_obs=None, full=True, pred=False, skip=()):
+        g_loglik=None, g_ll_obs=None, full=True, pred=False, skip=(), p1=False):
     """Returns (outputs6, grads dict or None, info).  ``skip``: cotangents NOT requested (null pointers, left zero)."""
     lib = build()
     f8 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))  # noqa: E731
@@ -88,7 +88,7 @@ def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_d
     glo = None if g_ll_obs is None else f8(g_ll_obs)
     rc = lib.hostsim_run(
         mk, m, p, n, _p(data), _p(a0), _p(P0), _p(T), _p(Z), _p(H), _p(C), _p(c), _p(d), _p(Pss), _p(Gss), _p(ts),
-        ctypes.c_double(ll_const), ctypes.c_double(d_sign), int(static_dims) | (2 if pred else 0), _p(loglik), _p(ll_obs), _p(fs), _p(ps),
+        ctypes.c_double(ll_const), ctypes.c_double(d_sign), int(static_dims) | (2 if pred else 0) | (4 if p1 else 0), _p(loglik), _p(ll_obs), _p(fs), _p(ps),
         _p(fc), _p(pc), _p(info), int(do_bwd), _p(gl), _p(glo),
         *([None if k in skip else _p(g[k]) for k in ("a0", "P0", "T", "Z", "H", "C", "c", "d", "Pss", "Gss")]
           if do_bwd else [None] * 10),

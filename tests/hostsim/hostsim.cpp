@@ -8,11 +8,13 @@
 
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
+#include "kf_p1.cuh"
 #include "kf_pred.cuh"
 #include "kf_smooth.cuh"
 
 using namespace kfb;
 
+static int g_p1 = 0;    // 1: adjoint through kf_p1.cuh (k_endog = 1, standard family) after the predictor-form forward
 static int g_pred = 0;  // 1: run the one-step-predictor programs (kf_pred.cuh) where they exist
 
 template <int MK, class X>
@@ -25,6 +27,25 @@ static void run_both(X& x, KfArgs& A, int do_bwd) {
     if (g_pred && PRED) backward_unit_pred<MK == MK_STEADY ? MK_STEADY : MK_STD>(x, A, 0);
     else backward_unit<MK>(x, A, 0);
   }
+}
+
+template <int M>
+static void run_p1(ThreadCtx<M, 1>& x, KfArgs& A, int do_bwd) {
+  forward_unit_pred<MK_STD>(x, A, 0);
+  if (!do_bwd) return;
+  p1::DirectTape<M> tape{x.tape_base(A, 0) + (long long)(A.n - 2) * x.tape_step(A), x.tape_step(A), x.tape_elem(A)};
+  const bool z = A.gZ != nullptr, hh = A.gH != nullptr;
+#define KFB_P1RUN(ZZ, HH, GG) p1::backward_unit_p1<M, ZZ, HH, GG>(A, 0, true, A.y.p, tape)
+  if (A.g_ll_obs) {
+    if (z) KFB_P1RUN(true, true, true);
+    else if (hh) KFB_P1RUN(false, true, true);
+    else KFB_P1RUN(false, false, true);
+  } else {
+    if (z) KFB_P1RUN(true, true, false);
+    else if (hh) KFB_P1RUN(false, true, false);
+    else KFB_P1RUN(false, false, false);
+  }
+#undef KFB_P1RUN
 }
 
 template <class X>
@@ -51,14 +72,27 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   A.Pss = {Pss, 0, 0}; A.Gss = {Gss, 0, 0};
   A.ll_const = ll_const; A.d_sign = d_sign;
   A.loglik = loglik; A.ll_obs = ll_obs; A.fs = fs; A.ps = ps; A.fc = fc; A.pc = pc; A.info = info;
-  std::vector<double> tape((size_t)(n > 1 ? n - 1 : 1) * tape_width(m));
+  std::vector<double> tape((size_t)(n > 1 ? n - 1 : 1) * tape_width(m) * 32);  // ThreadCtx layout: whole warps of units
   A.tape = tape.data();
   A.g_loglik = g_loglik; A.g_ll_obs = g_ll_obs;
   A.ga0 = ga0; A.gP0 = gP0; A.gT = gT; A.gZ = gZ; A.gH = gH; A.gC = gC; A.gc = gc; A.gd = gd;
   A.gPss = gPss; A.gGss = gGss;
 
   g_pred = (static_dims >> 1) & 1;
+  g_p1 = (static_dims >> 2) & 1;
   static_dims &= 1;
+  if (g_p1) {
+    if (p != 1 || mk != MK_STD || ts[0] || ts[1] || ts[2] || ts[3] || ts[4] || ts[5]) return 7;
+#define KFB_P1CASE(MM)                \
+  if (m == MM) {                      \
+    ThreadCtx<MM, 1> x{nullptr, nullptr, 0, 1}; \
+    run_p1<MM>(x, A, do_bwd);         \
+    return 0;                         \
+  }
+    KFB_P1CASE(1) KFB_P1CASE(2) KFB_P1CASE(3) KFB_P1CASE(4)
+#undef KFB_P1CASE
+    return 2;
+  }
   if (static_dims) {
 #define KFB_CASE(MM, PP)                                   \
   if (m == MM && p == PP) {                                \

@@ -53,7 +53,7 @@ def test_argument_validation_without_device():
     d.filter_kind, d.n_draws, d.n_series, d.n, d.m, d.p, d.r = 0, 1000, 1, 100, 2, 1, 1
     d.T_bs = 4
     assert lib.kfb_workspace_bytes(ctypes.byref(d), 1, ctypes.byref(n)) == _lib.KFB_OK
-    tape = 1000 * 99 * 5 * 8
+    tape = 1024 * 99 * 5 * 8  # units padded to whole warps (tape layout [t-1][warp][k][32])
     assert n.value >= tape and n.value < tape + 1000 * 4 * 8 * 2 + 4096
     d.filter_kind, d.p = _lib.KFB_SINGLE, 2  # "single" with k_endog > 1 (reference kalman_filter.py:19,329)
     assert lib.kfb_workspace_bytes(ctypes.byref(d), 0, ctypes.byref(n)) == _lib.KFB_ERR_INVALID_ARG

@@ -456,3 +456,46 @@ def test_invalid_requests_raise():
     with pytest.raises(KfbError, match="invalid argument"):
         BatchedKalman("single", 10, 2, 2, 1, n_draws=1).forward(z(10, 2), z(2), z(2, 2), z(2, 2), z(2, 2), z(2, 1),
                                                                 z(2, 2), z(1, 1))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_p1_adjoint_kernel_vs_generic_and_oracle(m):
+    """kf_p1.cu (k_endog = 1: TMA tape ring + symmetric-storage adjoint) against the generic thread-per-unit adjoint
+    (KFB_FLAG_GENERIC_ADJOINT) on every unit, and against torch-autograd of the oracle on a few: 77 units (two full
+    warps + 13 lanes), missing rows, non-symmetric P0, every cotangent subset that selects a different instantiation."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    rng = np.random.default_rng(40 + m)
+    B, n, r = 77, 37, min(m, 2)
+    systems = [list(random_system(rng, m, 1, r, n)) for _ in range(B)]
+    for s in systems:
+        s[2] = s[2] + 0.05 * rng.normal(size=(m, m))  # P0 as BayesianARMA(stationary_initialization=False) writes it
+    y = random_system(rng, m, 1, r, n, n_missing=4)[0]
+    y[[0, n - 1]] = np.nan
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    c, d = _dev(rng.normal(size=(B, m))), _dev(rng.normal(size=(B, 1)))
+    w = rng.normal(size=(B, n))
+    for kind, strict in (("standard", True), ("single", True), ("cholesky", False)):
+        for wrt, gobs in ((("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d"), None), (("a0", "P0", "T", "R", "Q"), None),
+                          (("T", "H", "Q", "d"), w), (("a0", "Z"), w)):
+            res = {}
+            for gen in (False, True):
+                bk = BatchedKalman(kind, n, m, 1, r, n_draws=B, strict_reference=strict, generic_adjoint=gen)
+                out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), stack(3), stack(4), stack(5), stack(6),
+                                 stack(7), c, d, outputs=("loglik",), save_for_backward=True)
+                g = bk.backward(g_loglik=None if gobs is None else _dev(np.full(B, 0.5)),
+                                g_ll_obs=None if gobs is None else _dev(gobs), wrt=wrt)
+                assert int((out["info"] != 0).sum()) == 0
+                res[gen] = {k: v.cpu().numpy() for k, v in g.items()}
+            for k in wrt:
+                scale = np.abs(res[True][k]).max()
+                assert np.abs(res[False][k] - res[True][k]).max() / scale < 1e-10, (kind, wrt, k)
+            for b in (0, 31, 32, 76):
+                args = (y,) + tuple(systems[b][1:])
+                _, gref = kt.loglik_and_grads(kind, *args, c=c[b].cpu().numpy()[:, None], d=d[b].cpu().numpy()[:, None],
+                                              strict_reference=strict,  # 0.5 * loglik + sum_t w_t ll_t
+                                              g_ll_obs=None if gobs is None else 0.5 + gobs[b])
+                for k in wrt:
+                    got = res[False][k][b].reshape(gref[k].shape)
+                    scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+                    assert np.abs(got - gref[k]).max() / scale < RTOL, (kind, wrt, k, b)

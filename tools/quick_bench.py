@@ -19,23 +19,25 @@ def arma11(B, n, seed=1):
     for t in range(n): y[t] = 0.6 * (y[t - 1] if t else 0) + e[t + 1] + 0.3 * e[t]
     return y[:, None], a0, P0, T, Z, R, H, Q
 
+WRT = tuple(os.environ.get('KFB_WRT', 'a0,P0,T,R,Q').split(','))  # default: what the ARMA theta-level path asks for
+
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device="cuda")
     y, a0, P0, T, Z, R, H, Q = map(dev, arma11(B, n))
     print("fp64 peak TFLOP/s:", fp64_peak_tflops())
-    for force in (False, True):
-        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force)
-        for it in range(3):
+    for force, gen in ((False, False), (False, True)) + (((True, False),) if B <= 16384 else ()):
+        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen)
+        for it in range(5):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
             out = bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=True)
             e[1].record()
-            g = bk.backward()
+            g = bk.backward(wrt=WRT)
             e[2].record(); torch.cuda.synchronize()
             tf, tb = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
-        print(f"coop={force} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
-              f"ll[0]={float(out['loglik'][0]):.6f} info!=0: {int((out['info']!=0).sum())}")
+        print(f"coop={force} generic_adjoint={gen} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
+              f"ll[0]={float(out['loglik'][0]):.6f} gT[0]={g['T'][0].flatten().tolist()} info!=0: {int((out['info']!=0).sum())}")
         if force and B > 16384: break
 main()
