@@ -62,8 +62,8 @@ enum {
 #define KFB_FLAG_CORRECTED 1u  /* strict_reference=False: fix SURVEY.md A.2 quirks Q1,Q4,Q5,Q6 */
 #define KFB_FLAG_FORCE_COOP 2u /* testing: use the cooperative (shared-memory) kernels even   */
                                /* when a thread-per-unit instantiation exists                   */
-#define KFB_FLAG_GENERIC_ADJOINT 4u /* testing: run the generic thread-per-unit adjoint where the        */
-                                    /* specialised k_endog = 1 adjoint (TMA tape ring) would be used     */
+#define KFB_FLAG_GENERIC_ADJOINT 4u /* testing: run the generic thread-per-unit kernels where the        */
+                                    /* specialised k_endog = 1 forward / adjoint kernels would be used   */
 
 typedef struct kfb_desc {
   int32_t filter_kind;

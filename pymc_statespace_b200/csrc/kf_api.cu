@@ -19,6 +19,7 @@ thread_launch_fn thread_launcher_m4(int p, int mk);
 
 bool p1_adjoint_supported(int m, int p, int mk);
 cudaError_t launch_p1_adjoint(const KfArgs& A, int y_smem_doubles, int bulk_ok, cudaStream_t s);
+cudaError_t launch_p1_forward(const KfArgs& A, int y_smem_doubles, int bulk_ok, cudaStream_t s);
 
 coopT_launch_fn coopT_launcher_m5(int p, int mk);
 coopT_launch_fn coopT_launcher_m6(int p, int mk);
@@ -146,9 +147,13 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
       bulk_ok = ((uintptr_t)A.y.p % 16 == 0) ? 1 : 0;
     }
     // k_endog = 1, shared observations: the specialised adjoint with the TMA tape ring (kf_p1.cu)
-    if (bwd && d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
-        p1_adjoint_supported(d->m, d->p, pl.mk))
+    const bool p1_ok = d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
+                       p1_adjoint_supported(d->m, d->p, pl.mk);
+    const bool full = A.ll_obs || A.fs || A.ps || A.fc || A.pc;
+    if (p1_ok && bwd)
       e = launch_p1_adjoint(A, ysm, bulk_ok, s);
+    else if (p1_ok && !full)
+      e = launch_p1_forward(A, ysm, bulk_ok, s);
     else
       e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
   } else {

@@ -158,7 +158,56 @@ static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t 
   return launch_one<M, false, false, false>(A, ysm, bulk_ok, s);
 }
 
+// ---- forward (loglik + tape) -------------------------------------------------------------------------------
+template <int M, bool SAVE>
+__global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
+    kf_p1_forward_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
+  extern __shared__ __align__(128) double kf_dyn_smem[];
+  constexpr int KT = Dim<M>::KT;
+  const double* yp = A.y.p;
+  if (y_smem_doubles > 0) {
+    stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
+    yp = kf_dyn_smem;
+  }
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= A.U) return;
+  const long long tstep = (long long)KT * tape_units_padded(A.U);
+  double* tp = SAVE ? A.tape + (u >> 5) * (KT * 32) + (u & 31) : nullptr;
+  forward_unit_p1<M, SAVE>(A, u, true, yp, tp, tstep);
+}
+
+template <int M, bool SAVE>
+static cudaError_t launch_fwd_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
+  const int block = 64;
+  const unsigned grid = (unsigned)((A.U + block - 1) / block);
+  const size_t smem = (size_t)((ysm + 1) & ~1) * 8;
+  auto kern = kf_p1_forward_kernel<M, SAVE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, block, smem, s>>>(A, ysm, bulk_ok);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int M>
+static cudaError_t launch_fwd_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
+  return A.tape ? launch_fwd_one<M, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false>(A, ysm, bulk_ok, s);
+}
+
 }  // namespace p1
+
+// Forward pass, loglik (+ tape) only, same conditions as the adjoint below.
+cudaError_t launch_p1_forward(const KfArgs& A, int y_smem_doubles, int bulk_ok, cudaStream_t s) {
+  switch (A.m) {
+    case 1: return p1::launch_fwd_m<1>(A, y_smem_doubles, bulk_ok, s);
+    case 2: return p1::launch_fwd_m<2>(A, y_smem_doubles, bulk_ok, s);
+    case 3: return p1::launch_fwd_m<3>(A, y_smem_doubles, bulk_ok, s);
+    case 4: return p1::launch_fwd_m<4>(A, y_smem_doubles, bulk_ok, s);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
 
 bool p1_adjoint_supported(int m, int p, int mk) { return p == 1 && mk == MK_STD && m >= 1 && m <= 4; }
 

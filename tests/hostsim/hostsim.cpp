@@ -31,7 +31,8 @@ static void run_both(X& x, KfArgs& A, int do_bwd) {
 
 template <int M>
 static void run_p1(ThreadCtx<M, 1>& x, KfArgs& A, int do_bwd) {
-  forward_unit_pred<MK_STD>(x, A, 0);
+  if (g_p1 == 2) forward_unit_pred<MK_STD>(x, A, 0);  // generic forward + specialised adjoint
+  else p1::forward_unit_p1<M, true>(A, 0, true, A.y.p, x.tape_base(A, 0), x.tape_step(A));
   if (!do_bwd) return;
   p1::DirectTape<M> tape{x.tape_base(A, 0) + (long long)(A.n - 2) * x.tape_step(A), x.tape_step(A), x.tape_elem(A)};
   const bool z = A.gZ != nullptr, hh = A.gH != nullptr;
@@ -79,7 +80,7 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
   A.gPss = gPss; A.gGss = gGss;
 
   g_pred = (static_dims >> 1) & 1;
-  g_p1 = (static_dims >> 2) & 1;
+  g_p1 = (static_dims >> 2) & 3;  // 1: specialised forward + adjoint, 2: generic forward + specialised adjoint
   static_dims &= 1;
   if (g_p1) {
     if (p != 1 || mk != MK_STD || ts[0] || ts[1] || ts[2] || ts[3] || ts[4] || ts[5]) return 7;

@@ -460,8 +460,8 @@ def test_invalid_requests_raise():
 
 @pytest.mark.parametrize("m", [1, 2, 3, 4])
 def test_p1_adjoint_kernel_vs_generic_and_oracle(m):
-    """kf_p1.cu (k_endog = 1: TMA tape ring + symmetric-storage adjoint) against the generic thread-per-unit adjoint
-    (KFB_FLAG_GENERIC_ADJOINT) on every unit, and against torch-autograd of the oracle on a few: 77 units (two full
+    """kf_p1.cu (k_endog = 1: branch-free forward, TMA tape ring + symmetric-storage adjoint) against the generic
+    thread-per-unit kernels (KFB_FLAG_GENERIC_ADJOINT) on every unit, and against torch-autograd of the oracle on a few: 77 units (two full
     warps + 13 lanes), missing rows, non-symmetric P0, every cotangent subset that selects a different instantiation."""
     from pymc_statespace_b200 import BatchedKalman
 
@@ -487,11 +487,16 @@ def test_p1_adjoint_kernel_vs_generic_and_oracle(m):
                                 g_ll_obs=None if gobs is None else _dev(gobs), wrt=wrt)
                 assert int((out["info"] != 0).sum()) == 0
                 res[gen] = {k: v.cpu().numpy() for k, v in g.items()}
+                res[gen]["loglik"] = out["loglik"].cpu().numpy()
+            assert np.abs(res[False]["loglik"] / res[True]["loglik"] - 1).max() < 1e-12, kind  # forward kernels agree
             for k in wrt:
                 scale = np.abs(res[True][k]).max()
                 assert np.abs(res[False][k] - res[True][k]).max() / scale < 1e-10, (kind, wrt, k)
             for b in (0, 31, 32, 76):
                 args = (y,) + tuple(systems[b][1:])
+                ll_ref = kn.kalman_filter(kind, *args, c=c[b].cpu().numpy()[:, None], d=d[b].cpu().numpy()[:, None],
+                                          strict_reference=strict)[4]
+                assert abs(res[False]["loglik"][b] - ll_ref) < RTOL * abs(ll_ref), (kind, b)
                 _, gref = kt.loglik_and_grads(kind, *args, c=c[b].cpu().numpy()[:, None], d=d[b].cpu().numpy()[:, None],
                                               strict_reference=strict,  # 0.5 * loglik + sum_t w_t ll_t
                                               g_ll_obs=None if gobs is None else 0.5 + gobs[b])

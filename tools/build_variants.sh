@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/.."
 TU=$1; shift
-mkdir -p build/variants
+rm -rf build/variants; mkdir -p build/variants
 OTHERS=$(ls build/csrc/*.o | grep -v "/${TU}.o")
 while [ $# -gt 0 ]; do
   name=$1; flags=$2; shift 2

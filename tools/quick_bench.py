@@ -37,6 +37,12 @@ def main():
             g = bk.backward(wrt=WRT)
             e[2].record(); torch.cuda.synchronize()
             tf, tb = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for it in range(3):
+            e[0].record()
+            bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=False)
+            e[1].record(); torch.cuda.synchronize()
+        print(f"   forward without tape: {e[0].elapsed_time(e[1]):.3f} ms")
         print(f"coop={force} generic_adjoint={gen} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
               f"ll[0]={float(out['loglik'][0]):.6f} gT[0]={g['T'][0].flatten().tolist()} info!=0: {int((out['info']!=0).sum())}")
         if force and B > 16384: break
