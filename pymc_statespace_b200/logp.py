@@ -25,6 +25,22 @@ from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapuno
 from .models import MATRICES, StateSpaceSpec
 
 
+def _capture(dev, body, warmup):
+    """Run `body` a few times on a side stream (lazy initialisation: function attributes, workspaces), then capture it."""
+    with torch.cuda.device(dev):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+    return graph
+
+
 class HostStepGraph:
     """ONE CUDA graph for a whole host-to-host evaluation:
 
@@ -32,16 +48,23 @@ class HostStepGraph:
             -> packed [B, 1 + n_theta] = (logp, dlogp/dtheta) -> D2H into a pinned host buffer.
 
     A sampler that keeps theta on the host pays ~8 kernel launches + 2 copies per leapfrog step; replaying them as one
-    graph removes the per-launch CPU cost that a per-step synchronisation otherwise exposes.  With ``chunks > 1`` the
-    draws are split into that many parallel branches of the graph (chains are independent), so each branch's PCIe copies
-    overlap the other branches' kernels.  Measured on B200, configs[1]: eager 1.66 ms, graph 1.56 ms, 4 branches 1.53 ms.
+    graph removes the per-launch CPU cost that a per-step synchronisation otherwise exposes.  The draws are split into
+    ``chunks`` pieces (chains are independent) so that PCIe copies overlap kernels:
+
+    * ``sequential=False`` (batches that fill the GPU only as a whole, e.g. 65,536 draws): every chunk is a parallel
+      branch of the graph with its own evaluator, workspace and stream.  Measured on B200, configs[1]: eager 1.66 ms,
+      graph 1.56 ms, 4 branches 1.53 ms (round 1 kernels).
+    * ``sequential=True`` (large batches, e.g. >= 1 M draws): the chunks are waves through ONE evaluator sized for a
+      single wave (a quarter of the tape memory); wave k's H2D / D2H run on copy streams under the kernels of the
+      neighbouring waves.
+
     ``theta_host`` / ``out_host`` are captured BY ADDRESS: write the next theta into ``theta_host`` in place, call the
-    object, read ``out_host``.  Single-GPU (no collective inside the graph).
+    object, read ``out_host``.  No collective inside the graph: with one process per GPU every rank replays its own.
     """
 
     def __init__(self, model: "KalmanLogp", theta_host: torch.Tensor, out_host: torch.Tensor, warmup: int = 3,
-                 chunks: int = 1):
-        B, nt = model.B, model.spec.n_theta
+                 chunks: int = 1, sequential: bool = False):
+        B, nt = model.B * (chunks if sequential else 1), model.spec.n_theta
         for name, t, shape in (("theta_host", theta_host, (B, nt)), ("out_host", out_host, (B, 1 + nt))):
             if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float64
                     and t.is_contiguous() and t.is_pinned() and tuple(t.shape) == shape):
@@ -51,38 +74,59 @@ class HostStepGraph:
         self.model, self.theta_host, self.out_host, self.chunks = model, theta_host, out_host, chunks
         dev = model.device
         h = B // chunks
-        # one evaluator per branch (its own workspace and tape); a single branch reuses the caller's model
-        self._subs = [model] if chunks == 1 else [model.clone_for(h) for _ in range(chunks)]
         self._theta_dev = [torch.empty((h, nt), dtype=torch.float64, device=dev) for _ in range(chunks)]
-        self._streams = [torch.cuda.Stream(device=dev) for _ in range(chunks)]
+        if sequential:
+            # ``model`` IS the one-wave evaluator (n_draws = B / chunks)
+            self._subs = [model]
+            copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self._streams = [copy_in, copy_out]
+            self._info = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._packed = [torch.empty((h, 1 + nt), dtype=torch.float64, device=dev) for _ in range(chunks)]
 
-        def body():
-            cur = torch.cuda.current_stream(dev)
-            for c, (sub, th, st) in enumerate(zip(self._subs, self._theta_dev, self._streams)):
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    th.copy_(theta_host[c * h:(c + 1) * h], non_blocking=True)
-                    logp, grad = sub.logp_and_grad(th)
-                    out_host[c * h:(c + 1) * h].copy_(torch.cat([logp[:, None], grad], dim=1), non_blocking=True)
-            for st in self._streams:
-                cur.wait_stream(st)
+            def body():
+                cur = torch.cuda.current_stream(dev)
+                copy_in.wait_stream(cur)
+                copy_out.wait_stream(cur)
+                ready = []
+                with torch.cuda.stream(copy_in):
+                    for c, th in enumerate(self._theta_dev):
+                        th.copy_(theta_host[c * h:(c + 1) * h], non_blocking=True)
+                        ready.append(copy_in.record_event())
+                for c, th in enumerate(self._theta_dev):
+                    cur.wait_event(ready[c])
+                    logp, grad = model.logp_and_grad(th)
+                    packed = self._packed[c]  # persistent: read by the copy stream while the next wave computes
+                    torch.cat([logp[:, None], grad], dim=1, out=packed)
+                    self._info[c * h:(c + 1) * h].copy_(model.info)
+                    done = cur.record_event()
+                    with torch.cuda.stream(copy_out):
+                        copy_out.wait_event(done)
+                        out_host[c * h:(c + 1) * h].copy_(packed, non_blocking=True)
+                cur.wait_stream(copy_out)
+                cur.wait_stream(copy_in)
+        else:
+            # one evaluator per branch (its own workspace and tape); a single branch reuses the caller's model
+            self._subs = [model] if chunks == 1 else [model.clone_for(h) for _ in range(chunks)]
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(chunks)]
+            self._info = None
 
-        with torch.cuda.device(dev):
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(max(1, warmup)):  # lazy initialisation (function attributes, occupancy queries) outside capture
-                    body()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                body()
+            def body():
+                cur = torch.cuda.current_stream(dev)
+                for c, (sub, th, st) in enumerate(zip(self._subs, self._theta_dev, self._streams)):
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        th.copy_(theta_host[c * h:(c + 1) * h], non_blocking=True)
+                        logp, grad = sub.logp_and_grad(th)
+                        out_host[c * h:(c + 1) * h].copy_(torch.cat([logp[:, None], grad], dim=1), non_blocking=True)
+                for st in self._streams:
+                    cur.wait_stream(st)
+
+        self.graph = _capture(dev, body, warmup)
 
     @property
     def info(self) -> torch.Tensor:
         """Per-draw status of the last replay (device tensor; 0 = ok)."""
-        return torch.cat([sub.info for sub in self._subs])
+        return self._info if self._info is not None else torch.cat([sub.info for sub in self._subs])
 
     def __call__(self) -> torch.Tensor:
         self.graph.replay()
@@ -127,7 +171,7 @@ class KalmanLogp:
         self.device = torch.device(device)
         self.lib = load()
         self.filter_type, self.strict_reference, self._force_coop = filter_type, strict_reference, force_coop
-        y = np.asarray(data, dtype=np.float64)
+        y = data.detach().to(dtype=torch.float64) if isinstance(data, torch.Tensor) else np.asarray(data, dtype=np.float64)
         if y.ndim == 1:
             y = y[:, None]
         if y.ndim == 3 and y.shape[-1] == 1:
@@ -212,13 +256,15 @@ class KalmanLogp:
         self.info = out["info"]
         return out["loglik"]
 
-    def capture_host_step(self, theta_host: torch.Tensor, out_host: torch.Tensor, chunks: int = 1) -> "HostStepGraph":
-        """Capture host theta -> (logp, grad) on the host as one replayable CUDA graph (see ``HostStepGraph``)."""
-        return HostStepGraph(self, theta_host, out_host, chunks=chunks)
+    def capture_host_step(self, theta_host: torch.Tensor, out_host: torch.Tensor, chunks: int = 1,
+                          sequential: bool = False) -> "HostStepGraph":
+        """Capture host theta -> (logp, grad) on the host as one replayable CUDA graph (see ``HostStepGraph``).
+        ``sequential=True``: this evaluator handles ONE wave; theta_host / out_host hold ``chunks * n_draws`` rows."""
+        return HostStepGraph(self, theta_host, out_host, chunks=chunks, sequential=sequential)
 
     def clone_for(self, n_draws: int) -> "KalmanLogp":
         """A second evaluator of the same model / data / filter for ``n_draws`` draws (own workspace and tape)."""
-        return KalmanLogp(self.spec, self.y.cpu().numpy(), n_draws=n_draws, filter_type=self.filter_type,
+        return KalmanLogp(self.spec, self.y, n_draws=n_draws, filter_type=self.filter_type,
                           strict_reference=self.strict_reference, device=self.device, force_coop=self._force_coop)
 
     def logp_and_grad(self, theta, g_loglik: Optional[torch.Tensor] = None):

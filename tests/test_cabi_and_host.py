@@ -146,6 +146,47 @@ dist.destroy_process_group()
 """
 
 
+_GLOO_WAVES_WORKER = r"""
+import os, sys, types, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pymc_statespace_b200.dist import GatherStepGraph
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+class Stub:  # stands in for KalmanLogp (CUDA only): logp = row sum, grad = 2 * theta
+    def __init__(self, h, nt):
+        self.B, self.spec, self.device = h, types.SimpleNamespace(n_theta=nt), torch.device("cpu")
+    def logp_and_grad(self, th):
+        self.info = torch.zeros(th.shape[0], dtype=torch.int32)
+        return th.sum(1), 2.0 * th
+
+h, nt, waves = 5, 3, 4
+B = h * waves
+full = torch.arange(world * B * nt, dtype=torch.float64).reshape(world * B, nt)   # draw d of the whole job
+g = GatherStepGraph(Stub(h, nt), full[rank * B:(rank + 1) * B].contiguous(), waves=waves)
+g()
+rows = g.rows()
+assert tuple(g.out.shape) == (waves, world, h, 1 + nt) and tuple(rows.shape) == (world * B, 1 + nt)
+assert torch.equal(rows[:, 0], full.sum(1)) and torch.equal(rows[:, 1:], 2.0 * full), rank   # draw order, every rank
+dist.barrier()
+if rank == 0:
+    print("GLOO_WAVES_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_gather_step_waves_world_size_2_gloo(tmp_path):
+    """N > 1 path of bench.py's resident leg (dist.GatherStepGraph): wave / rank / row layout and draw order, on CPU."""
+    script = tmp_path / "worker_waves.py"
+    script.write_text(_GLOO_WAVES_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29519", str(script), ROOT],
+        capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0 and "GLOO_WAVES_OK" in out.stdout, out.stderr[-2000:]
+
+
 def test_gather_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)

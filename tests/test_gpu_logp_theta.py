@@ -222,6 +222,34 @@ def test_host_step_graph_matches_eager(kind):
 
 
 @pytest.mark.gpu
+def test_wave_pipelines_match_single_pass():
+    """bench.py's c5 legs: HostStepGraph(sequential=True) and dist.GatherStepGraph (world 1) push the draws through ONE
+    wave-sized evaluator in 4 waves; every row must equal the single-pass evaluation bit for bit."""
+    from pymc_statespace_b200.dist import GatherStepGraph
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.synthetic import arma21_workload
+
+    B, n, waves = 2048, 60, 4
+    spec, y, theta = arma21_workload(B, n)
+    th_d = torch.as_tensor(theta, device="cuda")
+    lp, g = KalmanLogp(spec, y, n_draws=B).logp_and_grad(th_d)
+    ref = torch.cat([lp[:, None], g], dim=1).cpu()
+    wave_model = KalmanLogp(spec, y, n_draws=B // waves)
+    gsg = GatherStepGraph(wave_model, th_d, waves=waves)
+    assert gsg.graph is not None
+    gsg()
+    torch.cuda.synchronize()
+    assert torch.equal(gsg.rows().cpu(), ref) and int(gsg.info.abs().max()) == 0
+    th_h = torch.from_numpy(np.ascontiguousarray(theta)).pin_memory()
+    out_h = torch.empty((B, 1 + spec.n_theta), dtype=torch.float64).pin_memory()
+    step = wave_model.capture_host_step(th_h, out_h, chunks=waves, sequential=True)
+    assert torch.equal(step().clone(), ref) and int(step.info.abs().max()) == 0 and step.info.numel() == B
+    th_h.mul_(0.95)
+    lp2, g2 = KalmanLogp(spec, y, n_draws=B).logp_and_grad(th_h.to("cuda"))
+    assert torch.equal(step().clone(), torch.cat([lp2[:, None], g2], dim=1).cpu())
+
+
+@pytest.mark.gpu
 def test_scatter_multi_matches_numpy_and_single_calls():
     """kfb_scatter_forward_multi / kfb_scatter_backward_multi (one launch for all matrices) against a numpy restatement
     and the per-matrix entry points, including duplicate destinations (last writer wins) and a theta entry used twice."""
