@@ -115,9 +115,11 @@ KFB_HD void load_or_zero(X& x, TD& dst, const double* src, int cnt) {
   KFB_FOR(i, cnt) dst[i] = src ? src[i] : 0.0;
 }
 
-// Symmetric positive-definite p x p inverse via L D L^T (no square roots).  Reads the lower triangle
-// of F.  Serial; executed by one lane.  piv[] receives D (det F = prod D).  Returns false if a pivot
-// is not a positive finite number.
+// Symmetric positive-definite p x p inverse via L D L^T (no square roots).  Reads the UPPER triangle of F, like
+// LAPACK posv behind the reference's `solve(F, I, assume_a="pos")` (kalman_filter.py:267-269; scipy's default
+// lower=False) - it only matters when F is not symmetric, i.e. at t = 0 with a non-symmetric P0 and k_endog > 1
+// (BayesianVARMAX with stationary_initialization=False writes P0 = theta.reshape(m, m)).  Serial; executed by one lane.
+// piv[] receives D (det sym(F) = prod D).  Returns false if a pivot is not a positive finite number.
 template <class TF, class TG, class TL, class TP>
 KFB_HD bool ldl_inverse(const TF& F, TG& G, TL& L, TL& Li, TP& piv, int p) {
   bool ok = true;
@@ -133,7 +135,7 @@ KFB_HD bool ldl_inverse(const TF& F, TG& G, TL& L, TL& Li, TP& piv, int p) {
 #pragma unroll
     for (int i = 0; i < p; ++i) {
       if (i > j) {
-        double s = F[i * p + j];
+        double s = F[j * p + i];
 #pragma unroll
         for (int k = 0; k < p; ++k)
           if (k < j) s = kf_fma(-L[i * p + k] * L[j * p + k], piv[k], s);
@@ -170,6 +172,34 @@ KFB_HD bool ldl_inverse(const TF& F, TG& G, TL& L, TL& Li, TP& piv, int p) {
           if (k >= i) s = kf_fma(Li[k * p + i] * L[k * p + k], Li[k * p + j], s);
         G[i * p + j] = s;
         G[j * p + i] = s;
+      }
+    }
+  }
+  return ok;
+}
+
+// Pivots of the LU factorisation (Doolittle, no pivoting) of the FULL matrix F: prod piv = det F as the reference's
+// `pt.linalg.det(F)` (kalman_filter.py:281) sees it - every entry, not one triangle.  For a symmetric F these are the
+// L D L^T pivots again; the kernels call it only for the first step (the one place F can be non-symmetric, see
+// ldl_inverse).  W: p x p scratch.  Returns false if a pivot is not a positive finite number (log det undefined).
+template <class TF, class TW, class TP>
+KFB_HD bool lu_pivots(const TF& F, TW& W, TP& piv, int p) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < p * p; ++i) W[i] = F[i];
+#pragma unroll
+  for (int k = 0; k < p; ++k) {
+    const double d = W[k * p + k];
+    piv[k] = d;
+    ok = ok && (d > 0.0) && (d < 1.0e300);
+    const double r = 1.0 / d;
+#pragma unroll
+    for (int i = 0; i < p; ++i) {
+      if (i > k) {
+        const double l = W[i * p + k] * r;
+#pragma unroll
+        for (int j = 0; j < p; ++j)
+          if (j > k) W[i * p + j] = kf_fma(-l, W[k * p + j], W[i * p + j]);
       }
     }
   }
@@ -292,7 +322,8 @@ struct StepStat {
 // Outputs af, Pf and keeps v, Mm, F, Fi(=F^-1), K, A, w in `u` for the adjoint.
 template <int MK, class X, class TA, class TPm>
 KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, double d_sign, const TA& a,
-                                const TPm& P, UpdTmp<X>& u, TA& af, TPm& Pf, LogAcc* acc, bool per_step_log) {
+                                const TPm& P, UpdTmp<X>& u, TA& af, TPm& Pf, LogAcc* acc, bool per_step_log,
+                                bool full_det = false) {
   const int m = x.m(), p = x.p();
   StepStat st;
   KFB_FOR(i, p) {
@@ -322,6 +353,7 @@ KFB_HD StepStat update_observed(X& x, const Params<X>& prm, const double* yt, do
     }
   } else if (x.lane() == 0) {
     st.ok = ldl_inverse(u.F, u.Fi, u.L, u.Li, u.piv, p);
+    if (full_det && p > 1 && st.ok) st.ok = lu_pivots(u.F, u.L, u.piv, p);  // log det of the full matrix (t = 0)
     if (st.ok) {
 #pragma unroll
       for (int i = 0; i < p; ++i) {
@@ -530,7 +562,7 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
     } else {
       const int nm = count_missing(x, yt);
       if (nm == 0) {
-        StepStat st = update_observed<MK>(x, prm, yt, A.d_sign, a, P, tmp, af, Pf, &acc, full);
+        StepStat st = update_observed<MK>(x, prm, yt, A.d_sign, a, P, tmp, af, Pf, &acc, full, MK == MK_STD && t == 0);
         if (!st.ok && info == 0) info = t + 1;
         ll_t = -0.5 * (A.ll_const + st.logdet + st.quad);
       } else {

@@ -26,7 +26,7 @@ struct PredTmp {
 // v, Mm, F, Fi, TM, Kp, Lm(= T - Kp Z), w for an observed row.  Gain matrix = Fi (MK_STD) or prm.Gss (MK_STEADY).
 template <int MK, class X, class TA, class TPm>
 KFB_HD StepStat pred_gain(X& x, const Params<X>& prm, const double* yt, double d_sign, const TA& a, const TPm& P,
-                          PredTmp<X>& u, LogAcc* acc, bool per_step_log) {
+                          PredTmp<X>& u, LogAcc* acc, bool per_step_log, bool full_det = false) {
   const int m = x.m(), p = x.p();
   StepStat st;
   KFB_FOR(i, p) {
@@ -48,6 +48,7 @@ KFB_HD StepStat pred_gain(X& x, const Params<X>& prm, const double* yt, double d
   st.logdet = 0.0;
   if (x.lane() == 0) {
     st.ok = ldl_inverse(u.F, u.Fi, u.L, u.Li, u.piv, p);
+    if (full_det && p > 1 && st.ok) st.ok = lu_pivots(u.F, u.L, u.piv, p);  // log det of the full matrix (t = 0)
     if (st.ok) {
 #pragma unroll
       for (int i = 0; i < p; ++i) {
@@ -143,7 +144,7 @@ KFB_HD void forward_unit_pred(X& x, const KfArgs& A, long long u) {
     const double* yt = y + (long long)t * p;
     const int nm = count_missing(x, yt);
     if (nm == 0) {
-      StepStat st = pred_gain<MK>(x, prm, yt, A.d_sign, a, P, tmp, &acc, false);
+      StepStat st = pred_gain<MK>(x, prm, yt, A.d_sign, a, P, tmp, &acc, false, MK == MK_STD && t == 0);
       if (!st.ok && info == 0) info = t + 1;
       llsum += -0.5 * (A.ll_const + st.quad);
       KFB_FOR(i, m) {  // a' = T a + c + Kp v

@@ -154,7 +154,7 @@ struct RowGain {
 template <int M, int P, int R, int MK, class TR>
 __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d_sign, const double (&dv)[P], unsigned mask,
                                           const RowIdx<M, R>& rw, TR tr, const double (&Pr)[R][M], const double (&Gss)[P * P],
-                                          RowGain<M, P, R>& g) {
+                                          RowGain<M, P, R>& g, bool full_det = false) {
   using L = RowsLayout<M, P>;
   // ---- phase A: v (every lane), Mm rows
   {
@@ -201,6 +201,7 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
     for (int q = 0; q < R; ++q) g.TM[q][j] = s[q];
   }
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
+  if (MK == MK_STD && P > 1 && full_det && g.ok) g.ok = lu_pivots(Fr, Lr, g.piv, P);  // det of the full matrix (t = 0)
   double qd = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
@@ -319,7 +320,7 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
       for (int q = 0; q < R; ++q) an[q] = fma(Tr[q][k], ak, an[q]);
     }
     if (nm == 0) {
-      rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, Gss, g);
+      rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, Gss, g, t == 0);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll

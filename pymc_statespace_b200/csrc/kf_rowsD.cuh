@@ -165,7 +165,8 @@ struct RowDGain {
 // MK_STEADY: the gain matrix is the fixed Gss = (Z Pss Z^T + H)^-1 instead of F^-1 (F is still factorised for log det).
 template <int M, int P, int MK, class L>
 __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P],
-                                           const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g) {
+                                           const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g,
+                                           bool full_det = false) {
   constexpr int LD = L::LD;
   const int si = rowsD_swz(i);
   // ---- A: Mm row (own P row x Z rows), v (every lane)
@@ -234,6 +235,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     for (int j = 0; j < P; ++j) TM[j] = (Tq[j][0] + Tq[j][1]) + (Tq[j][2] + Tq[j][3]);
   }
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
+  if (MK == MK_STD && P > 1 && full_det && g.ok) g.ok = lu_pivots(Fr, Lr, g.piv, P);  // det of the full matrix (t = 0)
   double qd = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
@@ -350,7 +352,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
 #pragma unroll
     for (int j = 0; j < P; ++j) KH[j] = 0.0;
     if (observed) {
-      rowsD_gain<M, P, MK, L>(sm, yt, A.d_sign, dv, Gss, i, act, g);
+      rowsD_gain<M, P, MK, L>(sm, yt, A.d_sign, dv, Gss, i, act, g, t == 0);
       if (!g.ok && info == 0) info = t + 1;
       if (g.ok) {
 #pragma unroll

@@ -167,6 +167,18 @@ def local_level_spec() -> StateSpaceSpec:
     return StateSpaceSpec(m, 1, r, 9, base, maps, False, ("x0", "P0", "sigma_obs", "sigma_state"), slices)
 
 
+def local_level_1state_spec() -> StateSpaceSpec:
+    """BASELINE.json configs[0]: the TRUE local level model (k_states = 1; SURVEY.md section 8(d) C1(i), A.2-Q11 - the
+    reference class BayesianLocalLevel is a 2-state local linear trend, `local_level_spec`).  y_t = mu_t + eps_t,
+    mu_t+1 = mu_t + eta_t:  T = Z = R = [[1]];  theta = [a0, P0, sigma2_obs (H), sigma2_level (Q)]."""
+    base = _empty_base(1, 1, 1)
+    base["T"][0, 0] = base["Z"][0, 0] = base["R"][0, 0] = 1.0
+    maps = {k: [] for k in MATRICES}
+    maps["a0"], maps["P0"], maps["H"], maps["Q"] = [(0, 0)], [(1, 0)], [(2, 0)], [(3, 0)]
+    slices = {"x0": slice(0, 1), "P0": slice(1, 2), "sigma_obs": slice(2, 3), "sigma_state": slice(3, 4)}
+    return StateSpaceSpec(1, 1, 1, 4, base, maps, False, ("x0", "P0", "sigma_obs", "sigma_state"), slices)
+
+
 def custom_spec(k_states: int, k_endog: int, k_posdef: int, n_theta: int, base: Dict[str, np.ndarray],
                 maps: Dict[str, List[Tuple[int, int]]], stationary_initialization: bool = False,
                 param_names: Tuple[str, ...] = ()) -> StateSpaceSpec:

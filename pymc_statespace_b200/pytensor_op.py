@@ -5,9 +5,11 @@ gradient (BASELINE.json north_star).
 ``KalmanFilterGradOp`` whose ``perform`` runs the adjoint CUDA kernel - the same split the reference itself uses for
 ``SolveDiscreteARE`` (``pymc_statespace/utils/pytensor_scipy.py:11-60``: ``perform`` + symbolic ``grad``).
 
-PyTensor / PyMC are NOT installed in the build image, so this module is import-guarded and could
-not be executed here; everything below the Op boundary (``filters.BaseFilter._eager`` -> ``torch_op`` -> C ABI) is
-what the GPU tests exercise.  PyMC forks chain processes: CUDA is initialised lazily inside ``perform``.
+PyTensor / PyMC are NOT installed in the build image, so this module is import-guarded.  Its
+protocol wiring (make_node / infer_shape / connection_pattern / L_op / both ``perform`` bodies) is executed by
+tests/test_pytensor_shim.py against a minimal stand-in of the Op protocol (tests/fake_pytensor - NOT PyTensor); everything
+below the Op boundary (``filters.BaseFilter._eager`` -> ``torch_op`` -> C ABI) is what the GPU tests exercise.
+PyMC forks chain processes: CUDA is initialised lazily inside ``perform``.
 """
 from __future__ import annotations
 
@@ -26,6 +28,11 @@ except Exception:  # noqa: BLE001
     Op = object
 
 _IN_NAMES = ("data", "a0", "P0", "T", "Z", "R", "H", "Q", "c", "d")
+
+
+def _input_names(has_c, has_d):
+    """Names of the Op's inputs in order: the eight mandatory ones, then c and / or d if given."""
+    return _IN_NAMES[:8] + (("c",) if has_c else ()) + (("d",) if has_d else ())
 
 
 def _require():
@@ -122,7 +129,7 @@ class KalmanFilterGradOp(Op):
         import torch
 
         from .filters import FILTER_FACTORY
-        from .torch_op import kalman_filter_torch
+        from .torch_op import kalman_logp_grads
 
         arrs = [np.asarray(x, dtype=np.float64) for x in inputs]
         g_ll, g_llobs = arrs[-2], arrs[-1]
@@ -130,17 +137,13 @@ class KalmanFilterGradOp(Op):
         flt = FILTER_FACTORY[self.kind]()
         flt.strict_reference = self.strict_reference
         dev = torch.device("cuda", torch.cuda.current_device())
+        names = _input_names(self.has_c, self.has_d)[1:]
         ts = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in arrs]
-        for t in ts[1:]:
-            t.requires_grad_(True)
-        base, rest = ts[:8], ts[8:]
-        c = rest.pop(0) if self.has_c else None
-        d = rest.pop(0) if self.has_d else None
-        outs = kalman_filter_torch(flt, *base, c, d)
-        target = outs[4] * torch.as_tensor(g_ll, device=dev) + (outs[5] * torch.as_tensor(g_llobs, device=dev)).sum()
-        grads = torch.autograd.grad(target, ts[1:], allow_unused=True)
-        for storage, g, t in zip(output_storage, grads, ts[1:]):
-            storage[0] = (torch.zeros_like(t) if g is None else g).detach().cpu().numpy()
+        # one loglik-only forward (hot-path kernels + tape) and the adjoint kernel; no full-output pass, no autograd tape
+        _, grads = kalman_logp_grads(flt, ts[0], dict(zip(names, ts[1:])), g_loglik=g_ll,
+                                     g_ll_obs=(g_llobs if np.any(g_llobs != 0.0) else None))
+        for storage, k in zip(output_storage, names):
+            storage[0] = grads[k].detach().cpu().numpy()
 
 
 def build_symbolic_graph(flt, data, a0, P0, T, Z, R, H, Q, c=None, d=None):
@@ -151,8 +154,9 @@ def build_symbolic_graph(flt, data, a0, P0, T, Z, R, H, Q, c=None, d=None):
         inputs.append(c)
     if d is not None:
         inputs.append(d)
-    ndims = {n: pt.as_tensor_variable(x).ndim for n, x in zip(_IN_NAMES, inputs)}
-    if flt.kind in ("steady_state", "univariate") and any(ndims[k] == 3 for k in ("T", "Z", "R", "H", "Q")):
+    # names follow the inputs actually passed (c and d are optional and independent of each other)
+    ndims = {n: pt.as_tensor_variable(x).ndim for n, x in zip(_input_names(c is not None, d is not None), inputs)}
+    if flt.kind in ("steady_state", "univariate") and any(ndims.get(k) == 3 for k in ("T", "Z", "R", "H", "Q", "c", "d")):
         raise ValueError("All system matrices must be time-invariant to use this filter")
     op = KalmanFilterOp(flt.kind, flt.strict_reference, c is not None, d is not None)
     return list(op(*inputs))

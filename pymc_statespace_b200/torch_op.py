@@ -54,11 +54,47 @@ class _KalmanFn(torch.autograd.Function):
         return (None, None, None, *res)
 
 
+_BK_CACHE = {}
+
+
+def _evaluator(flt, n, m, p, r, tv, device):
+    """One BatchedKalman (and its workspace) per problem geometry: PyMC calls the Op once per leapfrog step with the
+    same shapes, so the evaluator and its device buffers are built once."""
+    key = (flt.kind, n, m, p, r, bool(flt.strict_reference), tuple(tv), str(device))
+    bk = _BK_CACHE.get(key)
+    if bk is None:
+        if len(_BK_CACHE) > 64:
+            _BK_CACHE.clear()
+        bk = _BK_CACHE[key] = BatchedKalman(flt.kind, n, m, p, r, n_draws=1, strict_reference=flt.strict_reference,
+                                            time_varying=tv, device=device)
+    return bk
+
+
+def kalman_logp_grads(flt, data, mats, g_loglik=1.0, g_ll_obs=None):
+    """What the gradient Op needs and nothing more: ONE loglik-only forward pass (hot-path kernels, tape saved) + the
+    adjoint kernel.  ``mats``: name -> float64 CUDA tensor in the reference's shapes (a0[m,1], P0[m,m], ..., optional c, d).
+    Returns (loglik 0-d tensor, {name: cotangent with the input's shape}) for
+    ``g_loglik * loglik + sum_t g_ll_obs[t] * ll_obs[t]``."""
+    full = {k: mats.get(k) for k in MATRIX_NAMES}
+    n, m, p, r, tv = flt._validate(data, *[full[k] for k in MATRIX_NAMES])
+    bk = _evaluator(flt, n, m, p, r, tv, data.device)
+    present = tuple(k for k in MATRIX_NAMES if full[k] is not None)
+    out = bk.forward(data[..., 0].contiguous(), *[None if full[k] is None else full[k].detach()[None] for k in MATRIX_NAMES],
+                     outputs=("loglik",), save_for_backward=True)
+    info = int(out["info"][0])
+    if info != 0:
+        _raise_info(info)
+    dev = data.device
+    gl = torch.as_tensor(g_loglik, dtype=torch.float64, device=dev).reshape(1).contiguous()
+    glo = None if g_ll_obs is None else torch.as_tensor(g_ll_obs, dtype=torch.float64, device=dev).reshape(1, n).contiguous()
+    grads = bk.backward(g_loglik=gl, g_ll_obs=glo, wrt=present)
+    return out["loglik"][0], {k: grads[k][0].reshape(full[k].shape) for k in present}
+
+
 def kalman_filter_torch(flt, data, a0, P0, T, Z, R, H, Q, c=None, d=None):
     """data[n,p,1], a0[m,1], ... float64 CUDA tensors -> the reference's 6-list (torch tensors)."""
     n, m, p, r, tv = flt._validate(data, a0, P0, T, Z, R, H, Q, c, d)
-    bk = BatchedKalman(flt.kind, n, m, p, r, n_draws=1, strict_reference=flt.strict_reference, time_varying=tv,
-                       device=data.device)
+    bk = _evaluator(flt, n, m, p, r, tv, data.device)
     full = {"a0": a0, "P0": P0, "T": T, "Z": Z, "R": R, "H": H, "Q": Q, "c": c, "d": d}
     present = tuple(k for k in MATRIX_NAMES if full[k] is not None)
     fs, ps, fc, pc, ll, llo = _KalmanFn.apply(bk, data[..., 0].contiguous(), present, *[full[k] for k in present])

@@ -93,6 +93,65 @@ def test_local_level_nile_cpu_config():
     _compare(om.local_level_matrices, y[:, :, None], theta, logp, grad, (0, 5, 15))
 
 
+def test_nile_true_local_level_k_states_1():
+    """BASELINE.json configs[0] as written: Nile, T = 100, k_states = 1, standard filter, logp + grad at theta level
+    (theta = [a0, P0, sigma2_obs, sigma2_level]) - against torch-autograd of the oracle and, for the value, against the
+    dense multivariate-normal density of the sample (no recursion at all)."""
+    from oracle import kalman_numpy as kn
+    from pymc_statespace_b200.models import local_level_1state_spec
+
+    spec = local_level_1state_spec()
+    y = nile_data()[:, None]
+    rng = np.random.default_rng(4)
+    B = 8
+    theta = np.stack([rng.normal(1120, 50, B), 1e6 * np.exp(rng.normal(0, 0.1, B)), 15000 * np.exp(rng.normal(0, 0.2, B)),
+                      1400 * np.exp(rng.normal(0, 0.2, B))], axis=1)
+
+    def mats(t):
+        one = torch.ones(1, 1, dtype=torch.float64)
+        return t[0].reshape(1, 1), t[1].reshape(1, 1), one, one, one, t[2].reshape(1, 1), t[3].reshape(1, 1)
+
+    for kind in ("standard", "single", "cholesky", "univariate"):
+        logp, grad, _ = _run(spec, y, theta, kind)
+        _compare(mats, y[:, :, None], theta, logp, grad, (0, 3, 7), kind, rtol=1e-7 if kind == "univariate" else RTOL)
+    for b in (0, 7):
+        m = spec.matrices(theta[b])
+        dense = kn.dense_gaussian_loglik(y[:, :, None], *[m[k] for k in ("a0", "P0", "T", "Z", "R", "H", "Q")], mp_digits=30)
+        assert abs(logp[b] - dense) < 1e-10 * abs(dense)
+
+
+def test_full_size_all_draws_match_c_port():
+    """configs[1] at full size, EVERY draw: 65,536 draws x T = 1000 on the GPU against the plain-C port
+    (oracle/kalman_c.c, itself validated against the torch oracle in tests/test_cabi_and_host.py) - logp and the five
+    matrix-level cotangents the theta-level gradient is assembled from."""
+    import os
+
+    from oracle import kalman_c
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.models import MATRICES
+    from pymc_statespace_b200.synthetic import arma11_workload
+
+    B, n = 65536, 1000
+    spec, y, theta = arma11_workload(B, n)
+    model = KalmanLogp(spec, y, n_draws=B)
+    mats = model._scatter(torch.as_tensor(theta, device="cuda"))
+    out = model.kalman.forward(model.y, *[mats[k] for k in MATRICES], outputs=("loglik",), save_for_backward=True)
+    g = model.kalman.backward(wrt=("a0", "P0", "T"))
+    gC = None
+    f = lambda t: (t if t.ndim == 3 or t.shape[0] == B else t.expand(B, *t.shape)).cpu().numpy()  # noqa: E731
+    T, R, Q, P0, a0 = f(mats["T"]), f(mats["R"]), f(mats["Q"]), f(mats["P0"]), f(mats["a0"])
+    C = R @ Q @ R.transpose(0, 2, 1)
+    ll, gc, bad = kalman_c.logp_grad_batch(y, a0.reshape(B, 2), P0, T, mats["Z"].cpu().numpy().reshape(1, 2),
+                                           mats["H"].cpu().numpy().reshape(1, 1), C, nthreads=os.cpu_count() or 1)
+    assert bad == 0 and int((out["info"] != 0).sum()) == 0
+    lg = out["loglik"].cpu().numpy()
+    assert np.abs(lg - ll).max() / np.abs(ll).max() < 1e-11 and (np.abs(lg / ll - 1) < 1e-9).all()
+    for k in ("a0", "P0", "T"):
+        got, ref = g[k].cpu().numpy().reshape(B, -1), gc[k].reshape(B, -1)
+        err = np.abs(got - ref).max(axis=1) / np.maximum(np.abs(ref).max(axis=1), 1e-300)
+        assert err.max() < 1e-8, (k, int(err.argmax()), err.max())
+
+
 def test_full_size_properties_arma11():
     """BASELINE.json configs[1] at full size (65,536 draws x T=1000): size-independent properties.
     (a) thread-per-unit and cooperative kernels agree; (b) sub-batch invariance; (c) sampled draws match the

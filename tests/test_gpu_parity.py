@@ -504,3 +504,69 @@ def test_p1_adjoint_kernel_vs_generic_and_oracle(m):
                     got = res[False][k][b].reshape(gref[k].shape)
                     scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
                     assert np.abs(got - gref[k]).max() / scale < RTOL, (kind, wrt, k, b)
+
+
+@pytest.mark.parametrize("n_missing", [0, 5])
+def test_nile_fixture_cuda_loglik_equals_dense_gaussian_density(n_missing):
+    """The CUDA log-likelihood of the one fixture the reference value-tests (Nile local linear trend, P0 = 1e6 I,
+    tests/test_kalman_filter.py:226-241) against the dense multivariate-normal density of the stacked sample in 40-digit
+    arithmetic (tests/golden/nile_dense_loglik.json) - a parity leg that does NOT route through the oracle's recursion.
+    Every kernel family that can run it: thread-per-unit (full outputs), k_endog = 1 hot path, cooperative."""
+    import json
+    import os
+
+    from pymc_statespace_b200 import BatchedKalman
+    from tests.helpers import GOLDEN
+
+    gold = json.load(open(os.path.join(GOLDEN, "nile_dense_loglik.json")))[str(n_missing)]["loglik"]
+    args = nile_inputs(n_missing)
+    for kind in KINDS_P1:
+        for force_coop in (False, True):
+            res, _, info = run_single(kind, args, force_coop=force_coop, bwd=False)
+            assert info == 0 and abs(res[4] - gold) < 1e-10 * abs(gold), (kind, force_coop, res[4], gold)
+    y, a0, P0, T, Z, R, H, Q = args
+    bk = BatchedKalman("standard", y.shape[0], 2, 1, 2, n_draws=1)   # loglik only -> kf_p1_forward_kernel
+    out = bk.forward(_dev(y[..., 0]), _dev(a0[None, :, 0]), _dev(P0[None]), _dev(T), _dev(Z), _dev(R), _dev(H), _dev(Q))
+    assert abs(float(out["loglik"][0]) - gold) < 1e-10 * abs(gold)
+
+
+@pytest.mark.parametrize("force_coop", [False, True], ids=["thread", "coop"])
+def test_single_filter_intercept_sign_quirk_on_device(force_coop):
+    """SURVEY A.2-Q5 on the GPU: SingleTimeseriesFilter computes v = y - Z a + d (kalman_filter.py:335-336); strict mode
+    reproduces the sign, corrected mode (strict_reference=False) uses v = y - Z a - d like every other filter."""
+    rng = np.random.default_rng(12)
+    args = random_system(rng, 3, 1, 2, 30, n_missing=3)
+    c, d = rng.normal(size=(3, 1)), rng.normal(size=(1, 1)) + 1.5
+    check_against_oracle("single", args, c, d, strict=True, force_coop=force_coop)
+    check_against_oracle("single", args, c, d, strict=False, force_coop=force_coop)
+    strict = run_single("single", args, c, d, strict=True, force_coop=force_coop, bwd=False)[0][4]
+    flipped = run_single("single", args, c, -d, strict=False, force_coop=force_coop, bwd=False)[0][4]
+    other = run_single("standard", args, c, d, force_coop=force_coop, bwd=False)[0][4]
+    assert abs(strict - flipped) < 1e-10 * abs(strict) and abs(strict - other) > 1e-3
+
+
+@pytest.mark.parametrize("dims", [(3, 2, 2), (4, 3, 2), (6, 3, 3), (8, 2, 2)])
+def test_non_symmetric_P0_multivariate(dims):
+    """P0 = theta.reshape(m, m) (BayesianVARMAX, stationary_initialization=False) is non-symmetric
+    under NUTS.  The reference inverts the UPPER triangle of F_0 (posv) and takes log det of the full matrix; thread,
+    cooperative and fused-row kernels must all reproduce the oracle's restatement of those SciPy calls."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = dims
+    rng = np.random.default_rng(90 + m)
+    args = list(random_system(rng, m, p, r, 15, n_missing=1))
+    args[2] = args[2] + 0.1 * rng.normal(size=(m, m))
+    for strict in (True, False):
+        ref = kn.kalman_filter("standard", *args, strict_reference=strict)
+        for force_coop in (False, True):
+            res, _, info = run_single("standard", args, strict=strict, force_coop=force_coop, bwd=False)
+            assert info == 0
+            for name, a, b in zip(ALL_OUT, res, ref):
+                assert rel_err(a, b) < RTOL, (name, force_coop)
+        y, a0, P0, T, Z, R, H, Q = args      # loglik-only request -> predictor-form / fused-row kernels
+        B = 9
+        bk = BatchedKalman("standard", y.shape[0], m, p, r, n_draws=B, strict_reference=strict)
+        rep = lambda x: _dev(np.repeat(x[None], B, axis=0))  # noqa: E731
+        out = bk.forward(_dev(y[..., 0]), rep(a0[:, 0]), rep(P0), rep(T), _dev(Z), rep(R), _dev(H), rep(Q))
+        ll = out["loglik"].cpu().numpy()
+        assert int((out["info"] != 0).sum()) == 0 and np.abs(ll - ref[4]).max() < 1e-10 * abs(ref[4])

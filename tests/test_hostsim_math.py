@@ -241,3 +241,24 @@ def test_p1_short_form_adjoint_nile_fixture():
         _, gt = kt.loglik_and_grads("standard", *args)
         for k in gt:
             assert rel_err(g[k], gt[k]) < (1e-6 if k == "P0" else 1e-10), (k, g[k], gt[k])
+
+
+@pytest.mark.parametrize("static", [True, False], ids=["ThreadCtx", "CoopCtx"])
+def test_non_symmetric_P0_multivariate_matches_reference_triangle_use(static):
+    """BayesianVARMAX(stationary_initialization=False) hands the filter P0 = theta.reshape(m, m),
+    which NUTS makes non-symmetric, so F_0 = Z P0 Z^T + H is non-symmetric.  The reference's StandardFilter then inverts
+    the UPPER triangle (LAPACK posv, scipy default lower=False, kalman_filter.py:267-269) and takes log det of the FULL
+    matrix (:281).  The kernels mirror both (ldl_inverse / lu_pivots); the oracle restates the reference's SciPy calls."""
+    rng = np.random.default_rng(17)
+    for (m, p, r) in ((3, 2, 2), (4, 3, 2)):
+        args = list(random_system(rng, m, p, r, 12, n_missing=1))
+        args[2] = args[2] + 0.1 * rng.normal(size=(m, m))
+        for pred in (False, True):
+            for strict in (True, False):
+                ref = kn.kalman_filter("standard", *args, strict_reference=strict)
+                outs, _, info = hostsim.run("standard", *args, strict=strict, static_dims=static, full=not pred, pred=pred,
+                                            do_bwd=False)
+                assert info == 0 and abs(outs[4] - ref[4]) < 1e-12 * abs(ref[4]), (m, p, pred, strict, outs[4], ref[4])
+                if not pred:
+                    for a, b in zip(outs[:4], ref[:4]):
+                        assert rel_err(a, b) < 1e-11

@@ -51,6 +51,38 @@ def test_four_filters_agree_on_nile_fixture(n_missing):
             np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-7)
 
 
+@pytest.mark.parametrize("n_missing", [0, 5])
+def test_nile_fixture_equals_dense_gaussian_density(n_missing):
+    """the one fixture the reference value-tests (Nile local linear trend, P0 = 1e6 I,
+    tests/test_kalman_filter.py:226-241) pinned on an algorithm-independent known answer - the dense multivariate-normal
+    log-density of the stacked sample (missing rows deleted), evaluated in 40-digit arithmetic and committed as
+    tests/golden/nile_dense_loglik.json (tests/golden/make_nile_dense.py).  All four filters the reference compares."""
+    import json
+
+    gold = json.load(open(os.path.join(GOLDEN, "nile_dense_loglik.json")))[str(n_missing)]
+    args = nile_inputs(n_missing)
+    assert sorted(np.where(np.isnan(args[0][:, 0, 0]))[0].tolist()) == gold["missing_rows"]
+    for kind in ("standard", "cholesky", "single", "univariate"):
+        ll = kn.kalman_filter(kind, *args)[4]
+        assert abs(ll - gold["loglik"]) < 1e-12 * abs(gold["loglik"]), (kind, ll, gold["loglik"])
+
+
+def test_dense_density_generator_reproduces_golden_value():
+    # the committed golden value is what the generator produces today (40-digit dense density, ~3 s)
+    import json
+
+    gold = json.load(open(os.path.join(GOLDEN, "nile_dense_loglik.json")))["5"]
+    assert kn.dense_gaussian_loglik(*nile_inputs(5), mp_digits=40) == gold["loglik"]
+
+
+def test_dense_density_with_partial_missing_rows():
+    # univariate filter (the only one that supports partially missing rows) against the dense density, float64 and mp
+    args = random_system(np.random.default_rng(3), 4, 3, 2, 12, n_missing=2, partial=True, diag_H=True)
+    ll = kn.kalman_filter("univariate", *args)[4]
+    assert abs(ll - kn.dense_gaussian_loglik(*args)) < 1e-10 * abs(ll)
+    assert abs(ll - kn.dense_gaussian_loglik(*args, mp_digits=30)) < 1e-12 * abs(ll)
+
+
 def test_standard_filter_log2pi_quirk_offset():
     # SURVEY A.2-Q1: strict standard filter counts log(2 pi) once per step instead of k_endog times
     p, n = 3, 20
