@@ -25,8 +25,9 @@
  *  - errors: integer status (0 = OK), never C++ exceptions; numerical failures are reported
  *    per unit in `info[u]` (0 ok; t+1 > 0: innovation covariance F_t not positive definite at
  *    0-based step t; -(t+1) < 0: partially-missing y_t in a filter that only supports
- *    all-or-nothing rows - reference raises LinAlgError there) and the
- *    unit's loglik is NaN.
+ *    all-or-nothing rows - reference raises LinAlgError there; KFB_INFO_DARE_FAILED:
+ *    the steady-state covariance (DARE) of this draw did not converge / F_ss not positive definite)
+ *    and the unit's loglik is NaN.
  */
 #ifndef KFB200_H
 #define KFB200_H
@@ -57,6 +58,11 @@ enum {
   KFB_SINGLE = 3,       /* SingleTimeseriesFilter kalman_filter.py:321-351 */
   KFB_CHOLESKY = 4      /* CholeskyFilter         kalman_filter.py:287-318 */
 };
+
+/* info[] codes beyond "t + 1" / "-(t + 1)" (no series is this long) */
+#define KFB_INFO_DARE_FAILED 0x40000001    /* steady_state: Riccati / Newton-Hewer iteration failed for this draw      */
+#define KFB_INFO_NOT_STATIONARY 0x40000002 /* set by the host layer (KalmanLogp): stationary P0 requested but the      */
+                                           /* Lyapunov doubling did not converge (spectral radius of T >= 1)            */
 
 /* flags */
 #define KFB_FLAG_CORRECTED 1u  /* strict_reference=False: fix SURVEY.md A.2 quirks Q1,Q4,Q5,Q6 */

@@ -126,6 +126,7 @@ static void fill_args(const kfb_desc* d, const kfb_inputs* in, const Plan& pl, c
   if (pl.mk == MK_STEADY) {
     A->Pss = {(const double*)(ws + pl.off_Pss), (long long)d->m * d->m, 0};  // one per draw
     A->Gss = {(const double*)(ws + pl.off_Gss), (long long)d->p * d->p, 0};
+    A->dare_info = (const int*)(ws + pl.off_dinfo);
   }
   A->ll_const = pl.ll_const;
   A->d_sign = pl.d_sign;
@@ -364,6 +365,7 @@ kfb_status kfb_scatter_backward_multi(int64_t B, int32_t n_theta, int32_t n_seg,
                                       double* gtheta, void* stream) {
   if (B <= 0 || n_theta <= 0 || !gtheta || !scatter_segs_ok(n_seg, segs, false)) return KFB_ERR_INVALID_ARG;
   cudaError_t e = launch_scatter_backward_multi(B, n_theta, n_seg, segs, gtheta, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;  // mapped elements exceed shared memory
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);
 }
 

@@ -611,7 +611,13 @@ cudaError_t launch_scatter_backward_multi(long long B, int n_theta, int n_seg, c
   }
   const long long total = B * n_theta;
   const unsigned grid = (unsigned)min((total + 255) / 256, (long long)148 * 32);
-  scatter_backward_multi_kernel<<<grid, 256, sum * sizeof(int), s>>>(B, n_theta, gtheta, S);
+  const size_t smem = (size_t)sum * sizeof(int);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // > 58k mapped elements: caller uses the per-matrix kernel
+  if (smem > 48 * 1024) {                                        // e.g. T and P0 of a k_states ~ 80 model mapped
+    cudaError_t e = cudaFuncSetAttribute(scatter_backward_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  scatter_backward_multi_kernel<<<grid, 256, smem, s>>>(B, n_theta, gtheta, S);
   count_launch();
   return cudaGetLastError();
 }

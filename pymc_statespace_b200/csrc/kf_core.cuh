@@ -24,6 +24,7 @@ namespace kfb {
 
 constexpr double KF_LOG_2PI = 1.8378770664093454835606594728112;  // MVN_CONST kalman_filter.py:16
 constexpr double KF_LN2 = 0.69314718055994530941723212145818;
+constexpr int KF_INFO_DARE_FAILED = 0x40000001;  // = KFB_INFO_DARE_FAILED (include/kfb200.h)
 
 enum MathKind : int { MK_STD = 0, MK_UNIV = 1, MK_STEADY = 2, MK_CHOLS = 3 };
 enum SizeClass : int { SZ_M = 0, SZ_P = 1, SZ_MM = 2, SZ_MP = 3, SZ_PP = 4, SZ_TAPE = 5 };
@@ -43,6 +44,7 @@ struct KfArgs {
   // forward outputs (any may be null)
   double *loglik, *ll_obs, *fs, *ps, *fc, *pc;
   int* info;
+  const int* dare_info;  // steady state: per-draw status of the DARE solve (0 = ok) or null
   double* tape;  // predicted (a_t, tri(P_t)) for t = 1..n-1
   // backward
   const double *g_loglik, *g_ll_obs;
@@ -593,6 +595,7 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
     if (!full) ll -= 0.5 * acc.value();
     if (info != 0) ll = nan("");
     if (A.loglik) A.loglik[u] = ll;
+    if (MK == MK_STEADY && A.dare_info && A.dare_info[draw] != 0) info = KF_INFO_DARE_FAILED;
     if (A.info) A.info[u] = info;
   }
 }

@@ -7,7 +7,6 @@
 #include "kf_pred.cuh"
 #include "kf_rows.cuh"
 #include "kf_rowsD.cuh"
-#include "kf_rowsL.cuh"
 #include "kf_smooth.cuh"
 
 namespace kfb {
@@ -158,20 +157,8 @@ __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (N
   else rows_forward<M, P, G, MK>(A, u, sm, l, mask);
 }
 
-// Fused row-per-lane, warp-per-unit programs for large systems (kf_rowsL.cuh).  BWD = adjoint, NEED_T = with T-bar.
-template <int M, int P, bool BWD, bool NEED_T>
-__global__ void __launch_bounds__(128, 1) kf_rowsL_kernel(const __grid_constant__ KfArgs A) {
-  extern __shared__ __align__(16) double kf_dyn_smem[];
-  constexpr int per_unit = BWD ? RowsLLayout<M, P, NEED_T>::bwd_doubles : RowsLLayout<M, P, false>::fwd_doubles;
-  const int warp = threadIdx.x >> 5;
-  const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (u >= A.U) return;
-  double* sm = kf_dyn_smem + (size_t)warp * per_unit;
-  if (BWD) rowsL_backward<M, P, NEED_T>(A, u, sm, threadIdx.x & 31, 0xffffffffu);
-  else rowsL_forward<M, P>(A, u, sm, threadIdx.x & 31, 0xffffffffu);
-}
-
-// Same path with the m^3 products on the FP64 tensor cores (kf_rowsD.cuh); MK = MK_STD or MK_STEADY.
+// Fused row-per-lane, warp-per-unit programs for large systems with the m^3 products on the FP64 tensor cores
+// (kf_rowsD.cuh); MK = MK_STD or MK_STEADY.  BWD = adjoint, NEED_T = with T-bar.
 template <int M, int P, int MK, bool BWD, bool NEED_T>
 __global__ void __launch_bounds__(128, 1) kf_rowsD_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];

@@ -193,6 +193,7 @@ KFB_HD void forward_unit_pred(X& x, const KfArgs& A, long long u) {
     double ll = llsum - 0.5 * acc.value();
     if (info != 0) ll = nan("");
     if (A.loglik) A.loglik[u] = ll;
+    if (MK == MK_STEADY && A.dare_info && A.dare_info[u / A.n_series] != 0) info = KF_INFO_DARE_FAILED;
     if (A.info) A.info[u] = info;
   }
 }

@@ -415,6 +415,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     double ll = llsum - 0.5 * acc.value();
     if (info != 0) ll = nan("");
     if (A.loglik) A.loglik[u] = ll;
+    if (MK == MK_STEADY && A.dare_info && A.dare_info[u / A.n_series] != 0) info = KF_INFO_DARE_FAILED;
     if (A.info) A.info[u] = info;
   }
 }

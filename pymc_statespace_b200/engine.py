@@ -162,6 +162,10 @@ class BatchedKalman:
         if bad.numel():
             u = int(bad[0, 0])
             code = int(info[u])
+            if code == _lib.KFB_INFO_DARE_FAILED:
+                raise KalmanNumericalError(f"unit {u}: the steady-state covariance (DARE) did not converge")
+            if code == _lib.KFB_INFO_NOT_STATIONARY:
+                raise KalmanNumericalError(f"unit {u}: T is not stationary, no stationary initial covariance exists")
             if code > 0:
                 raise KalmanNumericalError(f"unit {u}: innovation covariance F_t not positive definite at step {code - 1}")
             raise KalmanNumericalError(

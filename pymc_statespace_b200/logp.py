@@ -20,7 +20,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from ._lib import KFB_MAX_SCATTER_SEGMENTS, KfbScatterSeg, check, load
+from ._lib import (KFB_ERR_UNSUPPORTED, KFB_INFO_NOT_STATIONARY, KFB_MAX_SCATTER_SEGMENTS, KfbScatterSeg, check, load)
 from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapunov_forward
 from .models import MATRICES, StateSpaceSpec
 
@@ -253,8 +253,21 @@ class KalmanLogp:
     def logp(self, theta) -> torch.Tensor:
         mats = self._scatter(self._check_theta(theta))
         out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",))
-        self.info = out["info"]
+        self._kf_info = out["info"]
         return out["loglik"]
+
+    @property
+    def info(self) -> torch.Tensor:
+        """Per-draw status of the last evaluation (int32, 0 = ok; codes in include/kfb200.h).  A draw whose stationary
+        P0 could not be computed (Lyapunov doubling did not converge: spectral radius of T >= 1 - the reference's
+        bilinear solve returns a finite non-PSD matrix there and carries on, here logp is NaN) is reported as
+        KFB_INFO_NOT_STATIONARY instead of the follow-on "F_0 not positive definite".  Merged lazily: nothing is added
+        to the per-evaluation launch sequence."""
+        info = self._kf_info
+        if self.spec.stationary_initialization and getattr(self, "_lyap", None) is not None:
+            bad = self._lyap[2] != 0
+            info = torch.where(bad, torch.full_like(info, KFB_INFO_NOT_STATIONARY), info)
+        return info
 
     def capture_host_step(self, theta_host: torch.Tensor, out_host: torch.Tensor, chunks: int = 1,
                           sequential: bool = False) -> "HostStepGraph":
@@ -273,7 +286,7 @@ class KalmanLogp:
         sp = self.spec
         mats = self._scatter(theta)
         out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",), save_for_backward=True)
-        self.info = out["info"]
+        self._kf_info = out["info"]
         wrt = [k for k in MATRICES if k in self._maps]
         if sp.stationary_initialization and "P0" not in wrt:
             wrt.append("P0")
@@ -284,15 +297,18 @@ class KalmanLogp:
             lyapunov_backward(A, mats["R"], mats["Q"], X, g["P0"], g.get("T"), g.get("R"), g.get("Q"))
         ks = [k for k in self._maps if not (sp.stationary_initialization and k == "P0")]
         with torch.cuda.device(self.device):
+            status = KFB_ERR_UNSUPPORTED
             if 0 < len(ks) <= KFB_MAX_SCATTER_SEGMENTS:
                 # one launch: gtheta[b, j] = sum over matrices of the cotangents of the elements theta_j was written to
                 gtheta = torch.empty((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
                 segs = (KfbScatterSeg * len(ks))(*[
                     KfbScatterSeg(self._size(k), self._maps[k][2], None, _ptr(self._maps[k][0]), _ptr(self._maps[k][1]),
                                   _ptr(g[k])) for k in ks])
-                check(self.lib.kfb_scatter_backward_multi(self.B, sp.n_theta, len(ks), segs, _ptr(gtheta),
-                                                          _stream_ptr(self.device)), "kfb_scatter_backward_multi")
-            else:
+                status = self.lib.kfb_scatter_backward_multi(self.B, sp.n_theta, len(ks), segs, _ptr(gtheta),
+                                                             _stream_ptr(self.device))
+                if status != KFB_ERR_UNSUPPORTED:  # UNSUPPORTED: the mapped elements do not fit shared memory
+                    check(status, "kfb_scatter_backward_multi")
+            if status == KFB_ERR_UNSUPPORTED:
                 gtheta = torch.zeros((self.B, sp.n_theta), dtype=torch.float64, device=self.device)
                 for k in ks:
                     src, dst, nmap = self._maps[k]

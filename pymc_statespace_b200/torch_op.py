@@ -15,6 +15,12 @@ _OUT = ("filtered_states", "predicted_states", "filtered_covs", "predicted_covs"
 
 
 def _raise_info(info: int):
+    from ._lib import KFB_INFO_DARE_FAILED
+
+    if info == KFB_INFO_DARE_FAILED:
+        raise np.linalg.LinAlgError("the steady-state covariance could not be computed: the discrete algebraic Riccati "
+                                    "equation has no stabilising solution for these matrices (scipy's solve_discrete_are "
+                                    "raises LinAlgError at this point in the reference)")
     if info > 0:
         raise np.linalg.LinAlgError(
             f"innovation covariance F_t is not positive definite at step {info - 1} "

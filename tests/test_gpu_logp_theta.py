@@ -366,3 +366,35 @@ def test_scatter_multi_matches_numpy_and_single_calls():
                 ref[:, a] += g[:, b]
     assert np.allclose(gth.cpu().numpy(), ref, rtol=0, atol=1e-15)
     assert lib.kfb_scatter_forward_multi(B, nt, 9, arr, th.data_ptr(), stream) != 0  # more than KFB_MAX_SCATTER_SEGMENTS
+
+
+@pytest.mark.gpu
+def test_status_codes_for_non_stationary_draws_and_failed_dare():
+    """the real cause of a failed draw is reported, not the follow-on "F_0 not positive definite".
+    (a) stationary P0 requested for a draw with |rho| >= 1: KFB_INFO_NOT_STATIONARY, logp NaN, other draws untouched;
+    (b) steady_state filter whose Riccati equation has no stabilising solution: KFB_INFO_DARE_FAILED."""
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KFB_INFO_DARE_FAILED, KFB_INFO_NOT_STATIONARY
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.synthetic import arma11_workload
+
+    spec, y, theta = arma11_workload(64, 40)
+    theta[5, 3] = 1.2   # rho: explosive AR root
+    theta[9, 3] = 1.0   # unit root
+    model = KalmanLogp(spec, y, n_draws=64)
+    logp, grad = model.logp_and_grad(torch.as_tensor(theta, device="cuda"))
+    info = model.info.cpu().numpy()
+    assert info[5] == KFB_INFO_NOT_STATIONARY and info[9] == KFB_INFO_NOT_STATIONARY
+    assert (np.delete(info, [5, 9]) == 0).all() and bool(torch.isnan(logp[[5, 9]]).all())
+    assert bool(torch.isfinite(torch.cat([logp[:5], logp[10:]])).all())
+    # (b) unobservable explosive state: no stabilising DARE solution
+    n, dev = 20, "cuda"
+    f = lambda a: torch.as_tensor(np.asarray(a, dtype=float), device=dev)  # noqa: E731
+    bk = BatchedKalman("steady_state", n, 2, 1, 1, n_draws=2)
+    T = np.stack([np.array([[0.5, 0.0], [0.0, 0.3]]), np.array([[0.5, 0.0], [0.0, 1.5]])])
+    out = bk.forward(f(np.zeros((n, 1))), f(np.zeros(2)), f(np.eye(2)), f(T), f([[1.0, 0.0]]), f([[1.0], [1.0]]),
+                     f([[1.0]]), f([[1.0]]))
+    info = out["info"].cpu().numpy()
+    assert info[0] == 0 and info[1] == KFB_INFO_DARE_FAILED and bool(torch.isnan(out["loglik"][1]))
+    with pytest.raises(Exception, match="DARE"):
+        bk.raise_on_info(out["info"])
