@@ -12,10 +12,10 @@ static std::atomic<long long> g_launches{0};
 static thread_local const char* g_cuda_err = "";
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-thread_launch_fn thread_launcher_m1(int p, int mk);
-thread_launch_fn thread_launcher_m2(int p, int mk);
-thread_launch_fn thread_launcher_m3(int p, int mk);
-thread_launch_fn thread_launcher_m4(int p, int mk);
+thread_launch_fn thread_launcher_m1(int p, int mk, bool tv);
+thread_launch_fn thread_launcher_m2(int p, int mk, bool tv);
+thread_launch_fn thread_launcher_m3(int p, int mk, bool tv);
+thread_launch_fn thread_launcher_m4(int p, int mk, bool tv);
 
 bool p1_adjoint_supported(int m, int p, int mk);
 cudaError_t launch_p1_adjoint(const KfArgs& A, int y_smem_doubles, int bulk_ok, cudaStream_t s);
@@ -38,12 +38,12 @@ coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
   }
 }
 
-thread_launch_fn find_thread_launcher(int m, int p, int mk) {
+thread_launch_fn find_thread_launcher(int m, int p, int mk, bool tv) {
   switch (m) {
-    case 1: return thread_launcher_m1(p, mk);
-    case 2: return thread_launcher_m2(p, mk);
-    case 3: return thread_launcher_m3(p, mk);
-    case 4: return thread_launcher_m4(p, mk);
+    case 1: return thread_launcher_m1(p, mk, tv);
+    case 2: return thread_launcher_m2(p, mk, tv);
+    case 3: return thread_launcher_m3(p, mk, tv);
+    case 4: return thread_launcher_m4(p, mk, tv);
     default: return nullptr;
   }
 }
@@ -86,8 +86,7 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
   const bool C_batched = d->R_bs || d->Q_bs;
   const long long nDC = C_batched ? d->n_draws : 1;
   pl->C_bs = C_batched ? (long long)pl->nTC * d->m * d->m : 0;
-  pl->use_thread =
-      !pl->tv_any && !(d->flags & KFB_FLAG_FORCE_COOP) && find_thread_launcher(d->m, d->p, pl->mk) != nullptr;
+  pl->use_thread = !(d->flags & KFB_FLAG_FORCE_COOP) && find_thread_launcher(d->m, d->p, pl->mk, pl->tv_any) != nullptr;
   size_t off = 0;
   auto take = [&](size_t doubles) { size_t o = off; off += ((doubles * 8 + 255) / 256) * 256; return o; };
   pl->off_C = take((size_t)nDC * pl->nTC * d->m * d->m);
@@ -148,7 +147,7 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
       bulk_ok = ((uintptr_t)A.y.p % 16 == 0) ? 1 : 0;
     }
     // k_endog = 1, shared observations: the specialised adjoint with the TMA tape ring (kf_p1.cu)
-    const bool p1_ok = d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
+    const bool p1_ok = !pl.tv_any && d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
                        p1_adjoint_supported(d->m, d->p, pl.mk);
     const bool full = A.ll_obs || A.fs || A.ps || A.fc || A.pc;
     if (p1_ok && bwd)
@@ -156,7 +155,7 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
     else if (p1_ok && !full)
       e = launch_p1_forward(A, ysm, bulk_ok, s);
     else
-      e = find_thread_launcher(d->m, d->p, pl.mk)(A, bwd, ysm, bulk_ok, s);
+      e = find_thread_launcher(d->m, d->p, pl.mk, pl.tv_any)(A, bwd, ysm, bulk_ok, s);
   } else {
     // sub-warp kernels with compile-time dims need uniform control flow across the units of a warp:
     // static matrices and ONE observation stream shared by every unit

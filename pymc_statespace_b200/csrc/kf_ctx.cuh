@@ -18,9 +18,11 @@ struct RegBuf {
   KFB_HD const double& operator[](int i) const { return v[i]; }
 };
 
-template <int M, int P>
+// TV_ = true: time-varying matrices (3-D time-first inputs, reference filters/utilities.py:1-20) - the step programs
+// reload the varying matrices from global memory every step; everything else is identical.
+template <int M, int P, bool TV_ = false>
 struct ThreadCtx {
-  static constexpr bool TV = false;
+  static constexpr bool TV = TV_;
   static constexpr bool PIPELINE = false;  // adjoint: overlap gain(t-1) with adjoint(t)
   static constexpr bool SKIP_LB = false;   // adjoint without T-bar / Z-bar: keep the single code path (a run-time branch cost the m = 2 kernel 14 %)
   template <int SZ>

@@ -67,7 +67,7 @@ __device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
 
 // 65,536 units (the headline batch) need 443 resident threads per SM for a single wave: the pipelined adjoint of the
 // k_states <= 2 kernels is capped at 7 CTAs x 64 threads per SM (<= 144 registers) instead of spilling into a 2nd wave.
-template <int M, int P, int MK, int MODE>
+template <int M, int P, int MK, int MODE, bool TV = false>
 __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     kf_thread_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
   if (u >= A.U) return;
   // the adjoint kernel's tape ring lives behind the staged observations (16-byte aligned)
   double* ring = kf_dyn_smem + ((y_smem_doubles + 1) & ~1);
-  ThreadCtx<M, P> x{ysm, ring, (int)threadIdx.x, (int)blockDim.x};
+  ThreadCtx<M, P, TV> x{ysm, ring, (int)threadIdx.x, (int)blockDim.x};
   run_unit<MK, MODE>(x, A, u);
 }
 
@@ -251,7 +251,7 @@ cudaError_t launch_smoother(const SmoothArgs& S, cudaStream_t s);
 
 // launchers implemented in kf_thread_m*.cu / kf_coop.cu
 typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);
-thread_launch_fn find_thread_launcher(int m, int p, int mk);
+thread_launch_fn find_thread_launcher(int m, int p, int mk, bool tv = false);
 cudaError_t launch_coop(const KfArgs& A, bool bwd, cudaStream_t s);
 typedef cudaError_t (*coopT_launch_fn)(const KfArgs& A, bool bwd, cudaStream_t s);
 coopT_launch_fn find_coopT_launcher(int m, int p, int mk);

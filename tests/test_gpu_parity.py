@@ -139,10 +139,19 @@ def test_time_varying_matrices():
     y, a0, P0 = sys_t[0][:3]
     T, Z, R, H, Q = (np.stack([s[i] for s in sys_t]) for i in range(3, 8))
     c, d = rng.normal(size=(n, m, 1)), rng.normal(size=(n, p, 1))
-    check_against_oracle("standard", (y, a0, P0, T, Z, R, H, Q), c, d, time_varying=("T", "Z", "R", "H", "Q", "c", "d"))
-    # only some matrices time varying
-    check_against_oracle("standard", (y, a0, P0, T, sys_t[0][4], sys_t[0][5], H, sys_t[0][7]),
-                         time_varying=("T", "H"))
+    for force_coop in (False, True):  # thread-per-unit kernels with per-step reloads (ThreadCtx<M,P,true>) / generic cooperative
+        check_against_oracle("standard", (y, a0, P0, T, Z, R, H, Q), c, d, force_coop=force_coop,
+                             time_varying=("T", "Z", "R", "H", "Q", "c", "d"))
+        # only some matrices time varying
+        check_against_oracle("standard", (y, a0, P0, T, sys_t[0][4], sys_t[0][5], H, sys_t[0][7]), force_coop=force_coop,
+                             time_varying=("T", "H"))
+    # k_endog = 1 (the specialised static kernels must NOT be picked) with missing rows and a per-step ll cotangent
+    n, m, p, r = 15, 2, 1, 1
+    sys_t = [random_system(rng, m, p, r, n, n_missing=2) for _ in range(n)]
+    y, a0, P0 = sys_t[0][:3]
+    T, Q = (np.stack([s[i] for s in sys_t]) for i in (3, 7))
+    check_against_oracle("standard", (y, a0, P0, T, sys_t[0][4], sys_t[0][5], sys_t[0][6], Q), time_varying=("T", "Q"),
+                         g_ll_obs=rng.normal(size=n))
 
 
 @pytest.mark.parametrize("p,m,r,n", [(1, 1, 1, 10), (1, 2, 2, 10), (1, 5, 2, 10), (1, 5, 1, 10), (5, 5, 1, 10)])
