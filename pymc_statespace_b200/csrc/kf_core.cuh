@@ -291,6 +291,24 @@ KFB_HD void chols_adjoint(const TG& Gb, const TL& L, const TL& Li, const TG& Gk,
     for (int j = 0; j < p; ++j) Fb[i * p + j] = 0.5 * (W2[i * p + j] + W2[j * p + i]);
 }
 
+// Per-step outputs of the full-output forward pass (the reference's moments and ll_obs, kalman_filter.py:184-191).
+// Row r of output array `arr` of unit u lives at base[(u * rows + r) * w .. + w).
+enum OutArr : int { O_FS = 0, O_PS = 1, O_FC = 2, O_PC = 3, O_LL = 4 };
+
+KFB_HD double* out_base(const KfArgs& A, int arr) {
+  return arr == O_FS ? A.fs : arr == O_PS ? A.ps : arr == O_FC ? A.fc : arr == O_PC ? A.pc : A.ll_obs;
+}
+
+// Default (cooperative contexts, host): the lanes of a unit store the row directly - consecutive lanes, consecutive
+// doubles.  ThreadCtx overrides this with a shared-memory stager (kf_ctx.cuh): one unit per thread would otherwise
+// scatter every 8-byte store into its own sector.
+template <class X, class TS>
+KFB_HD void store_row_direct(X& x, const KfArgs& A, int arr, long long u, long long rows, long long r, int w, const TS& src) {
+  double* base = out_base(A, arr);
+  if (!base) return;
+  KFB_FOR(i, w) base[(u * rows + r) * w + i] = src[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-unit constant parameters + scratch, allocated from the context (registers or shared memory)
 // ------------------------------------------------------------------------------------------------
@@ -575,12 +593,20 @@ KFB_HD void forward_unit(X& x, const KfArgs& A, long long u) {
       }
     }
     llsum += ll_t;
-    if (full && lane0) A.ll_obs[u * n + t] = ll_t;
-    if (FULL && A.fs) KFB_FOR(i, m) A.fs[(u * n + t) * m + i] = af[i];
-    if (FULL && A.fc) KFB_FOR(i, m * m) A.fc[(u * n + t) * m * m + i] = Pf[i];
+    if (FULL) {
+      if (full) {
+        const double llv[1] = {ll_t};
+        x.store_row(A, O_LL, u, n, t, 1, llv);
+      }
+      x.store_row(A, O_FS, u, n, t, m, af);
+      x.store_row(A, O_FC, u, n, t, m * m, Pf);
+    }
     predict(x, prm.T, C, c, af, Pf, a, P, tmp.S1, tmp.S2);
-    if (FULL && A.ps) KFB_FOR(i, m) A.ps[(u * (n + 1) + t + 1) * m + i] = a[i];
-    if (FULL && A.pc) KFB_FOR(i, m * m) A.pc[(u * (n + 1) + t + 1) * m * m + i] = P[i];
+    if (FULL) {
+      x.store_row(A, O_PS, u, n + 1, t + 1, m, a);
+      x.store_row(A, O_PC, u, n + 1, t + 1, m * m, P);
+      x.end_step(A, u, t, n);
+    }
     if (tp && t + 1 < n) {
       KFB_FOR(k, m) tp[k * telem] = a[k];
       KFB_FOR(idx, m * m) {

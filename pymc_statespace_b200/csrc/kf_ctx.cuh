@@ -30,6 +30,83 @@ struct ThreadCtx {
   const double* y_smem;  // observations staged in shared memory (shared y) or nullptr
   double* ring;          // shared-memory ring for the adjoint kernel's tape read-ahead (device only)
   int tid, nthr;
+  // ---- full-output forward pass: per-warp shared-memory stager (device only; nullptr = direct stores)
+  // A thread owns a unit, and the outputs are unit-major ([U, n, w]), so a direct store puts every lane's 8 bytes into
+  // its own 32-byte sector (measured: 0.65 TB/s, 10 % of the HBM copy rate at k_states = 2).  Instead the rows of
+  // OUT_K consecutive steps are staged in shared memory as [step][element][lane] (row stride 33: conflict-free writes,
+  // 2-way reads) and flushed by the whole warp unit by unit: the OUT_K * w doubles of one unit and one output array
+  // are contiguous in global memory, so the warp writes them as 32..128-byte runs of whole sectors.
+  double* ostage = nullptr;
+  long long warp_u0 = 0;  // first unit of this thread's warp
+  static constexpr int OUT_W = 2 * M + 2 * M * M + 1;            // doubles per unit and step (fs, ps, fc, pc, ll)
+  static constexpr int OUT_K = 4;                                // steps per flush (k_states 2: 13.7 KB per warp)
+  static constexpr int OUT_LD = 33;
+  static constexpr int OUT_DOUBLES = OUT_K * OUT_W * OUT_LD;     // per warp
+  KFB_HD static constexpr int out_off(int arr) {
+    return arr == O_FS ? 0 : arr == O_PS ? M : arr == O_FC ? 2 * M : arr == O_PC ? 2 * M + M * M : 2 * M + 2 * M * M;
+  }
+  KFB_HD static constexpr int out_width(int arr) { return arr == O_FS || arr == O_PS ? M : arr == O_LL ? 1 : M * M; }
+  template <class TS>
+  KFB_HD void store_row(const KfArgs& A, int arr, long long u, long long rows, long long r, int w, const TS& src) {
+#if defined(__CUDA_ARCH__)
+    if (ostage) {
+      // ps / pc rows are shifted by one (row 0 = a0 / P0 is written before the loop): slot by step, not by row
+      const int slot = (int)((arr == O_PS || arr == O_PC ? r - 1 : r) % OUT_K);
+      double* dst = ostage + (size_t)(slot * OUT_W + out_off(arr)) * OUT_LD + (tid & 31);
+#pragma unroll
+      for (int i = 0; i < (M * M > 1 ? M * M : 1); ++i)
+        if (i < w) dst[i * OUT_LD] = src[i];
+      return;
+    }
+#endif
+    store_row_direct(*this, A, arr, u, rows, r, w, src);
+  }
+  // flush `count` staged steps (rows t0 .. t0 + count - 1) of one output array; COUNT > 0: compile-time count
+  template <int ARR, int COUNT>
+  KFB_HD void flush_arr(const KfArgs& A, int count, int t0, int n, int lane) {
+#if defined(__CUDA_ARCH__)
+    double* base = out_base(A, ARR);
+    if (!base) return;
+    constexpr int w = out_width(ARR), off = out_off(ARR);
+    const long long rows = (ARR == O_PS || ARR == O_PC) ? n + 1 : n;
+    const long long r0 = (ARR == O_PS || ARR == O_PC) ? t0 + 1 : t0;
+    const int Lc = (COUNT > 0 ? COUNT : count) * w;  // contiguous doubles per unit
+#pragma unroll
+    for (int it = 0; it < (COUNT > 0 ? COUNT * w : OUT_K * w); ++it) {
+      if (COUNT == 0 && it >= Lc) break;
+      const int idx = it * 32 + lane;
+      const int unit = idx / Lc, e = idx - unit * Lc;
+      const int sidx = e / w, i = e - sidx * w;
+      if (warp_u0 + unit < A.U)
+        base[((warp_u0 + unit) * rows + r0) * w + e] = ostage[(size_t)(sidx * OUT_W + off + i) * OUT_LD + unit];
+    }
+#endif
+  }
+  // called by every lane of the warp at the end of step t
+  KFB_HD void end_step(const KfArgs& A, long long, int t, int n) {
+#if defined(__CUDA_ARCH__)
+    if (!ostage) return;
+    const int slot = t % OUT_K;
+    if (slot != OUT_K - 1 && t != n - 1) return;
+    const int count = slot + 1, t0 = t - slot, lane = tid & 31;
+    __syncwarp();
+    if (count == OUT_K) {
+      flush_arr<O_FS, OUT_K>(A, count, t0, n, lane);
+      flush_arr<O_PS, OUT_K>(A, count, t0, n, lane);
+      flush_arr<O_FC, OUT_K>(A, count, t0, n, lane);
+      flush_arr<O_PC, OUT_K>(A, count, t0, n, lane);
+      flush_arr<O_LL, OUT_K>(A, count, t0, n, lane);
+    } else {
+      flush_arr<O_FS, 0>(A, count, t0, n, lane);
+      flush_arr<O_PS, 0>(A, count, t0, n, lane);
+      flush_arr<O_FC, 0>(A, count, t0, n, lane);
+      flush_arr<O_PC, 0>(A, count, t0, n, lane);
+      flush_arr<O_LL, 0>(A, count, t0, n, lane);
+    }
+    __syncwarp();
+#endif
+  }
+
   static constexpr int KT = M + (M * (M + 1)) / 2;
   static constexpr int TAPE_DEPTH = 4;              // entries in flight
   static constexpr int TAPE_SLOTS = TAPE_DEPTH + 1;  // +1: the slot being refilled was consumed one step earlier
@@ -181,6 +258,11 @@ struct CoopCtx {
     return v;
 #endif
   }
+  template <class TS>
+  KFB_HD void store_row(const KfArgs& A, int arr, long long u, long long rows, long long r, int w, const TS& src) {
+    store_row_direct(*this, A, arr, u, rows, r, w, src);
+  }
+  KFB_HD void end_step(const KfArgs&, long long, int, int) {}
   KFB_HD const double* y_base(const KfArgs& A, long long series) const { return A.y.p + series * A.y.bs; }
   KFB_HD double* tape_base(const KfArgs& A, long long u) const {
     return A.tape + u * (long long)(A.n - 1) * tape_width(m_);
@@ -313,6 +395,11 @@ struct CoopCtxT {
     return v;
 #endif
   }
+  template <class TS>
+  KFB_HD void store_row(const KfArgs& A, int arr, long long u, long long rows, long long r, int w, const TS& src) {
+    store_row_direct(*this, A, arr, u, rows, r, w, src);
+  }
+  KFB_HD void end_step(const KfArgs&, long long, int, int) {}
   KFB_HD const double* y_base(const KfArgs& A, long long series) const { return A.y.p + series * A.y.bs; }
   KFB_HD double* tape_base(const KfArgs& A, long long u) const { return A.tape + u * (long long)(A.n - 1) * KT; }
   KFB_HD long long tape_step(const KfArgs&) const { return KT; }

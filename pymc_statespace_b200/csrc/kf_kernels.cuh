@@ -65,6 +65,12 @@ __device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
   }
 }
 
+// a padding lane of the last warp in the full-output kernel: same program on the last unit's inputs
+template <int MK, int MODE, class X>
+__device__ __forceinline__ void run_unit_padded(X& x, const KfArgs& B, long long u_last) {
+  run_unit<MK, MODE>(x, B, u_last);
+}
+
 // 65,536 units (the headline batch) need 443 resident threads per SM for a single wave: the pipelined adjoint of the
 // k_states <= 2 kernels is capped at 7 CTAs x 64 threads per SM (<= 144 registers) instead of spilling into a 2nd wave.
 template <int M, int P, int MK, int MODE, bool TV = false>
@@ -76,11 +82,27 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
     ysm = kf_dyn_smem;
   }
-  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= A.U) return;
-  // the adjoint kernel's tape ring lives behind the staged observations (16-byte aligned)
+  long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // the adjoint kernel's tape ring / the full-output stager live behind the staged observations (16-byte aligned)
   double* ring = kf_dyn_smem + ((y_smem_doubles + 1) & ~1);
   ThreadCtx<M, P, TV> x{ysm, ring, (int)threadIdx.x, (int)blockDim.x};
+  if (MODE == 1) {
+    // outputs go through the per-warp stager; the padding lanes of the last warp run along (on the last unit's
+    // parameters) because the flush at the end of every OUT_K-th step is warp-collective
+    const long long u0 = u - (threadIdx.x & 31);
+    if (u0 >= A.U) return;
+    x.ostage = ring + (size_t)(threadIdx.x >> 5) * ThreadCtx<M, P, TV>::OUT_DOUBLES;
+    x.warp_u0 = u0;
+    if (u >= A.U) {
+      KfArgs B = A;  // padding lane: compute, store nothing of its own
+      B.loglik = nullptr; B.info = nullptr; B.tape = nullptr;
+      run_unit_padded<MK, MODE>(x, B, A.U - 1);
+      return;
+    }
+    run_unit<MK, MODE>(x, A, u);
+    return;
+  }
+  if (u >= A.U) return;
   run_unit<MK, MODE>(x, A, u);
 }
 
