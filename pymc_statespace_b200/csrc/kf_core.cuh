@@ -25,6 +25,7 @@ namespace kfb {
 constexpr double KF_LOG_2PI = 1.8378770664093454835606594728112;  // MVN_CONST kalman_filter.py:16
 constexpr double KF_LN2 = 0.69314718055994530941723212145818;
 constexpr int KF_INFO_DARE_FAILED = 0x40000001;  // = KFB_INFO_DARE_FAILED (include/kfb200.h)
+constexpr int KF_INFO_BAD_STRUCTURE = 0x40000003;  // = KFB_INFO_BAD_STRUCTURE: a KFB_FLAG_Z_UNIT0 / KFB_FLAG_H_ZERO promise is false
 
 enum MathKind : int { MK_STD = 0, MK_UNIV = 1, MK_STEADY = 2, MK_CHOLS = 3 };
 enum SizeClass : int { SZ_M = 0, SZ_P = 1, SZ_MM = 2, SZ_MP = 3, SZ_PP = 4, SZ_TAPE = 5 };
@@ -45,6 +46,7 @@ struct KfArgs {
   double *loglik, *ll_obs, *fs, *ps, *fc, *pc;
   int* info;
   const int* dare_info;  // steady state: per-draw status of the DARE solve (0 = ok) or null
+  int struct_flags;      // bit 0: Z = [1, 0, .., 0] (k_endog = 1); bit 1: H = 0   (caller's promises, kfb200.h flags)
   double* tape;  // predicted (a_t, tri(P_t)) for t = 1..n-1
   // backward
   const double *g_loglik, *g_ll_obs;

@@ -14,7 +14,8 @@ from typing import Dict, Iterable, Optional
 import torch
 
 from . import _lib
-from ._lib import (FILTER_KIND, KFB_FLAG_CORRECTED, KFB_FLAG_FORCE_COOP, KFB_FLAG_GENERIC_ADJOINT, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
+from ._lib import (FILTER_KIND, KFB_FLAG_CORRECTED, KFB_FLAG_FORCE_COOP, KFB_FLAG_GENERIC_ADJOINT, KFB_FLAG_H_ZERO,
+                   KFB_FLAG_Z_UNIT0, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
                    KfbOutputs, check, load)
 
 MATRIX_NAMES = ("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d")
@@ -47,7 +48,7 @@ class BatchedKalman:
 
     def __init__(self, kind: str, n: int, m: int, p: int, r: int, n_draws: int, n_series: int = 1,
                  strict_reference: bool = True, time_varying: Iterable[str] = (), device="cuda",
-                 force_coop: bool = False, generic_adjoint: bool = False):
+                 force_coop: bool = False, generic_adjoint: bool = False, z_unit0: bool = False, h_zero: bool = False):
         kind = kind.lower()
         if kind not in FILTER_KIND:
             raise NotImplementedError("The following are valid filter types: " + ", ".join(FILTER_KIND))
@@ -61,7 +62,9 @@ class BatchedKalman:
         if self.device.type != "cuda":
             raise RuntimeError("pymc_statespace_b200 runs on CUDA devices only (no CPU fallback)")
         self.flags = ((0 if strict_reference else KFB_FLAG_CORRECTED) | (KFB_FLAG_FORCE_COOP if force_coop else 0)
-                      | (KFB_FLAG_GENERIC_ADJOINT if generic_adjoint else 0))  # the last two: testing / A-B timing only
+                      | (KFB_FLAG_GENERIC_ADJOINT if generic_adjoint else 0)  # the last two: testing / A-B timing only
+                      # structure promises (k_endog = 1): Z = [1, 0, ..], H = 0 - verified per unit by the forward kernel
+                      | (KFB_FLAG_Z_UNIT0 if z_unit0 else 0) | (KFB_FLAG_H_ZERO if (h_zero and z_unit0) else 0))
         self._base = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (p, m), "R": (m, r), "H": (p, p), "Q": (r, r),
                       "c": (m,), "d": (p,)}
         self._desc = None
@@ -162,6 +165,8 @@ class BatchedKalman:
         if bad.numel():
             u = int(bad[0, 0])
             code = int(info[u])
+            if code == _lib.KFB_INFO_BAD_STRUCTURE:
+                raise KalmanNumericalError(f"unit {u}: z_unit0 / h_zero was promised but Z != [1, 0, ..] or H != 0")
             if code == _lib.KFB_INFO_DARE_FAILED:
                 raise KalmanNumericalError(f"unit {u}: the steady-state covariance (DARE) did not converge")
             if code == _lib.KFB_INFO_NOT_STATIONARY:

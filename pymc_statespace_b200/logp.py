@@ -184,8 +184,13 @@ class KalmanLogp:
             raise ValueError('Cannot use filter_type = "single" with multiple observed time series')
         self.B = int(n_draws)
         self.y = torch.as_tensor(y, dtype=torch.float64, device=self.device).contiguous()
+        # structure the model guarantees for every draw: constant (unmapped) design row [1, 0, ..] / zero observation variance
+        z_unit0 = (p == 1 and not spec.maps.get("Z") and np.array_equal(
+            np.asarray(spec.base["Z"], dtype=np.float64).ravel(), np.eye(spec.k_states)[0]))
+        h_zero = p == 1 and not spec.maps.get("H") and not np.any(np.asarray(spec.base["H"]))
         self.kalman = BatchedKalman(filter_type, self.n, spec.k_states, spec.k_endog, spec.k_posdef, n_draws=self.B,
-                                    strict_reference=strict_reference, device=device, force_coop=force_coop)
+                                    strict_reference=strict_reference, device=device, force_coop=force_coop,
+                                    z_unit0=z_unit0, h_zero=h_zero)
         m, pp, r = spec.k_states, spec.k_endog, spec.k_posdef
         self._shape = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (pp, m), "R": (m, r), "H": (pp, pp), "Q": (r, r),
                        "c": (m,), "d": (pp,)}

@@ -579,3 +579,51 @@ def test_non_symmetric_P0_multivariate(dims):
         out = bk.forward(_dev(y[..., 0]), rep(a0[:, 0]), rep(P0), rep(T), _dev(Z), rep(R), _dev(H), rep(Q))
         ll = out["loglik"].cpu().numpy()
         assert int((out["info"] != 0).sum()) == 0 and np.abs(ll - ref[4]).max() < 1e-10 * abs(ref[4])
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_p1_structure_flags_on_device(m):
+    """KFB_FLAG_Z_UNIT0 / KFB_FLAG_H_ZERO (Z = [1, 0, ..], H = 0 promised by the caller): identical loglik and cotangents
+    to the unflagged k_endog = 1 kernels on every unit, oracle parity on a few, and a false promise is reported per unit."""
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KFB_INFO_BAD_STRUCTURE
+
+    rng = np.random.default_rng(70 + m)
+    B, n, r = 45, 33, min(m, 2)
+    systems = [list(random_system(rng, m, 1, r, n)) for _ in range(B)]
+    y = random_system(rng, m, 1, r, n, n_missing=3)[0]
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    Z = np.eye(m)[:1]
+    w = rng.normal(size=(B, n))
+    for h_zero in (False, True):
+        H = np.zeros((1, 1)) if h_zero else np.array([[0.7]])
+        for gobs in (None, w):
+            res = {}
+            for flagged in (False, True):
+                bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=flagged, h_zero=flagged and h_zero)
+                out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), stack(3), _dev(Z), stack(5), _dev(H), stack(7),
+                                 outputs=("loglik",), save_for_backward=True)
+                g = bk.backward(g_loglik=None if gobs is None else _dev(np.full(B, 0.5)),
+                                g_ll_obs=None if gobs is None else _dev(gobs), wrt=("a0", "P0", "T", "R", "Q"))
+                assert int((out["info"] != 0).sum()) == 0
+                res[flagged] = {k: v.cpu().numpy() for k, v in g.items()}
+                res[flagged]["loglik"] = out["loglik"].cpu().numpy()
+            for k in res[True]:
+                scale = np.abs(res[False][k]).max()
+                assert np.abs(res[True][k] - res[False][k]).max() / scale < 1e-13, (k, h_zero)
+            for b in (0, 44):
+                args = (y, systems[b][1], systems[b][2], systems[b][3], Z, systems[b][5], H, systems[b][7])
+                ll_ref, gref = kt.loglik_and_grads("standard", *args, g_ll_obs=None if gobs is None else 0.5 + gobs[b])
+                if gobs is None:
+                    assert abs(res[True]["loglik"][b] - ll_ref) < RTOL * abs(ll_ref)
+                for k in ("a0", "P0", "T", "R", "Q"):
+                    got = res[True][k][b].reshape(gref[k].shape)
+                    scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+                    assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b, h_zero)
+    # false promises: unit 3 has another design row / a non-zero observation variance
+    Zb = np.repeat(Z[None], B, 0)
+    Zb[3, 0, 0] = 0.9
+    bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True)
+    out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), stack(3), _dev(Zb), stack(5), _dev(np.array([[0.7]])), stack(7))
+    info = out["info"].cpu().numpy()
+    assert info[3] == KFB_INFO_BAD_STRUCTURE and (np.delete(info, 3) == 0).all() and bool(torch.isnan(out["loglik"][3]))

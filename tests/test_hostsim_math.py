@@ -262,3 +262,39 @@ def test_non_symmetric_P0_multivariate_matches_reference_triangle_use(static):
                 if not pred:
                     for a, b in zip(outs[:4], ref[:4]):
                         assert rel_err(a, b) < 1e-11
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_p1_structure_flags_give_identical_values(m):
+    """KFB_FLAG_Z_UNIT0 / KFB_FLAG_H_ZERO: with Z = [1, 0, ..] (and H = 0) promised, the products with the known ones and
+    zeros are not issued.  Values and cotangents must equal the unflagged kernels' (same operations on the remaining
+    terms) and the oracle's; a false promise is reported, not silently used."""
+    rng = np.random.default_rng(300 + m)
+    for h_zero in (False, True):
+        for n, n_missing in ((25, 3), (2, 0), (1, 0)):
+            args = list(random_system(rng, m, 1, min(m, 2), n, n_missing=n_missing))
+            args[4] = np.eye(m)[:1].copy()                       # Z = e_0
+            if h_zero:
+                args[6] = np.zeros((1, 1))
+            args[2] = args[2] + 0.05 * rng.normal(size=(m, m))   # non-symmetric P0 (t = 0 runs the literal adjoint)
+            c, d = rng.normal(size=(m, 1)), rng.normal(size=(1, 1))
+            for w in (None, rng.normal(size=n)):
+                kw = dict(c=c, d=d, static_dims=True, full=False, pred=True, p1=True, g_ll_obs=w,
+                          g_loglik=(0.0 if w is not None else None), skip=("Z", "H"))
+                o0, g0, i0 = hostsim.run("standard", *args, **kw)
+                o1, g1, i1 = hostsim.run("standard", *args, z_unit0=True, h_zero=h_zero, **kw)
+                assert i0 == 0 and i1 == 0 and abs(o1[4] - o0[4]) <= 1e-14 * abs(o0[4])
+                _, gt = kt.loglik_and_grads("standard", *args, c=c, d=d, g_ll_obs=w)
+                for k in gt:
+                    if k in ("Z", "H"):
+                        continue
+                    assert rel_err(g1[k], g0[k]) < 1e-13 or np.abs(g1[k] - g0[k]).max() < 1e-14, (k, n, h_zero)
+                    assert rel_err(g1[k], gt[k]) < 1e-9 or np.abs(g1[k] - gt[k]).max() < 1e-13, (k, n, h_zero)
+    # a false promise: Z is not the unit vector / H is not zero
+    args = list(random_system(rng, m, 1, 1, 6))
+    _, _, info = hostsim.run("standard", *args, static_dims=True, full=False, pred=True, p1=True, z_unit0=True, do_bwd=False)
+    assert info == 0x40000003
+    args[4] = np.eye(m)[:1].copy()
+    _, _, info = hostsim.run("standard", *args, static_dims=True, full=False, pred=True, p1=True, z_unit0=True, h_zero=True,
+                             do_bwd=False)
+    assert info == 0x40000003

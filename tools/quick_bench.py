@@ -28,7 +28,8 @@ def main():
     y, a0, P0, T, Z, R, H, Q = map(dev, arma11(B, n))
     print("fp64 peak TFLOP/s:", fp64_peak_tflops())
     for force, gen in ((False, False), (False, True)) + (((True, False),) if B <= 16384 else ()):
-        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen)
+        st = os.environ.get('KFB_STRUCT', '1') == '1' and not gen and not force   # ARMA: Z = [1, 0], H = 0
+        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen, z_unit0=st, h_zero=st)
         for it in range(5):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
@@ -43,7 +44,7 @@ def main():
             bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=False)
             e[1].record(); torch.cuda.synchronize()
         print(f"   forward without tape: {e[0].elapsed_time(e[1]):.3f} ms")
-        print(f"coop={force} generic_adjoint={gen} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
+        print(f"coop={force} generic_adjoint={gen} struct={st} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
               f"ll[0]={float(out['loglik'][0]):.6f} gT[0]={g['T'][0].flatten().tolist()} info!=0: {int((out['info']!=0).sum())}")
         if force and B > 16384: break
 main()
