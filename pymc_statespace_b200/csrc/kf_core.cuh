@@ -212,32 +212,67 @@ KFB_HD bool lu_pivots(const TF& F, TW& W, TP& piv, int p) {
 
 // Cholesky F = L L^T (lower, full storage) and Li = L^-1, serial (one lane).  Used only by the as-coded
 // CholeskyFilter for k_endog > 1 (MK_CHOLS).  logdet <- log det F.
-template <class TF, class TL>
-KFB_HD bool chol_factor(const TF& F, TL& L, TL& Li, int p, double* logdet) {
+// chol_factor with the squared pivots returned instead of their logarithms (deferred-log accumulation in the fused kernels)
+template <class TF, class TL, class TP>
+KFB_HD bool chol_factor_piv(const TF& F, TL& L, TL& Li, TP& piv, int p) {
   bool ok = true;
-  double ld = 0.0;
-  for (int j = 0; j < p; ++j) {
+  _Pragma("unroll") for (int j = 0; j < p; ++j) {
     double dj = F[j * p + j];
-    for (int k = 0; k < j; ++k) dj -= L[j * p + k] * L[j * p + k];
+    _Pragma("unroll") for (int k = 0; k < p; ++k)
+      if (k < j) dj -= L[j * p + k] * L[j * p + k];
     ok = ok && (dj > 0.0) && (dj < 1.0e300);
+    piv[j] = dj;
     const double lj = sqrt(dj);
-    ld += log(dj);
     L[j * p + j] = lj;
-    for (int i = 0; i < p; ++i) {
+    _Pragma("unroll") for (int i = 0; i < p; ++i) {
       if (i < j) L[i * p + j] = 0.0;
       if (i > j) {
         double s = F[i * p + j];
-        for (int k = 0; k < j; ++k) s -= L[i * p + k] * L[j * p + k];
+        _Pragma("unroll") for (int k = 0; k < p; ++k)
+          if (k < j) s -= L[i * p + k] * L[j * p + k];
         L[i * p + j] = s / lj;
       }
     }
   }
-  for (int c = 0; c < p; ++c)
-    for (int i = 0; i < p; ++i) {
+  _Pragma("unroll") for (int c = 0; c < p; ++c)
+    _Pragma("unroll") for (int i = 0; i < p; ++i) {
       if (i < c) Li[i * p + c] = 0.0;
       else {
         double s = (i == c) ? 1.0 : 0.0;
-        for (int k = c; k < i; ++k) s -= L[i * p + k] * Li[k * p + c];
+        _Pragma("unroll") for (int k = 0; k < p; ++k)
+          if (k >= c && k < i) s -= L[i * p + k] * Li[k * p + c];
+        Li[i * p + c] = s / L[i * p + i];
+      }
+    }
+  return ok;
+}
+
+template <class TF, class TL>
+KFB_HD bool chol_factor(const TF& F, TL& L, TL& Li, int p, double* logdet) {
+  bool ok = true;
+  double ld = 0.0;
+  _Pragma("unroll") for (int j = 0; j < p; ++j) {
+    double dj = F[j * p + j];
+    _Pragma("unroll") for (int k = 0; k < j; ++k) dj -= L[j * p + k] * L[j * p + k];
+    ok = ok && (dj > 0.0) && (dj < 1.0e300);
+    const double lj = sqrt(dj);
+    ld += log(dj);
+    L[j * p + j] = lj;
+    _Pragma("unroll") for (int i = 0; i < p; ++i) {
+      if (i < j) L[i * p + j] = 0.0;
+      if (i > j) {
+        double s = F[i * p + j];
+        _Pragma("unroll") for (int k = 0; k < j; ++k) s -= L[i * p + k] * L[j * p + k];
+        L[i * p + j] = s / lj;
+      }
+    }
+  }
+  _Pragma("unroll") for (int c = 0; c < p; ++c)
+    _Pragma("unroll") for (int i = 0; i < p; ++i) {
+      if (i < c) Li[i * p + c] = 0.0;
+      else {
+        double s = (i == c) ? 1.0 : 0.0;
+        _Pragma("unroll") for (int k = c; k < i; ++k) s -= L[i * p + k] * Li[k * p + c];
         Li[i * p + c] = s / L[i * p + i];
       }
     }
@@ -252,45 +287,45 @@ template <class TG, class TL, class TW>
 KFB_HD void chols_adjoint(const TG& Gb, const TL& L, const TL& Li, const TG& Gk, double lb, TW& W1, TW& W2, TG& Fb,
                           int p) {
   // W1 = Lib : Lib[i][k] = Gb[k][i] / L_ii
-  for (int i = 0; i < p; ++i)
-    for (int k = 0; k < p; ++k) W1[i * p + k] = Gb[k * p + i] / L[i * p + i];
+  _Pragma("unroll") for (int i = 0; i < p; ++i)
+    _Pragma("unroll") for (int k = 0; k < p; ++k) W1[i * p + k] = Gb[k * p + i] / L[i * p + i];
   // W2 = Lb = -Li^T Lib Li^T
-  for (int i = 0; i < p; ++i)
-    for (int j = 0; j < p; ++j) {
+  _Pragma("unroll") for (int i = 0; i < p; ++i)
+    _Pragma("unroll") for (int j = 0; j < p; ++j) {
       double s = 0.0;
-      for (int a = 0; a < p; ++a) {
+      _Pragma("unroll") for (int a = 0; a < p; ++a) {
         double t = 0.0;
-        for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[j * p + b];
+        _Pragma("unroll") for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[j * p + b];
         s += Li[a * p + i] * t;
       }
       W2[i * p + j] = -s;
     }
-  for (int i = 0; i < p; ++i) {
+  _Pragma("unroll") for (int i = 0; i < p; ++i) {
     double s = 0.0;
-    for (int k = 0; k < p; ++k) s += Gb[k * p + i] * Gk[k * p + i];
+    _Pragma("unroll") for (int k = 0; k < p; ++k) s += Gb[k * p + i] * Gk[k * p + i];
     W2[i * p + i] += -s / L[i * p + i] - lb / L[i * p + i];
   }
   // W1 = Phi = tril(L^T Lb), diagonal halved
-  for (int i = 0; i < p; ++i)
-    for (int j = 0; j < p; ++j) {
+  _Pragma("unroll") for (int i = 0; i < p; ++i)
+    _Pragma("unroll") for (int j = 0; j < p; ++j) {
       double s = 0.0;
       if (j <= i)
-        for (int k = 0; k < p; ++k) s += L[k * p + i] * W2[k * p + j];
+        _Pragma("unroll") for (int k = 0; k < p; ++k) s += L[k * p + i] * W2[k * p + j];
       W1[i * p + j] = (i == j) ? 0.5 * s : s;
     }
   // W2 = S = Li^T Phi Li ; Fb = (S + S^T) / 2
-  for (int i = 0; i < p; ++i)
-    for (int j = 0; j < p; ++j) {
+  _Pragma("unroll") for (int i = 0; i < p; ++i)
+    _Pragma("unroll") for (int j = 0; j < p; ++j) {
       double s = 0.0;
-      for (int a = 0; a < p; ++a) {
+      _Pragma("unroll") for (int a = 0; a < p; ++a) {
         double t = 0.0;
-        for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[b * p + j];
+        _Pragma("unroll") for (int b = 0; b < p; ++b) t += W1[a * p + b] * Li[b * p + j];
         s += Li[a * p + i] * t;
       }
       W2[i * p + j] = s;
     }
-  for (int i = 0; i < p; ++i)
-    for (int j = 0; j < p; ++j) Fb[i * p + j] = 0.5 * (W2[i * p + j] + W2[j * p + i]);
+  _Pragma("unroll") for (int i = 0; i < p; ++i)
+    _Pragma("unroll") for (int j = 0; j < p; ++j) Fb[i * p + j] = 0.5 * (W2[i * p + j] + W2[j * p + i]);
 }
 
 // Per-step outputs of the full-output forward pass (the reference's moments and ll_obs, kalman_filter.py:184-191).

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(G > 128 ? G : 128, G > 128 ? 2 : 1)
 template <int M, int P, int G, int MK, bool BWD, bool NEED_Z>
 __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (NEED_Z ? 2 : 3) : 4)) kf_rows_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
-  constexpr int per_unit = BWD ? RowsLayout<M, P, NEED_Z, MK == MK_STEADY>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
+  constexpr int per_unit =
+      BWD ? RowsLayout<M, P, NEED_Z, MK == MK_STEADY || MK == MK_CHOLS>::bwd_doubles : RowsLayout<M, P>::fwd_doubles;
   constexpr int UPW = RowsCfg<M, P, G>::UPW;
   const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int grp = lane32 / G, l = lane32 - grp * G;

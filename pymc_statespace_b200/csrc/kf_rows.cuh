@@ -145,6 +145,7 @@ __device__ __forceinline__ void store_rows(double* base, const RowIdx<M, R>& rw,
 template <int M, int P, int R>
 struct RowGain {
   double TM[R][P], Kp[R][P], Lm[R][M], Fi[P * P], v[P], w[P], piv[P], quad;
+  double Lc[P * P], Lic[P * P];  // MK_CHOLS only: Cholesky factor of F and its inverse (dead registers elsewhere)
   bool ok;
 };
 
@@ -200,14 +201,24 @@ __device__ __forceinline__ void rows_gain(double* sm, const double* yt, double d
 #pragma unroll
     for (int q = 0; q < R; ++q) g.TM[q][j] = s[q];
   }
-  g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
-  if (MK == MK_STD && P > 1 && full_det && g.ok) g.ok = lu_pivots(Fr, Lr, g.piv, P);  // det of the full matrix (t = 0)
+  if (MK == MK_CHOLS) {
+    // the as-coded CholeskyFilter for k_endog > 1: gain matrix Gk[k][i] = Li[i][k] / L_ii, w = Gk^T v
+    g.ok = chol_factor_piv(Fr, g.Lc, g.Lic, g.piv, P);
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+#pragma unroll
+      for (int i = 0; i < P; ++i) g.Fi[k * P + i] = g.Lic[i * P + k] / g.Lc[i * P + i];
+  } else {
+    g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
+    if (MK == MK_STD && P > 1 && full_det && g.ok) g.ok = lu_pivots(Fr, Lr, g.piv, P);  // det of the full matrix (t = 0)
+  }
   double qd = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s = fma(MK == MK_STEADY ? Gss[j * P + k] : g.Fi[j * P + k], g.v[k], s);
+    for (int k = 0; k < P; ++k)
+      s = fma(MK == MK_STEADY ? Gss[j * P + k] : MK == MK_CHOLS ? g.Fi[k * P + j] : g.Fi[j * P + k], g.v[k], s);
     g.w[j] = s;
     qd = fma(g.v[j], s, qd);
   }
@@ -477,7 +488,7 @@ __device__ __forceinline__ void rows_tape_wait() {
 // Z-bar accumulators and the Lb / Mb exchanges exist only in that instantiation.
 template <int M, int P, int G, int MK, bool NEED_Z>
 __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
-  using L = RowsLayout<M, P, NEED_Z, MK == MK_STEADY>;
+  using L = RowsLayout<M, P, NEED_Z, MK == MK_STEADY || MK == MK_CHOLS>;
   constexpr int R = RowsCfg<M, P, G>::R;
   constexpr int KT = L::KT;
   const int n = A.n;
@@ -580,7 +591,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     const bool observed = (rows_count_missing<P>(yt) == 0);
     if (observed) {
       rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, tr, Pr, Gss, g);
-      if (MK == MK_STEADY) store_rows<M, R, P>(sm + L::TMs, rw, g.TM);  // read by every lane in phase 3 (after syncs)
+      if (MK == MK_STEADY || MK == MK_CHOLS) store_rows<M, R, P>(sm + L::TMs, rw, g.TM);  // read by every lane in phase 3 (after syncs)
     } else {
 #pragma unroll
       for (int q = 0; q < R; ++q) {
@@ -746,6 +757,27 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
             Fb[a2 * P + b2] = -0.5 * lb * g.Fi[b2 * P + a2];
           }
         }
+      } else if (MK == MK_CHOLS) {
+        // vb = Kp^T ab - lb/2 (Gk + Gk^T) v ; Gk-bar = TM^T Kb - lb/2 v v^T ; Fb = adjoint of the as-coded gain matrix
+        // and of - sum log L_ii through the Cholesky factor (chols_adjoint, kf_core.cuh)
+        double Gkb[P * P], W1[P * P], W2[P * P];
+#pragma unroll
+        for (int a2 = 0; a2 < P; ++a2) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < M; ++k) s = fma(sm[L::Kp + k * P + a2], sm[L::ab + k], s);
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) s = fma(-0.5 * lb * (g.Fi[a2 * P + b2] + g.Fi[b2 * P + a2]), g.v[b2], s);
+          vb[a2] = s;
+#pragma unroll
+          for (int b2 = 0; b2 < P; ++b2) {
+            double q1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) q1 = fma(sm[L::TMs + k * P + a2], sm[L::Kb + k * P + b2], q1);
+            Gkb[a2 * P + b2] = fma(-0.5 * lb * g.v[a2], g.v[b2], q1);
+          }
+        }
+        chols_adjoint(Gkb, g.Lc, g.Lic, g.Fi, lb, W1, W2, Fb, P);
       } else {
         double Q1[P * P];
 #pragma unroll

@@ -627,3 +627,45 @@ def test_p1_structure_flags_on_device(m):
     out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), stack(3), _dev(Zb), stack(5), _dev(np.array([[0.7]])), stack(7))
     info = out["info"].cpu().numpy()
     assert info[3] == KFB_INFO_BAD_STRUCTURE and (np.delete(info, 3) == 0).all() and bool(torch.isnan(out["loglik"][3]))
+
+
+@pytest.mark.parametrize("wrt", [("a0", "P0", "T", "R", "H", "Q", "c", "d"), ("a0", "R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
+@pytest.mark.parametrize("dims", [(5, 3, 2), (6, 2, 3), (6, 3, 3), (8, 3, 3)], ids=lambda d: "m%dp%dr%d" % d)
+def test_fused_row_kernels_as_coded_cholesky(dims, wrt):
+    """BASELINE.json configs[2] names the cholesky filter: strict_reference = the AS-CODED CholeskyFilter for k_endog > 1
+    (kalman_filter.py:287-318, second trtrs reads only diag(L): SURVEY A.2-Q4) on the fused row kernels (MK_CHOLS
+    instantiations of kf_rows.cuh: gain matrix Gk, adjoint through the Cholesky factor) - values and gradients against
+    the oracle's restatement of the as-coded filter, and against the generic cooperative kernels on every unit."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = dims
+    rng = np.random.default_rng(2000 + 10 * m + p)
+    B, n = 13, 24
+    systems = [random_system(rng, m, p, r, n, scale_T=0.25) for _ in range(B)]
+    y = random_system(rng, m, p, r, n, n_missing=3)[0]
+    cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    wt = rng.normal(size=(B, n))
+    res = {}
+    for force in (False, True):
+        bk = BatchedKalman("cholesky", n, m, p, r, n_draws=B, strict_reference=True, force_coop=force)
+        out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                         c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
+        g = bk.backward(wrt=wrt)
+        g2 = bk.backward(g_loglik=_dev(np.zeros(B)), g_ll_obs=_dev(wt), wrt=wrt)
+        assert int(out["info"].abs().max()) == 0
+        res[force] = (out["loglik"].cpu().numpy(), {k: v.cpu().numpy() for k, v in g.items()},
+                      {k: v.cpu().numpy() for k, v in g2.items()})
+    assert np.abs(res[False][0] / res[True][0] - 1).max() < 1e-11
+    for k in wrt:
+        for idx in (1, 2):
+            scale = np.abs(res[True][idx][k]).max()
+            assert np.abs(res[False][idx][k] - res[True][idx][k]).max() / scale < 1e-9, (k, idx)
+    for b in (0, 8, 12):
+        args = (y,) + tuple(systems[b][1:])
+        ref, gref = kt.loglik_and_grads("cholesky", *args, c=cs[b][:, None], d=ds[b][:, None], strict_reference=True)
+        assert abs(res[False][0][b] - ref) < RTOL * abs(ref)
+        for k in wrt:
+            got = res[False][1][k][b].reshape(gref[k].shape)
+            scale = max(np.abs(gref[k]).max(), 1e-12)
+            assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b)
