@@ -7,6 +7,7 @@
 #include "kf_pred.cuh"
 #include "kf_rows.cuh"
 #include "kf_rowsD.cuh"
+#include "kf_rowsU.cuh"
 #include "kf_smooth.cuh"
 
 namespace kfb {
@@ -178,6 +179,21 @@ __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (N
   double* sm = kf_dyn_smem + (size_t)slot * per_unit;
   if (BWD) rows_backward<M, P, G, MK, NEED_Z>(A, u, sm, l, mask);
   else rows_forward<M, P, G, MK>(A, u, sm, l, mask);
+}
+
+// Fused UnivariateFilter programs (kf_rowsU.cuh): 8 lanes per unit, 4 units per warp.  BWD = adjoint (no Z-bar).
+template <int M, int P, bool BWD>
+__global__ void __launch_bounds__(128, BWD ? 2 : 3) kf_rowsU_kernel(const __grid_constant__ KfArgs A) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int per_unit = BWD ? RowsULayout<M, P>::bwd_doubles : RowsULayout<M, P>::fwd_doubles;
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp * 4 + (lane32 >> 3);
+  const long long u = (long long)blockIdx.x * ((blockDim.x >> 5) * 4) + slot;
+  if (u >= A.U) return;
+  const unsigned mask = __activemask();
+  double* sm = kf_dyn_smem + (size_t)slot * per_unit;
+  if (BWD) rowsU_backward<M, P>(A, u, sm, lane32 & 7, mask);
+  else rowsU_forward<M, P>(A, u, sm, lane32 & 7, mask);
 }
 
 // Fused row-per-lane, warp-per-unit programs for large systems with the m^3 products on the FP64 tensor cores

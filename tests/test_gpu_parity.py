@@ -669,3 +669,49 @@ def test_fused_row_kernels_as_coded_cholesky(dims, wrt):
             got = res[False][1][k][b].reshape(gref[k].shape)
             scale = max(np.abs(gref[k]).max(), 1e-12)
             assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b)
+
+
+@pytest.mark.parametrize("wrt", [("a0", "P0", "T", "R", "H", "Q", "c", "d"), ("a0", "R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
+@pytest.mark.parametrize("dims", [(5, 1, 2), (5, 3, 2), (6, 2, 3), (6, 3, 3), (7, 3, 2), (8, 3, 3)], ids=lambda d: "m%dp%dr%d" % d)
+def test_fused_row_kernels_univariate(dims, wrt):
+    """UnivariateFilter (kalman_filter.py:444-505) on the fused kernels of kf_rowsU.cuh (8 lanes per unit, replicated
+    state, one exchange per scalar update): loglik-only forward + adjoint without Z-bar, PARTIALLY missing rows (the one
+    filter that supports them), whole missing rows, non-diagonal H (only its diagonal is used, A.2-Q9), non-symmetric P0
+    (entry-wise gauge of P0-bar), 13 units (partial last warp), n = 24 / 2 / 1, loglik and per-step cotangents -
+    against the generic cooperative kernels on every unit and against torch-autograd of the oracle."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    m, p, r = dims
+    rng = np.random.default_rng(3000 + 10 * m + p)
+    for n in (24, 2, 1):
+        B = 13
+        systems = [list(random_system(rng, m, p, r, n, scale_T=0.25)) for _ in range(B)]
+        for s_ in systems:
+            s_[2] = s_[2] + 0.05 * rng.normal(size=(m, m))
+        y = random_system(rng, m, p, r, n, n_missing=min(3, n - 1), partial=True)[0]
+        cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
+        stack = lambda i: _dev(np.stack([s_[i] for s_ in systems]))  # noqa: E731
+        wt = rng.normal(size=(B, n))
+        res = {}
+        for force in (False, True):
+            bk = BatchedKalman("univariate", n, m, p, r, n_draws=B, force_coop=force)
+            out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7),
+                             c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
+            g = bk.backward(wrt=wrt)
+            g2 = bk.backward(g_loglik=_dev(np.full(B, 0.25)), g_ll_obs=_dev(wt), wrt=wrt)
+            assert int(out["info"].abs().max()) == 0
+            res[force] = (out["loglik"].cpu().numpy(), {k: v.cpu().numpy() for k, v in g.items()},
+                          {k: v.cpu().numpy() for k, v in g2.items()})
+        assert np.abs(res[False][0] / res[True][0] - 1).max() < 1e-12
+        for k in wrt:
+            for idx in (1, 2):
+                scale = max(np.abs(res[True][idx][k]).max(), 1e-300)
+                assert np.abs(res[False][idx][k] - res[True][idx][k]).max() / scale < 1e-10, (k, idx, n)
+        for b in (0, 8, 12):
+            args = (y,) + tuple(systems[b][1:])
+            ref, gref = kt.loglik_and_grads("univariate", *args, c=cs[b][:, None], d=ds[b][:, None])
+            assert abs(res[False][0][b] - ref) < RTOL * abs(ref)
+            for k in wrt:
+                got = res[False][1][k][b].reshape(gref[k].shape)
+                scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+                assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b, n)
