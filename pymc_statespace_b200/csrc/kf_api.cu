@@ -25,7 +25,14 @@ coopT_launch_fn coopT_launcher_m5(int p, int mk);
 coopT_launch_fn coopT_launcher_m6(int p, int mk);
 coopT_launch_fn coopT_launcher_m7(int p, int mk);
 coopT_launch_fn coopT_launcher_m8(int p, int mk);
+coopT_launch_fn coopT_launcher_m18(int p, int mk);
+coopT_launch_fn coopT_launcher_m20(int p, int mk);
+coopT_launch_fn coopT_launcher_m22(int p, int mk);
+coopT_launch_fn coopT_launcher_m24(int p, int mk);
+coopT_launch_fn coopT_launcher_m26(int p, int mk);
+coopT_launch_fn coopT_launcher_m28(int p, int mk);
 coopT_launch_fn coopT_launcher_m30(int p, int mk);
+coopT_launch_fn coopT_launcher_m32(int p, int mk);
 
 coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
   switch (m) {
@@ -33,7 +40,14 @@ coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
     case 6: return coopT_launcher_m6(p, mk);
     case 7: return coopT_launcher_m7(p, mk);
     case 8: return coopT_launcher_m8(p, mk);
+    case 18: return coopT_launcher_m18(p, mk);
+    case 20: return coopT_launcher_m20(p, mk);
+    case 22: return coopT_launcher_m22(p, mk);
+    case 24: return coopT_launcher_m24(p, mk);
+    case 26: return coopT_launcher_m26(p, mk);
+    case 28: return coopT_launcher_m28(p, mk);
     case 30: return coopT_launcher_m30(p, mk);
+    case 32: return coopT_launcher_m32(p, mk);
     default: return nullptr;
   }
 }

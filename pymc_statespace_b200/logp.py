@@ -22,7 +22,7 @@ import torch
 
 from ._lib import (KFB_ERR_UNSUPPORTED, KFB_INFO_NOT_STATIONARY, KFB_MAX_SCATTER_SEGMENTS, KfbScatterSeg, check, load)
 from .engine import BatchedKalman, _ptr, _stream_ptr, lyapunov_backward, lyapunov_forward
-from .models import MATRICES, StateSpaceSpec
+from .models import FUSED_K_STATES, MATRICES, StateSpaceSpec, pad_spec
 
 
 def _capture(dev, body, warmup):
@@ -166,7 +166,14 @@ def logp_and_grad_in_waves(spec: StateSpaceSpec, data, theta: torch.Tensor, filt
 
 class KalmanLogp:
     def __init__(self, spec: StateSpaceSpec, data, n_draws: int, filter_type: str = "standard",
-                 strict_reference: bool = True, device="cuda", force_coop: bool = False):
+                 strict_reference: bool = True, device="cuda", force_coop: bool = False, pad_to_fused: bool = True):
+        # sizes between the fused instantiations (k_states 9..31 outside {18, 20, .., 32}; e.g. seasonal models of period
+        # 12 or 24): embed the model in the next instantiated size - exact (models.pad_spec) and far cheaper than the
+        # generic run-time-dims kernels, because the tensor-core kernels work on zero-padded 32 x 32 tiles anyway
+        self.k_states_model = spec.k_states
+        if (pad_to_fused and spec.k_endog == 1 and 8 < spec.k_states < 32 and spec.k_states not in FUSED_K_STATES
+                and filter_type in ("standard", "single", "cholesky", "steady_state")):
+            spec = pad_spec(spec, min(k for k in FUSED_K_STATES if k >= max(spec.k_states, 18)))
         self.spec = spec
         self.device = torch.device(device)
         self.lib = load()
@@ -253,7 +260,16 @@ class KalmanLogp:
                                      "ll_obs")):
         """Forward pass with the reference's six outputs (batched over draws)."""
         mats = self._scatter(self._check_theta(theta))
-        return self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=outputs)
+        out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=outputs)
+        m = self.k_states_model
+        if m != self.spec.k_states:  # padded model: report the moments of the model's own states
+            for k in ("filtered_states", "predicted_states"):
+                if k in out:
+                    out[k] = out[k][..., :m].contiguous()
+            for k in ("filtered_covs", "predicted_covs"):
+                if k in out:
+                    out[k] = out[k][..., :m, :m].contiguous()
+        return out
 
     def logp(self, theta) -> torch.Tensor:
         mats = self._scatter(self._check_theta(theta))

@@ -209,3 +209,35 @@ def trend_seasonal_spec(period: int = 29) -> StateSpaceSpec:
     maps["Q"] = [(0, 0), (1, 4), (2, 8)]
     maps["H"] = [(3, 0)]
     return StateSpaceSpec(m, 1, r, 4, base, maps, False, ("sigma2_level", "sigma2_slope", "sigma2_seasonal", "sigma2_obs"))
+
+
+FUSED_K_STATES = tuple(range(1, 9)) + tuple(range(18, 33, 2))  # sizes with fused hot-path kernels in libkfb200.so
+
+
+def pad_spec(spec: StateSpaceSpec, k_states: int) -> StateSpaceSpec:
+    """The same model embedded in ``k_states`` >= spec.k_states states: the extra states have zero rows / columns in
+    T, Z, R, c, a0, P0, so they stay identically zero (mean and covariance), never reach an observation and leave logp,
+    every per-step output of the original states and every d logp / d theta unchanged - exactly (the padded products only
+    add zeros).  Used by ``KalmanLogp`` to run e.g. a 13-state seasonal model (period 12) on the 18-state tensor-core
+    kernels instead of the generic run-time-dims kernels."""
+    m, m2, p, r = spec.k_states, int(k_states), spec.k_endog, spec.k_posdef
+    if m2 < m:
+        raise ValueError("cannot pad to fewer states")
+    if m2 == m:
+        return spec
+    shapes = {"a0": (m2, 1), "P0": (m2, m2), "T": (m2, m2), "Z": (p, m2), "R": (m2, r), "H": (p, p), "Q": (r, r),
+              "c": (m2, 1), "d": (p, 1)}
+    base = {}
+    for k in MATRICES:
+        old = np.asarray(spec.base[k], dtype=np.float64)
+        old = old.reshape(old.shape[0], -1) if old.ndim else old.reshape(1, 1)
+        new = np.zeros(shapes[k])
+        new[:old.shape[0], :old.shape[1]] = old
+        base[k] = new
+    ncols = {"a0": (1, 1), "P0": (m, m2), "T": (m, m2), "Z": (m, m2), "R": (r, r), "H": (p, p), "Q": (r, r), "c": (1, 1), "d": (1, 1)}
+    maps = {}
+    for k in MATRICES:
+        old_c, new_c = ncols[k]
+        maps[k] = [(ti, (fi // old_c) * new_c + (fi % old_c)) for ti, fi in spec.maps.get(k, [])]
+    return StateSpaceSpec(m2, p, r, spec.n_theta, base, maps, spec.stationary_initialization, spec.param_names,
+                          dict(spec.param_slices))

@@ -117,6 +117,32 @@ def test_c_port_matches_torch_oracle():
             assert rel_err(g[k][0].reshape(gt[k].shape), gt[k]) < 1e-10, k
 
 
+def test_pad_spec_is_exact_in_the_oracle():
+    """models.pad_spec (sizes between the fused kernel instantiations): the padded model has the same log-likelihood, the
+    same moments of the original states and identical theta-maps semantics - checked with the CPU oracle."""
+    from oracle import kalman_numpy as kn
+    from pymc_statespace_b200.models import arma_spec, pad_spec, trend_seasonal_spec
+
+    rng = np.random.default_rng(0)
+    for spec, theta, m2 in ((trend_seasonal_spec(12), np.array([0.1, 0.01, 0.05, 0.5]), 18),
+                            (arma_spec((3, 2), stationary_initialization=False), None, 5)):
+        if theta is None:
+            theta = rng.normal(size=spec.n_theta) * 0.3
+            L = rng.normal(size=(3, 3)) * 0.3 + np.eye(3)
+            theta[spec.param_slices["P0"]] = (L @ L.T).ravel()
+            theta[spec.param_slices["sigma_state"]] = 0.8
+        big = pad_spec(spec, m2)
+        assert big.k_states == m2 and big.n_theta == spec.n_theta
+        a, b = spec.matrices(theta), big.matrices(theta)
+        y = rng.normal(size=(30, 1, 1))
+        o1 = kn.kalman_filter("standard", y, *[a[k] for k in ("a0", "P0", "T", "Z", "R", "H", "Q")])
+        o2 = kn.kalman_filter("standard", y, *[b[k] for k in ("a0", "P0", "T", "Z", "R", "H", "Q")])
+        m = spec.k_states
+        assert abs(o1[4] - o2[4]) < 1e-13 * abs(o1[4])
+        assert np.abs(o1[0] - o2[0][:, :m]).max() < 1e-13 and np.abs(o1[3] - o2[3][:, :m, :m]).max() < 1e-12
+        assert np.abs(o2[0][:, m:]).max() == 0.0 and np.abs(o2[3][:, m:, :]).max() == 0.0   # extra states stay zero
+
+
 def test_shard_bounds_cover_all_draws():
     from pymc_statespace_b200.dist import shard_bounds
 

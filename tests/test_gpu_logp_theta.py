@@ -398,3 +398,46 @@ def test_status_codes_for_non_stationary_draws_and_failed_dare():
     assert info[0] == 0 and info[1] == KFB_INFO_DARE_FAILED and bool(torch.isnan(out["loglik"][1]))
     with pytest.raises(Exception, match="DARE"):
         bk.raise_on_info(out["info"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("period,kind", [(12, "standard"), (24, "standard"), (12, "steady_state"), (7, "standard")])
+def test_sizes_between_instantiations_are_padded_exactly(period, kind):
+    """Seasonal models whose k_states falls between the fused instantiations (period 12 -> 13 states, period 24 -> 25):
+    KalmanLogp embeds them in the next instantiated size (models.pad_spec: extra states identically zero).  logp and
+    d logp / d theta must equal the un-padded evaluation on the generic run-time-dims kernels and the oracle."""
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.models import FUSED_K_STATES, trend_seasonal_spec
+
+    spec = trend_seasonal_spec(period)
+    rng = np.random.default_rng(period)
+    B, n = 24, 60
+    theta = np.exp(rng.normal(np.log([0.1, 0.01, 0.05, 0.5]), 0.2, size=(B, 4)))
+    y = (np.sin(2 * np.pi * np.arange(n) / period) + np.cumsum(rng.normal(0, 0.3, n)) + rng.normal(0, 0.7, n))[:, None]
+    y[[5, 17]] = np.nan
+    th = torch.as_tensor(theta, device="cuda")
+    padded = KalmanLogp(spec, y, n_draws=B, filter_type=kind)
+    plain = KalmanLogp(spec, y, n_draws=B, filter_type=kind, pad_to_fused=False)
+    m = spec.k_states
+    assert plain.spec.k_states == m and padded.k_states_model == m
+    assert padded.spec.k_states == (m if m in FUSED_K_STATES else min(k for k in FUSED_K_STATES if k >= max(m, 18)))
+    lp1, g1 = padded.logp_and_grad(th)
+    lp0, g0 = plain.logp_and_grad(th)
+    assert int((padded.info != 0).sum()) == 0 and int((plain.info != 0).sum()) == 0
+    gtol = 1e-6 if kind == "steady_state" else 1e-9
+    assert float(((lp1 - lp0).abs() / lp0.abs()).max()) < 1e-11
+    assert float(((g1 - g0).abs().amax(1) / g0.abs().amax(1)).max()) < gtol
+
+    def mats(t):
+        mm = spec.matrices(t.detach().numpy())
+        T, Z, R = (torch.tensor(mm[k]) for k in ("T", "Z", "R"))
+        Q = torch.zeros(3, 3, dtype=torch.float64)
+        Q[0, 0], Q[1, 1], Q[2, 2] = t[0], t[1], t[2]
+        return torch.zeros(m, 1, dtype=torch.float64), torch.eye(m, dtype=torch.float64), T, Z, R, t[3].reshape(1, 1), Q
+
+    ll, gr = om.logp_and_grad_theta(mats, theta[3], y[:, :, None], kind)
+    assert abs(float(lp1[3]) - ll) <= 1e-8 * abs(ll)
+    assert np.abs(g1[3].cpu().numpy() - gr).max() <= (1e-6 if kind == "steady_state" else 1e-8) * np.abs(gr).max()
+    # the full-output call reports the model's own states only
+    out = padded.filter(th, outputs=("filtered_states", "predicted_covs", "loglik"))
+    assert tuple(out["filtered_states"].shape) == (B, n, m) and tuple(out["predicted_covs"].shape) == (B, n + 1, m, m)
