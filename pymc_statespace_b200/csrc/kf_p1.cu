@@ -171,7 +171,7 @@ static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t 
 // per-SM store path, not HBM, was the limit at 14 resident warps per SM.  Two slots per warp; a slot is reused only after
 // the bulk store issued from it two steps earlier has finished READING it (cp.async.bulk.wait_group.read 1).
 #ifndef KFB_P1_BULK_STORE
-#define KFB_P1_BULK_STORE 1
+#define KFB_P1_BULK_STORE 0
 #endif
 template <int M>
 struct BulkSink {
@@ -215,7 +215,11 @@ __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     yp = kf_dyn_smem;
   }
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#if defined(KFB_P1_DEBUG_TSTEP0)  // experiment only: every step overwrites the same (L2-resident) entry
+  const long long tstep = 0;
+#else
   const long long tstep = (long long)KT * tape_units_padded(A.U);
+#endif
   if (SAVE && KFB_P1_BULK_STORE) {
     // warp-collective stores: the padding lanes of the last warp run along on the last unit's inputs (their columns of
     // the padded tape are never read)

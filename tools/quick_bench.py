@@ -30,19 +30,33 @@ def main():
     for force, gen in ((False, False), (False, True)) + (((True, False),) if B <= 16384 else ()):
         st = os.environ.get('KFB_STRUCT', '1') == '1' and not gen and not force   # ARMA: Z = [1, 0], H = 0
         bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen, z_unit0=st, h_zero=st)
-        for it in range(5):
+        # the CPU must run AHEAD of the GPU or the events also measure launch latency: enqueue several evaluations
+        # back to back, time the later ones
+        for it in range(3):
+            out = bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=True)
+            g = bk.backward(wrt=WRT)
+        torch.cuda.synchronize()
+        evs = []
+        for it in range(6):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
             out = bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=True)
             e[1].record()
             g = bk.backward(wrt=WRT)
-            e[2].record(); torch.cuda.synchronize()
-            tf, tb = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        for it in range(3):
+            e[2].record()
+            evs.append(e)
+        torch.cuda.synchronize()
+        tf = min(e[0].elapsed_time(e[1]) for e in evs[2:])
+        tb = min(e[1].elapsed_time(e[2]) for e in evs[2:])
+        evs = []
+        for it in range(8):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             e[0].record()
             bk.forward(y, a0, P0, T, Z, R, H, Q, outputs=("loglik",), save_for_backward=False)
-            e[1].record(); torch.cuda.synchronize()
+            e[1].record()
+            evs.append(e)
+        torch.cuda.synchronize()
+        e = min(evs[3:], key=lambda ev: ev[0].elapsed_time(ev[1]))
         print(f"   forward without tape: {e[0].elapsed_time(e[1]):.3f} ms")
         print(f"coop={force} generic_adjoint={gen} struct={st} B={B} n={n} fwd {tf:.3f} ms bwd {tb:.3f} ms  -> {B*n/((tf+tb)*1e-3):.3e} steps/s; "
               f"ll[0]={float(out['loglik'][0]):.6f} gT[0]={g['T'][0].flatten().tolist()} info!=0: {int((out['info']!=0).sum())}")
