@@ -46,14 +46,17 @@ struct RowsDLayout {
   static_assert(M % 2 == 0 && M > 16 && M <= 32 && P <= 3, "even k_states in 18..32");
   static constexpr int LD = rowsD_LD, MS = 32 * LD;  // one padded matrix
   static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), ME = M + (M & 1);
+  static constexpr int MP32 = 32 * P;  // vectors that the mma-fragment-layout code reads by padded row (rows >= M stay 0)
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
-  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MPE,
-                       a = Kp + MPE, END_COMMON = a + ME;
+  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MP32,
+                       a = Kp + MPE, END_COMMON = a + 32;
   // forward only: X (then S2) ; KH rows
   static constexpr int X = END_COMMON, KH = X + MS, END_FWD = KH + MPE;
-  // adjoint only: W / X-for-lz live in Pm's slot; Lb lives in Xb's slot
-  static constexpr int Pb = END_COMMON, W = Pm, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MPE, lz = PK + MPE, TMs = lz + MPE,
-                       ab = TMs + MPE, tp = ab + ME, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0);
+  // adjoint only: W = Ps L lives in Pm's slot (without T-bar nothing reads P after the gain) or in its own (with T-bar:
+  // T-bar += 2 W P).  lz: (P0 + P0^T) Z^T, t = 0 only.  Mb: the rank-p part of P-bar, kept apart from L^T W.
+  static constexpr int Pb = END_COMMON, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MP32, lz = PK + MPE, TMs = lz + MPE,
+                       ab = TMs + MPE, Mb = ab + 32, tp = Mb + MPE, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0),
+                       W = NEED_T ? Xb : Pm;
   static constexpr int fwd_doubles = (END_FWD + 1) & ~1, bwd_doubles = (END_BWD + 1) & ~1;
 };
 
@@ -65,7 +68,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 // acc (32 x 32, as 4 x 4 tiles of 8 x 8 in mma fragment layout: lane holds [8I + lane/4][8J + 2 (lane%4) + {0,1}])
 //   = op(A) op(B),  op = transpose if TA / TB.  A, B: padded row-major matrices (leading dimension LD) in shared memory.
-template <bool TA, bool TB, int LD>
+// ZERO = false: accumulate onto acc.  UPPER: only the tiles I <= J (the result is symmetric and its consumer reads it
+// through rowD_load_symU): 10 instead of 16 tile products.
+template <bool TA, bool TB, int LD, bool ZERO = true, bool UPPER = false>
 __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, const double* B, int lane) {
   const int r = lane >> 2, c = lane & 3;
   // "N" pattern: element (row 8X + r, col 4kk + c) ; "T" pattern: element (row 4kk + c, col 8X + r)
@@ -76,10 +81,12 @@ __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, co
   const double* nB = B + r * LD + (c & 1);
   const double* tA = A + c * LD + (r & 1);
   const double* tB = B + c * LD + (r & 1);
+  if (ZERO) {
 #pragma unroll
-  for (int I = 0; I < 4; ++I)
+    for (int I = 0; I < 4; ++I)
 #pragma unroll
-    for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+      for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+  }
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     double af[4], bf[4];
@@ -94,14 +101,15 @@ __device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, co
 #pragma unroll
     for (int I = 0; I < 4; ++I)
 #pragma unroll
-      for (int J = 0; J < 4; ++J) dmma884(acc[I][J][0], acc[I][J][1], af[I], bf[J]);
+      for (int J = 0; J < 4; ++J)
+        if (!UPPER || I <= J) dmma884(acc[I][J][0], acc[I][J][1], af[I], bf[J]);
   }
 }
 
-// D = alpha * acc (full 32 x 32 including the zero padding)
-template <int LD>
+// D = alpha * acc (full 32 x 32 including the zero padding; UPPER: the tiles I <= J only)
+template <int LD, bool UPPER = false>
 __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][2], double alpha, int lane) {
-  // D may be one of the product's own operands (X <- X L^T, Pm's slot <- 2 L Pm, Xb <- Ps Xb): every fragment load is
+  // D may be one of the product's own operands (X <- X L^T, Xb <- Ps Xb): every fragment load is
   // behind an mma.sync that consumed it, but make the ordering explicit (and visible to racecheck)
   __syncwarp();
   const int r = lane >> 2, c = lane & 3;
@@ -109,10 +117,21 @@ __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][
   for (int I = 0; I < 4; ++I)
 #pragma unroll
     for (int J = 0; J < 4; ++J)
-      *reinterpret_cast<double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1)) =
-          make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
+      if (!UPPER || I <= J)
+        *reinterpret_cast<double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1)) =
+            make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
 }
 
+// Swizzled layout only: the per-lane chunk offsets (j ^ swz(row)) of the row accesses must NOT be kept as loop
+// invariants (15 + 40 registers in kernels at the 255-register limit: the round-1 A/B lost on spills).  An empty
+// volatile asm makes the lane's swizzle value opaque at every use, so ptxas re-derives each offset with one LOP3 next to
+// its access (issue slots are < 20 % busy in these kernels) instead of hoisting it.
+__device__ __forceinline__ int rowsD_fresh(int x) {
+#if KFB_ROWSD_SWZ && defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(x));
+#endif
+  return x;
+}
 // row i of a tile matrix: rowp = &mat[i * LD], si = rowsD_swz(i); chunk j of the row lives at rowp + ((j ^ si) << 1)
 __device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int si, int j) {
   return reinterpret_cast<const double2*>(rowp + ((j ^ si) << 1));
@@ -122,11 +141,13 @@ __device__ __forceinline__ double2* rowD_chunk(double* rowp, int si, int j) {
 }
 template <int M>
 __device__ __forceinline__ void rowD_store(double* rowp, int si, const double (&v)[M]) {
+  si = rowsD_fresh(si);
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, si, j) = make_double2(v[2 * j], v[2 * j + 1]);
 }
 template <int M>
 __device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, int si) {
+  si = rowsD_fresh(si);
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
     const double2 x = *rowD_chunk(rowp, si, j);
@@ -136,7 +157,33 @@ __device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, in
 }
 // element (row j, column i) of a tile matrix, j a compile-time constant after unrolling: the lane's COLUMN accesses
 __device__ __forceinline__ double colD(const double* mat, int j, int i) {
+  i = rowsD_fresh(i);
   return mat[j * rowsD_LD + ((((i >> 1) ^ rowsD_swz(j)) << 1) | (i & 1))];
+}
+
+// The lane's row i of sym(U) for a matrix U = A^T S A (S symmetric) of which only the 8 x 8 tiles I <= J were computed
+// (mm32<.., UPPER>): entries right of the lane's diagonal tile come from its row, entries left of it from its column
+// (the mirrored tile), the diagonal tile is averaged.  Exactly symmetric by construction, and the loads of the tiles a
+// lane does not need are predicated off (whole 8-lane groups: fewer shared-memory wavefronts than the full row + column).
+template <int M>
+__device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat, int i, int si) {
+  const int ti = i >> 3;
+  const double* rowp = mat + i * rowsD_LD;
+  si = rowsD_fresh(si);
+#pragma unroll
+  for (int j = 0; j < M / 2; ++j) {
+    double2 x = make_double2(0.0, 0.0);
+    if (((2 * j) >> 3) >= ti) x = *rowD_chunk(rowp, si, j);
+    v[2 * j] = x.x;
+    v[2 * j + 1] = x.y;
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    if ((j >> 3) <= ti) {
+      const double cj = colD(mat, j, i);
+      v[j] = ((j >> 3) < ti) ? cj : 0.5 * (v[j] + cj);
+    }
+  }
 }
 
 // init + sum_{k<N} x_k y_k with four interleaved partial sums.  With one warp per SM sub-partition nothing hides the
@@ -180,9 +227,10 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     }
     const double* pr = sm + L::Pm + i * LD;
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
+    const int sA = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 pk = *rowD_chunk(pr, si, k), ak = av[k];
+      const double2 pk = *rowD_chunk(pr, sA, k), ak = av[k];
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -212,9 +260,10 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
 #pragma unroll
     for (int j = 0; j < P; ++j) Tq[j][0] = Tq[j][1] = Tq[j][2] = Tq[j][3] = 0.0;
     const double* tr = sm + L::T + i * LD;
+    const int sB = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = *rowD_chunk(tr, si, k);
+      const double2 tk = *rowD_chunk(tr, sB, k);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -257,16 +306,17 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
   {
     const double* tr = sm + L::T + i * LD;
     double* lr = sm + L::Lm + i * LD;
+    const int sC = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      double2 lk = *rowD_chunk(tr, si, k);
+      double2 lk = *rowD_chunk(tr, sC, k);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
         lk.x = fma(-g.Kp[e], z.x, lk.x);
         lk.y = fma(-g.Kp[e], z.y, lk.y);
       }
-      if (act) *rowD_chunk(lr, si, k) = lk;
+      if (act) *rowD_chunk(lr, sC, k) = lk;
     }
   }
   if (act) {
@@ -339,9 +389,10 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
       double aq[4] = {ci, 0.0, 0.0, 0.0};
       const double* tr = sm + L::T + i * LD;
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
+      const int sT = rowsD_fresh(si);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = *rowD_chunk(tr, si, k), ak = av[k];
+        const double2 tk = *rowD_chunk(tr, sT, k), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -377,17 +428,19 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
       mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
       mm32_store<LD>(sm + L::X, c4, 1.0, lane);
       __syncwarp();
-      mm32<false, true, LD>(c4, sm + L::X, Lsrc, lane);
-      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+      // S2raw = (L P) L^T is symmetric up to rounding: only its upper tiles are computed (the lower tiles of X's slot
+      // keep stale values that rowD_load_symU never selects)
+      mm32<false, true, LD, true, true>(c4, sm + L::X, Lsrc, lane);
+      mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
     }
     __syncwarp();
     // ---- P' = sym(C + S2raw + KH Kp^T) row, a' ; tape
     const bool taped = tp && t + 1 < n;
     {
       double S[M];
-      rowD_load<M>(S, sm + L::X + i * LD, si);
+      rowD_load_symU<M>(S, sm + L::X, i, si);
 #pragma unroll
-      for (int j = 0; j < M; ++j) S[j] = fma(0.5, S[j] + colD(sm + L::X, j, i), Cs[j]);
+      for (int j = 0; j < M; ++j) S[j] += Cs[j];
       if (observed) {
 #pragma unroll
         for (int j = 0; j < M; ++j) {
@@ -420,7 +473,17 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   }
 }
 
+
 // ------------------------------------------------------------------------------------------------ adjoint
+// Per step (going backwards), with Ps = sym(P-bar') the symmetrised cotangent of the step above:
+//     W = Ps L                 (tile product)
+//     P-bar = L^T W + Mb Z     (tile product, upper tiles only: L^T Ps L is symmetric; the rank-p part Mb Z is kept
+//                               apart in shared memory and joins in the next step's symmetrisation / the write-out)
+//     L-bar = Ps L (P + P^T) = 2 W P :  T-bar += L-bar is accumulated ON the tensor cores, in mma fragment layout,
+//                               across all steps (T-bar = 2 Tacc; the rank-1 terms ab a^T and TMb Mm^T join it there);
+//                               L-bar Z^T = 2 W (P Z^T) = 2 W Mm is a row-wise dot product with the gain's Mm.
+// Round 1 formed X = 2 L P with a third (fourth, with T-bar) tile product and stored / re-read L-bar as a matrix:
+// 26 instead of 48 tile products per step without T-bar, 42 instead of 64 with it - same terms, associated differently.
 template <int M, int P, int MK, bool NEED_T>
 __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lane) {
   using L = RowsDLayout<M, P, NEED_T>;
@@ -430,11 +493,12 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   const bool act = lane < M;
   const int i = act ? lane : 0;
   const int si = rowsD_swz(i);
+  const int fr = lane >> 2, fc = lane & 3;  // mma fragment coordinates
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
   const double* tape = A.tape + u * (long long)(n - 1) * KT;  // entry t-1 = predicted moments of step t
-  for (int k = lane; k < L::bwd_doubles; k += 32) sm[k] = 0.0;  // zero padding, Pb = 0, ab = 0
+  for (int k = lane; k < L::bwd_doubles; k += 32) sm[k] = 0.0;  // zero padding, Pb = 0, ab = 0, Mb = 0
   __syncwarp();
   if (n >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(n - 2) * KT, lane);
   for (int k = lane; k < M * M; k += 32) {
@@ -457,12 +521,16 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
     Gb[k] = 0.0;
   }
-  // gradient accumulators: the lane's rows of Cb (and Tb) in registers; lanes < P hold rows of Hb; cb (row), db (lane)
-  double Cb[M], Tb[NEED_T ? M : 1], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
+  // gradient accumulators: the lane's row of Cb in registers; HALF of T-bar in mma fragment layout (lane holds
+  // [8I + fr][8J + 2 fc + {0,1}]); lanes < P hold rows of Hb; cb (row), db (lane)
+  constexpr int TI = NEED_T ? 4 : 1;
+  double Cb[M], Tacc[TI][TI][2], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
 #pragma unroll
   for (int j = 0; j < M; ++j) Cb[j] = 0.0;
 #pragma unroll
-  for (int j = 0; j < (NEED_T ? M : 1); ++j) Tb[j] = 0.0;
+  for (int I = 0; I < TI; ++I)
+#pragma unroll
+    for (int J = 0; J < TI; ++J) Tacc[I][J][0] = Tacc[I][J][1] = 0.0;
 #pragma unroll
   for (int j = 0; j < P; ++j) Hb[j] = 0.0;
   RowDGain<M, P> g;
@@ -471,7 +539,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   for (int j = 0; j < P; ++j) ynx[j] = y[(long long)(n - 1) * P + j];
 
   for (int t = n - 1; t >= 0; --t) {
-    // ---- predicted moments of step t -> shared memory (Pm's slot held W: its padding is zero either way)
+    // ---- predicted moments of step t -> shared memory (without T-bar Pm's slot held W: its padding is zero either way)
     if (t == 0) {
       const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
       for (int k = lane; k < M * M; k += 32) {
@@ -514,94 +582,89 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       }
     }
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
-    if (t == 0) {  // P0 may be any matrix: X needs P + P^T (for t >= 1 the taped P is symmetric: P + P^T = 2 P)
+    if (t == 0) {  // P0 may be any matrix: L-bar = W (P + P^T); for t >= 1 the taped P is symmetric: P + P^T = 2 P
       double S0[M];
       rowD_load<M>(S0, sm + L::Pm + i * LD, si);
 #pragma unroll
       for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD(sm + L::Pm, j, i));
+      if (observed) {  // lz = (P + P^T) Z^T rows
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          const double s = dot4<M>(0.0, [&](int j, double& x, double& y2) {
+            x = S0[j];
+            y2 = sm[L::Z + e * M + j];
+          });
+          if (act) sm[L::lz + i * P + e] = 2.0 * s;
+        }
+      }
       __syncwarp();
-      if (act) rowD_store<M>(sm + L::Pm + i * LD, si, S0);
+      if (NEED_T && act) rowD_store<M>(sm + L::Pm + i * LD, si, S0);
       __syncwarp();
     }
-    // ---- 1: X = 2 L P (tensor cores) -> Xb (with T-bar) or Pm's slot (only X Z^T is needed) ; Ps = sym(Pb) in place
-    // (row-wise work that does not depend on a tile product sits between its last mma and its store: a DMMA issues
-    //  once per ~16 cycles, the scheduler fills the gaps with the independent loads / DFMAs)
+    // ---- 1: Ps = sym(P-bar') = symU(L^T W of the step above) + sym(Mb Z), in place ; Cb += Ps
     cb += abi;
     {
-      double c4[4][4][2], Ps[M];
-      mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
-      rowD_load<M>(Ps, sm + L::Pb + i * LD, si);
+      double Ps[M];
+      rowD_load_symU<M>(Ps, sm + L::Pb, i, si);
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
-        Ps[j] = 0.5 * (Ps[j] + colD(sm + L::Pb, j, i));
-        Cb[j] += Ps[j];
+      for (int k = 0; k < P; ++k) {
+        const double mi = 0.5 * sm[L::Mb + i * P + k], zi = 0.5 * sm[L::Z + k * M + i];
+#pragma unroll
+        for (int j = 0; j < M; ++j) Ps[j] = fma(mi, sm[L::Z + k * M + j], fma(zi, sm[L::Mb + j * P + k], Ps[j]));
       }
-      mm32_store<LD>(sm + (NEED_T ? L::Xb : L::Pm), c4, 2.0, lane);  // Pm's fragment loads are behind the mma's
-      __syncwarp();  // every lane has read its row and column of Pb; X is visible
+#pragma unroll
+      for (int j = 0; j < M; ++j) Cb[j] += Ps[j];
+      __syncwarp();  // every lane has read its row and column of P-bar'
       if (act) rowD_store<M>(sm + L::Pb + i * LD, si, Ps);
     }
-    if (!NEED_T && observed) {  // lz = X Z^T rows
-      double Xr[M];
-      rowD_load<M>(Xr, sm + L::Pm + i * LD, si);
-#pragma unroll
-      for (int e = 0; e < P; ++e) {
-        const double s = dot4<M>(0.0, [&](int j, double& x, double& y) {
-          x = Xr[j];
-          y = sm[L::Z + e * M + j];
-        });
-        if (act) sm[L::lz + i * P + e] = s;
-      }
-    }
-    __syncwarp();  // Ps, lz visible; nobody reads X in Pm's slot any more
-    // ---- 2: W = Ps L (tensor cores) -> Pm's slot ; (T-bar) Lb = Ps X -> Xb's slot ; PK, Kb, T^T ab
-    double lbz[P], PK[P], Kb[P], abn;
+    __syncwarp();  // Ps visible
+    // ---- 2: W = Ps L (tensor cores) ; PK = Ps Kp, T^T ab (row-wise, independent of the product: they sit between its
+    //         last mma and its store - a DMMA issues once per ~16 cycles, the scheduler fills the gaps)
+    double PK[P], Kb[P], abn;
     {
       double c4[4][4][2], Psv[M];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
-      // independent of the product (pure register results; lz / Kp are stale but unused when nothing is observed)
-      rowD_load<M>(Psv, sm + L::Pb + i * LD, si);  // the lane's Ps row, once, for both consumers
+      rowD_load<M>(Psv, sm + L::Pb + i * LD, si);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        lbz[e] = NEED_T ? 0.0 : dot4<M>(0.0, [&](int k, double& x, double& y) {
+        PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y2) {  // (Kp is stale but unused when nothing is observed)
           x = Psv[k];
-          y = sm[L::lz + k * P + e];
-        });
-        PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y) {
-          x = Psv[k];
-          y = sm[L::Kp + k * P + e];
+          y2 = sm[L::Kp + k * P + e];
         });
       }
-      abn = dot4<M>(0.0, [&](int k, double& x, double& y) {
+      abn = dot4<M>(0.0, [&](int k, double& x, double& y2) {
         x = colD(sm + L::T, k, i);
-        y = sm[L::ab + k];
+        y2 = sm[L::ab + k];
       });
-      mm32_store<LD>(sm + L::W, c4, 1.0, lane);
-      if (NEED_T) {
-        mm32<false, false, LD>(c4, sm + L::Pb, sm + L::Xb, lane);
-        mm32_store<LD>(sm + L::Xb, c4, 1.0, lane);
-      }
+      mm32_store<LD>(sm + L::W, c4, 1.0, lane);  // without T-bar: Pm's slot (its fragment loads... none: P is not an operand)
     }
-    __syncwarp();  // W (and Lb) visible
-    if (NEED_T) {
-      double Lb[M];
-      rowD_load<M>(Lb, sm + L::Xb + i * LD, si);
+    __syncwarp();  // W visible
+    // ---- 2b: (T-bar) Tacc += W P + ab a^T / 2 ; L-bar Z^T = 2 W Mm (t = 0: W lz) ; Kb
+    if constexpr (NEED_T) {
+      mm32<false, false, LD, false>(Tacc, sm + L::W, sm + L::Pm, lane);  // P symmetric (t = 0: sym(P0))
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
-        Tb[NEED_T ? j : 0] += fma(abi, sm[L::a + j], Lb[j]);  // Tb += ab a^T + Lb
-      }
-      if (observed) {
+      for (int I = 0; I < TI; ++I) {
+        const double abI = 0.5 * sm[L::ab + 8 * I + fr];
 #pragma unroll
-        for (int e = 0; e < P; ++e)
-          lbz[e] = dot4<M>(0.0, [&](int j, double& x, double& y) {
-            x = Lb[j];
-            y = sm[L::Z + e * M + j];
-          });
+        for (int J = 0; J < TI; ++J) {
+          const double2 a2 = *reinterpret_cast<const double2*>(sm + L::a + 8 * J + 2 * fc);
+          Tacc[I][J][0] = fma(abI, a2.x, Tacc[I][J][0]);
+          Tacc[I][J][1] = fma(abI, a2.y, Tacc[I][J][1]);
+        }
       }
     }
     if (observed) {
+      double Wr[M];
+      rowD_load<M>(Wr, sm + L::W + i * LD, si);
+      const double* m2 = (t == 0) ? sm + L::lz : sm + L::Mm;
+      const double sc = (t == 0) ? 1.0 : 2.0;
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        double s = abi * g.v[e] - lbz[e];
+        const double lbz = sc * dot4<M>(0.0, [&](int k, double& x, double& y2) {
+          x = Wr[k];
+          y2 = m2[k * P + e];
+        });
+        double s = abi * g.v[e] - lbz;
 #pragma unroll
         for (int k = 0; k < P; ++k) s = fma(PK[k], sm[L::H + k * P + e] + sm[L::H + e * P + k], s);
         Kb[e] = s;
@@ -614,29 +677,29 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         }
       }
     }
-    // ---- 3: Pb' = L^T W (tensor cores) -> Pb (Ps rows were last read above, by their owners, before this point in
-    //         program order of every lane; the store follows the last mma, which all lanes execute together)
-    __syncwarp();  // Kb visible; all row reads of Ps done
+    // ---- 3: L^T W (tensor cores, upper tiles) -> Pb (Ps rows were last read above, by their owners, before this point
+    //         in program order of every lane; the store follows the last mma, which all lanes execute together)
+    __syncwarp();  // Kb visible; all row reads of Ps and W done
     double c4p[4][4][2];
-    mm32<true, false, LD>(c4p, Lsrc, sm + L::W, lane);  // stored after the row-wise block below (independent of it)
+    mm32<true, false, LD, true, true>(c4p, Lsrc, sm + L::W, lane);  // stored after the row-wise block below
     double vb[P], Fb[P * P], TMb[P];
     if (observed) {
       if (MK == MK_STEADY) {
         // vb = Kp^T ab - lb sym(Gss) v ; Gss-bar += TM^T Kb - lb/2 v v^T ; Fb = -lb/2 F^-T ; TMb = Kb Gss^T
 #pragma unroll
         for (int a2 = 0; a2 < P; ++a2) {
-          double s = dot4<M>(0.0, [&](int k, double& x, double& y) {
+          double s = dot4<M>(0.0, [&](int k, double& x, double& y2) {
             x = sm[L::Kp + k * P + a2];
-            y = sm[L::ab + k];
+            y2 = sm[L::ab + k];
           });
 #pragma unroll
           for (int b2 = 0; b2 < P; ++b2) s = fma(-0.5 * lb * (Gss[a2 * P + b2] + Gss[b2 * P + a2]), g.v[b2], s);
           vb[a2] = s;
 #pragma unroll
           for (int b2 = 0; b2 < P; ++b2) {
-            const double q1 = dot4<M>(Gb[a2 * P + b2], [&](int k, double& x, double& y) {
+            const double q1 = dot4<M>(Gb[a2 * P + b2], [&](int k, double& x, double& y2) {
               x = sm[L::TMs + k * P + a2];
-              y = sm[L::Kb + k * P + b2];
+              y2 = sm[L::Kb + k * P + b2];
             });
             Gb[a2 * P + b2] = fma(-0.5 * lb * g.v[a2], g.v[b2], q1);
             Fb[a2 * P + b2] = -0.5 * lb * g.Fi[b2 * P + a2];
@@ -650,42 +713,35 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           TMb[e] = s;
         }
       } else {
-      double Q1[P * P];
+        double Q1[P * P];
 #pragma unroll
-      for (int a2 = 0; a2 < P; ++a2) {
-        vb[a2] = dot4<M>(-lb * g.w[a2], [&](int k, double& x, double& y) {
-          x = sm[L::Kp + k * P + a2];
-          y = sm[L::ab + k];
-        });
-#pragma unroll
-        for (int b2 = 0; b2 < P; ++b2)
-          Q1[a2 * P + b2] = dot4<M>(0.0, [&](int k, double& x, double& y) {
+        for (int a2 = 0; a2 < P; ++a2) {
+          vb[a2] = dot4<M>(-lb * g.w[a2], [&](int k, double& x, double& y2) {
             x = sm[L::Kp + k * P + a2];
-            y = sm[L::Kb + k * P + b2];
+            y2 = sm[L::ab + k];
           });
-      }
 #pragma unroll
-      for (int a2 = 0; a2 < P; ++a2)
-#pragma unroll
-        for (int b2 = 0; b2 < P; ++b2) {
-          double s = -0.5 * lb * (g.Fi[b2 * P + a2] - g.w[a2] * g.w[b2]);
-#pragma unroll
-          for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
-          Fb[a2 * P + b2] = s;
+          for (int b2 = 0; b2 < P; ++b2)
+            Q1[a2 * P + b2] = dot4<M>(0.0, [&](int k, double& x, double& y2) {
+              x = sm[L::Kp + k * P + a2];
+              y2 = sm[L::Kb + k * P + b2];
+            });
         }
 #pragma unroll
-      for (int e = 0; e < P; ++e) {
-        double s = 0.0;
+        for (int a2 = 0; a2 < P; ++a2)
 #pragma unroll
-        for (int k = 0; k < P; ++k) s = fma(Kb[k], g.Fi[e * P + k], s);
-        TMb[e] = s;
-      }
-      }
-      if (NEED_T) {
+          for (int b2 = 0; b2 < P; ++b2) {
+            double s = -0.5 * lb * (g.Fi[b2 * P + a2] - g.w[a2] * g.w[b2]);
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
+            for (int k = 0; k < P; ++k) s = fma(-Q1[a2 * P + k], g.Fi[b2 * P + k], s);
+            Fb[a2 * P + b2] = s;
+          }
 #pragma unroll
-          for (int k = 0; k < P; ++k) Tb[NEED_T ? j : 0] = fma(TMb[k], sm[L::Mm + j * P + k], Tb[NEED_T ? j : 0]);
+        for (int e = 0; e < P; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < P; ++k) s = fma(Kb[k], g.Fi[e * P + k], s);
+          TMb[e] = s;
         }
       }
       if (act) {
@@ -693,29 +749,20 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         for (int e = 0; e < P; ++e) sm[L::TMb + i * P + e] = TMb[e];
       }
     }
-    mm32_store<LD>(sm + L::Pb, c4p, 1.0, lane);
-    __syncwarp();  // Pb' and TMb visible; ab's readers are done
-    // ---- 4: (observed) Mb = T^T TMb + Z^T Fb ; Pb' row += Mb Z ; ab' = T^T ab - Z^T vb
+    mm32_store<LD, true>(sm + L::Pb, c4p, 1.0, lane);
+    __syncwarp();  // L^T W and TMb visible; ab's readers are done
+    // ---- 4: (observed) Mb = T^T TMb + Z^T Fb (the rank-p part of P-bar) ; ab' = T^T ab - Z^T vb ; T-bar += TMb Mm^T
     if (observed) {
-      double Mb[P];
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        double s = dot4<M>(0.0, [&](int k, double& x, double& y) {
+        double s = dot4<M>(0.0, [&](int k, double& x, double& y2) {
           x = colD(sm + L::T, k, i);
-          y = sm[L::TMb + k * P + e];
+          y2 = sm[L::TMb + k * P + e];
         });
 #pragma unroll
         for (int k = 0; k < P; ++k) s = fma(sm[L::Z + k * M + i], Fb[k * P + e], s);
-        Mb[e] = s;
+        if (act) sm[L::Mb + i * P + e] = s;
       }
-      double Pbn[M];
-      rowD_load<M>(Pbn, sm + L::Pb + i * LD, si);
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) Pbn[j] = fma(Mb[k], sm[L::Z + k * M + j], Pbn[j]);
-      }
-      if (act) rowD_store<M>(sm + L::Pb + i * LD, si, Pbn);
 #pragma unroll
       for (int k = 0; k < P; ++k) abn = fma(-sm[L::Z + k * M + i], vb[k], abn);
 #pragma unroll
@@ -727,33 +774,70 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           if (lane != e) continue;
 #pragma unroll
           for (int j = 0; j < P; ++j) {
-            Hb[j] = dot4<M>(Hb[j] + Fb[e * P + j], [&](int k, double& x, double& y) {  // + Kp^T Ps Kp
+            Hb[j] = dot4<M>(Hb[j] + Fb[e * P + j], [&](int k, double& x, double& y2) {  // + Kp^T Ps Kp
               x = sm[L::Kp + k * P + e];
-              y = sm[L::PK + k * P + j];
+              y2 = sm[L::PK + k * P + j];
             });
           }
         }
       }
+      if constexpr (NEED_T) {
+#pragma unroll
+        for (int I = 0; I < TI; ++I) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const double tI = 0.5 * sm[L::TMb + (8 * I + fr) * P + k];
+#pragma unroll
+            for (int J = 0; J < TI; ++J) {
+              Tacc[I][J][0] = fma(tI, sm[L::Mm + (8 * J + 2 * fc) * P + k], Tacc[I][J][0]);
+              Tacc[I][J][1] = fma(tI, sm[L::Mm + (8 * J + 2 * fc + 1) * P + k], Tacc[I][J][1]);
+            }
+          }
+        }
+      }
+    } else if (act) {
+#pragma unroll
+      for (int e = 0; e < P; ++e) sm[L::Mb + i * P + e] = 0.0;
     }
     if (act) sm[L::ab + i] = abn;
     abi = abn;
     __syncwarp();
   }
-  // ---- write-out (row i by lane i)
-  if (act) {
-    if (A.ga0) A.ga0[u * M + i] = abi;
+  // ---- write-out (row i by lane i): P-bar = symU(L^T W) + Mb Z of step 0
+  {
+    double Pf[M];
+    rowD_load_symU<M>(Pf, sm + L::Pb, i, si);
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      if (MK == MK_STEADY) {
-        if (A.gPss) A.gPss[u * M * M + i * M + j] = sm[L::Pb + i * LD + ((((j >> 1) ^ si) << 1) | (j & 1))];
-        if (A.gP0) A.gP0[u * M * M + i * M + j] = 0.0;
-      } else if (A.gP0) {
-        A.gP0[u * M * M + i * M + j] = sm[L::Pb + i * LD + ((((j >> 1) ^ si) << 1) | (j & 1))];
-      }
-      if (NEED_T && A.gT) A.gT[u * M * M + i * M + j] = Tb[NEED_T ? j : 0];
-      if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
+    for (int k = 0; k < P; ++k) {
+      const double mi = sm[L::Mb + i * P + k];
+#pragma unroll
+      for (int j = 0; j < M; ++j) Pf[j] = fma(mi, sm[L::Z + k * M + j], Pf[j]);
     }
-    if (A.gc) A.gc[u * M + i] = cb;
+    if (act) {
+      if (A.ga0) A.ga0[u * M + i] = abi;
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        if (MK == MK_STEADY) {
+          if (A.gPss) A.gPss[u * M * M + i * M + j] = Pf[j];
+          if (A.gP0) A.gP0[u * M * M + i * M + j] = 0.0;
+        } else if (A.gP0) {
+          A.gP0[u * M * M + i * M + j] = Pf[j];
+        }
+        if (A.gC) A.gC[u * M * M + i * M + j] = Cb[j];
+      }
+      if (A.gc) A.gc[u * M + i] = cb;
+    }
+  }
+  if (NEED_T && A.gT) {
+#pragma unroll
+    for (int I = 0; I < TI; ++I)
+#pragma unroll
+      for (int J = 0; J < TI; ++J)
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int row = 8 * I + fr, col = 8 * J + 2 * fc + x;
+          if (row < M && col < M) A.gT[u * M * M + row * M + col] = 2.0 * Tacc[I][J][x];
+        }
   }
   if (lane < P) {
     if (A.gd) A.gd[u * P + lane] = db;
