@@ -55,8 +55,13 @@ struct RowsDLayout {
   // adjoint only: W = Ps L lives in Pm's slot (without T-bar nothing reads P after the gain) or in its own (with T-bar:
   // T-bar += 2 W P).  lz: (P0 + P0^T) Z^T, t = 0 only.  Mb: the rank-p part of P-bar, kept apart from L^T W.
   static constexpr int Pb = END_COMMON, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MP32, lz = PK + MPE, TMs = lz + MPE,
-                       ab = TMs + MPE, Mb = ab + 32, tp = Mb + MPE, Xb = tp + KTP, END_BWD = Xb + (NEED_T ? MS : 0),
+                       ab = TMs + MPE, Mb = ab + 32, Xb = Mb + MPE, END_BWD = Xb + (NEED_T ? MS : 0),
                        W = NEED_T ? Xb : Pm;
+  // The tape entry of the NEXT step is staged in Lm's slot, which is free from the last product of a step (phase 3) to
+  // the next step's gain: no staging buffer of its own, 37.5 instead of 41.5 KB per unit = 6 instead of 5 units per SM.
+  // It clobbers the zero padding of Lm's first rows: the adjoint's gain rewrites its rows including the padding columns.
+  static constexpr int tp = Lm;
+  static_assert(KTP <= M * LD, "the staged tape entry must not reach the zero rows of Lm");
   static constexpr int fwd_doubles = (END_FWD + 1) & ~1, bwd_doubles = (END_BWD + 1) & ~1;
 };
 
@@ -210,7 +215,7 @@ struct RowDGain {
 // v, Mm | TM, F, F^-1, w, quad, Kp, Lm for an observed step (row-per-lane).  Leaves Mm, Kp, Lm in shared memory (visible
 // after the trailing sync); returns the lane's Kp row and (every lane) v, F^-1, w.
 // MK_STEADY: the gain matrix is the fixed Gss = (Z Pss Z^T + H)^-1 instead of F^-1 (F is still factorised for log det).
-template <int M, int P, int MK, class L>
+template <int M, int P, int MK, class L, bool PADL = false>
 __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P],
                                            const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g,
                                            bool full_det = false) {
@@ -317,6 +322,10 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
         lk.y = fma(-g.Kp[e], z.y, lk.y);
       }
       if (act) *rowD_chunk(lr, sC, k) = lk;
+    }
+    if (PADL && act) {  // the row's zero padding (Lm's slot doubles as the adjoint's tape staging buffer)
+#pragma unroll
+      for (int k = M / 2; k < 16; ++k) *rowD_chunk(lr, sC, k) = make_double2(0.0, 0.0);
     }
   }
   if (act) {
@@ -561,8 +570,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         }
         rowD_store<M>(sm + L::Pm + i * LD, si, Pr);
       }
-      __syncwarp();  // every lane has read the staging buffer: refill it for step t-1
-      if (t >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(t - 2) * KT, lane);
+      // (every lane has read the staging buffer before the sync below; the gain may overwrite it)
     }
     __syncwarp();
 #pragma unroll
@@ -575,7 +583,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
     for (int j = 0; j < P; ++j) observed = observed && (yt[j] == yt[j]);
     if (observed) {
-      rowsD_gain<M, P, MK, L>(sm, yt, A.d_sign, dv, Gss, i, act, g);
+      rowsD_gain<M, P, MK, L, true>(sm, yt, A.d_sign, dv, Gss, i, act, g);
       if (MK == MK_STEADY && act) {
 #pragma unroll
         for (int e = 0; e < P; ++e) sm[L::TMs + i * P + e] = g.TM[e];  // read by every lane in phase 3 (after syncs)
@@ -603,8 +611,8 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     // ---- 1: Ps = sym(P-bar') = symU(L^T W of the step above) + sym(Mb Z), in place ; Cb += Ps
     cb += abi;
+    double Ps[M];  // without T-bar the row stays in registers for phase 2; with it (64 more accumulators) it is re-read
     {
-      double Ps[M];
       rowD_load_symU<M>(Ps, sm + L::Pb, i, si);
 #pragma unroll
       for (int k = 0; k < P; ++k) {
@@ -622,13 +630,13 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     //         last mma and its store - a DMMA issues once per ~16 cycles, the scheduler fills the gaps)
     double PK[P], Kb[P], abn;
     {
-      double c4[4][4][2], Psv[M];
+      double c4[4][4][2];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
-      rowD_load<M>(Psv, sm + L::Pb + i * LD, si);
+      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD, si);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y2) {  // (Kp is stale but unused when nothing is observed)
-          x = Psv[k];
+          x = Ps[k];
           y2 = sm[L::Kp + k * P + e];
         });
       }
@@ -682,6 +690,8 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     __syncwarp();  // Kb visible; all row reads of Ps and W done
     double c4p[4][4][2];
     mm32<true, false, LD, true, true>(c4p, Lsrc, sm + L::W, lane);  // stored after the row-wise block below
+    __syncwarp();  // last use of Lm in this step: stage the tape entry of step t-1 in its slot
+    if (t >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(t - 2) * KT, lane);
     double vb[P], Fb[P * P], TMb[P];
     if (observed) {
       if (MK == MK_STEADY) {
