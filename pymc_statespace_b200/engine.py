@@ -112,7 +112,9 @@ class BatchedKalman:
 
     # ------------------------------------------------------------------ forward
     def forward(self, y, a0, P0, T, Z, R, H, Q, c=None, d=None, outputs=("loglik",), save_for_backward=False,
-                check_info=False) -> Dict[str, torch.Tensor]:
+                check_info=False, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``out``: optional caller-owned result buffers (name -> contiguous tensor of the documented shape, "info"
+        included); anything not given is allocated.  Lets a captured CUDA graph write straight into a staging buffer."""
         if y.ndim >= 2 and y.shape[-1] == 1 and y.shape[-2] == self.p and y.ndim in (3, 4) and y.shape[-3] == self.n:
             y = y[..., 0]  # reference layout data[n,p,1]
         if not (y.is_cuda and y.dtype == torch.float64):
@@ -141,12 +143,12 @@ class BatchedKalman:
         U, n, m, p = self.units, self.n, self.m, self.p
         shapes = {"loglik": (U,), "ll_obs": (U, n), "filtered_states": (U, n, m), "predicted_states": (U, n + 1, m),
                   "filtered_covs": (U, n, m, m), "predicted_covs": (U, n + 1, m, m)}
-        out = {}
+        given, out = (out or {}), {}
         for k in outputs:
             if k not in shapes:
                 raise KeyError(k)
-            out[k] = torch.empty(shapes[k], dtype=torch.float64, device=self.device)
-        out["info"] = torch.empty((U,), dtype=torch.int32, device=self.device)
+            out[k] = self._buffer(given.get(k), shapes[k], torch.float64, k)
+        out["info"] = self._buffer(given.get("info"), (U,), torch.int32, "info")
         ins = KfbInputs(*[_ptr(held[k]) for k in ("y",) + MATRIX_NAMES])
         outs = KfbOutputs(*[_ptr(out.get(k)) for k in ("loglik", "ll_obs", "filtered_states", "predicted_states",
                                                         "filtered_covs", "predicted_covs", "info")])
@@ -158,6 +160,13 @@ class BatchedKalman:
         if check_info:
             self.raise_on_info(out["info"])
         return out
+
+    def _buffer(self, t, shape, dtype, name):
+        if t is None:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        if not (t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.numel() == int(torch.Size(shape).numel())):
+            raise TypeError(f"{name}: expected a contiguous {dtype} CUDA buffer of {tuple(shape)}")
+        return t.view(shape)
 
     @staticmethod
     def raise_on_info(info: torch.Tensor):
@@ -179,8 +188,9 @@ class BatchedKalman:
 
     # ------------------------------------------------------------------ backward
     def backward(self, g_loglik: Optional[torch.Tensor] = None, g_ll_obs: Optional[torch.Tensor] = None,
-                 wrt: Iterable[str] = MATRIX_NAMES) -> Dict[str, torch.Tensor]:
-        """Per-unit gradients of  sum_u (g_loglik[u] * loglik[u] + sum_t g_ll_obs[u,t] * ll_obs[u,t])."""
+                 wrt: Iterable[str] = MATRIX_NAMES, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Per-unit gradients of  sum_u (g_loglik[u] * loglik[u] + sum_t g_ll_obs[u,t] * ll_obs[u,t]).
+        ``out``: optional caller-owned gradient buffers (see ``forward``)."""
         if not self._saved:
             raise RuntimeError("backward() needs a preceding forward(..., save_for_backward=True)")
         U, n = self.units, self.n
@@ -190,7 +200,7 @@ class BatchedKalman:
             if k not in shapes:
                 raise KeyError(k)
             lead = (U, n) if k in self.time_varying else (U,)
-            grads[k] = torch.empty(lead + shapes[k], dtype=torch.float64, device=self.device)
+            grads[k] = self._buffer((out or {}).get(k), lead + shapes[k], torch.float64, k)
         for name, t in (("g_loglik", g_loglik), ("g_ll_obs", g_ll_obs)):
             if t is not None and not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
                 raise TypeError(f"{name}: expected a contiguous float64 CUDA tensor")

@@ -86,6 +86,15 @@ class BaseFilter:
         from .torch_op import kalman_filter_torch
 
         as_numpy = not any(isinstance(x, torch.Tensor) for x in (data, a0, P0, T, Z, R, H, Q, c, d) if x is not None)
+        if as_numpy:
+            if not torch.cuda.is_available():
+                raise RuntimeError("pymc_statespace_b200 filters need a CUDA device (no CPU fallback)")
+            from .seam import filter_numpy
+
+            # numpy in, numpy out: one pinned upload, the kernels and one download replayed as a CUDA graph
+            return filter_numpy(self, *[np.asarray(x, dtype=np.float64) for x in (data, a0, P0, T, Z, R, H, Q)],
+                                None if c is None else np.asarray(c, dtype=np.float64),
+                                None if d is None else np.asarray(d, dtype=np.float64), device=self.device)
         dev = torch.device(self.device) if self.device is not None else None
         if dev is None:
             for x in (data, a0, P0, T, Z, R, H, Q):

@@ -77,8 +77,10 @@ class KalmanFilterOp(Op):
         return [(n, m, 1), (n + 1, m, 1), (n, m, m), (n + 1, m, m), (), (n,)]
 
     def perform(self, node, inputs, output_storage):
+        from .seam import filter_numpy
+
         base, c, d = self._split([np.asarray(x, dtype=np.float64) for x in inputs])
-        outs = self._filter()._eager(*base, c, d)
+        outs = filter_numpy(self._filter(), *base, c, d)  # one replayed CUDA graph per call (seam.SeamGraph)
         for storage, o in zip(output_storage, outs):
             storage[0] = np.asarray(o, dtype=np.float64)
 
@@ -126,24 +128,20 @@ class KalmanFilterGradOp(Op):
         return [shapes[1 + i] for i in range(n_mats)]
 
     def perform(self, node, inputs, output_storage):
-        import torch
-
         from .filters import FILTER_FACTORY
-        from .torch_op import kalman_logp_grads
+        from .seam import logp_grads_numpy
 
         arrs = [np.asarray(x, dtype=np.float64) for x in inputs]
         g_ll, g_llobs = arrs[-2], arrs[-1]
         arrs = arrs[:-2]
         flt = FILTER_FACTORY[self.kind]()
         flt.strict_reference = self.strict_reference
-        dev = torch.device("cuda", torch.cuda.current_device())
-        names = _input_names(self.has_c, self.has_d)[1:]
-        ts = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in arrs]
-        # one loglik-only forward (hot-path kernels + tape) and the adjoint kernel; no full-output pass, no autograd tape
-        _, grads = kalman_logp_grads(flt, ts[0], dict(zip(names, ts[1:])), g_loglik=g_ll,
-                                     g_ll_obs=(g_llobs if np.any(g_llobs != 0.0) else None))
-        for storage, k in zip(output_storage, names):
-            storage[0] = grads[k].detach().cpu().numpy()
+        names = _input_names(self.has_c, self.has_d)
+        # one loglik-only forward (hot-path kernels + tape) and the adjoint kernel, replayed as ONE CUDA graph with a single
+        # pinned upload / download (seam.SeamGraph); no full-output pass, no autograd tape
+        _, grads = logp_grads_numpy(flt, dict(zip(names, arrs)), g_loglik=g_ll, g_ll_obs=g_llobs)
+        for storage, k in zip(output_storage, names[1:]):
+            storage[0] = grads[k]
 
 
 def build_symbolic_graph(flt, data, a0, P0, T, Z, R, H, Q, c=None, d=None):
