@@ -235,3 +235,47 @@ def test_pytensor_op_perform_paths_without_pytensor():
             if kind == "cholesky" and name in ("P0", "H"):
                 continue  # gauge of the symmetric inputs differs for the Cholesky-based filter
             assert rel_err(s[0], want) < 1e-8, (kind, name)
+
+
+def test_seam_graph_is_reused_and_matches_oracle():
+    """numpy in / numpy out at one model per call (seam.SeamGraph): the cached CUDA graph of a geometry is replayed with
+    new values, with and without a per-step cotangent, with c / d and time-varying T; failures still raise."""
+    from pymc_statespace_b200 import seam
+    from pymc_statespace_b200.filters import StandardFilter, UnivariateFilter
+
+    rng = np.random.default_rng(11)
+    n, m, p, r = 30, 3, 2, 2
+    flt = StandardFilter()
+    seam._CACHE.clear()
+    for rep in range(3):
+        y, a0, P0, T, Z, R, H, Q = random_system(rng, m, p, r, n, n_missing=2)
+        c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+        arrays = {"data": y, "a0": a0, "P0": P0, "T": T, "Z": Z, "R": R, "H": H, "Q": Q, "c": c, "d": d}
+        outs = flt.build_graph(y, a0, P0, T, Z, R, H, Q, c=c, d=d)
+        ref = kn.kalman_filter("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d)
+        for o, e in zip(outs, ref):
+            assert rel_err(np.asarray(o), np.asarray(e)) < 1e-9
+        w, wt = float(rng.normal()), rng.normal(size=n)
+        _, g1 = kt.loglik_and_grads("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d)
+        _, g2 = kt.loglik_and_grads("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d, g_ll_obs=wt)
+        for g_obs in (None, wt):
+            ll, g = seam.logp_grads_numpy(flt, arrays, g_loglik=w, g_ll_obs=g_obs)
+            assert abs(ll - float(ref[4])) < 1e-9 * abs(float(ref[4]))
+            for k in ("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d"):
+                want = w * g1[k] + (0.0 if g_obs is None else g2[k])
+                assert g[k].shape == arrays[k].shape
+                assert rel_err(g[k], np.asarray(want).reshape(g[k].shape)) < 1e-8, (k, rep, g_obs is None)
+    assert len(seam._CACHE) == 3  # six outputs ; grad ; grad with g_ll_obs - each captured once, replayed three times
+    # time-varying T (time-first, filters/utilities.py:9-14) is its own geometry
+    y, a0, P0, T, Z, R, H, Q = random_system(rng, m, p, r, n)
+    Tt = np.repeat(T[None], n, axis=0) * (1.0 + 0.05 * rng.normal(size=(n, 1, 1)))
+    ll, g = seam.logp_grads_numpy(flt, {"data": y, "a0": a0, "P0": P0, "T": Tt, "Z": Z, "R": R, "H": H, "Q": Q})
+    lref, gref = kt.loglik_and_grads("standard", y, a0, P0, Tt, Z, R, H, Q)
+    assert abs(ll - lref) < 1e-9 * abs(lref) and g["T"].shape == Tt.shape
+    assert rel_err(g["T"], np.asarray(gref["T"])) < 1e-8
+    # a partially missing row: LinAlgError for the standard filter (SURVEY A.2-Q2), fine for the univariate one
+    yb = y.copy()
+    yb[4, 0, 0] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        flt.build_graph(yb, a0, P0, T, Z, R, H, Q)
+    UnivariateFilter().build_graph(yb, a0, P0, T, Z, R, H, Q)
