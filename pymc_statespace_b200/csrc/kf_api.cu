@@ -34,6 +34,29 @@ coopT_launch_fn coopT_launcher_m28(int p, int mk);
 coopT_launch_fn coopT_launcher_m30(int p, int mk);
 coopT_launch_fn coopT_launcher_m32(int p, int mk);
 
+dare_launch_fn dareD_launcher_m18(int p);
+dare_launch_fn dareD_launcher_m20(int p);
+dare_launch_fn dareD_launcher_m22(int p);
+dare_launch_fn dareD_launcher_m24(int p);
+dare_launch_fn dareD_launcher_m26(int p);
+dare_launch_fn dareD_launcher_m28(int p);
+dare_launch_fn dareD_launcher_m30(int p);
+dare_launch_fn dareD_launcher_m32(int p);
+
+dare_launch_fn find_dareD_launcher(int m, int p) {
+  switch (m) {
+    case 18: return dareD_launcher_m18(p);
+    case 20: return dareD_launcher_m20(p);
+    case 22: return dareD_launcher_m22(p);
+    case 24: return dareD_launcher_m24(p);
+    case 26: return dareD_launcher_m26(p);
+    case 28: return dareD_launcher_m28(p);
+    case 30: return dareD_launcher_m30(p);
+    case 32: return dareD_launcher_m32(p);
+    default: return nullptr;
+  }
+}
+
 coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
   switch (m) {
     case 5: return coopT_launcher_m5(p, mk);
@@ -244,7 +267,8 @@ kfb_status kfb_forward(const kfb_desc* desc, const kfb_inputs* in, const kfb_out
     D.T = MatArg{in->T, desc->T_bs, 0}; D.Z = MatArg{in->Z, desc->Z_bs, 0}; D.H = MatArg{in->H, desc->H_bs, 0};
     D.C = A.C;
     D.Pss = (double*)(ws + pl.off_Pss); D.Gss = (double*)(ws + pl.off_Gss); D.info = (int*)(ws + pl.off_dinfo);
-    e = launch_dare(D, false, s);
+    const dare_launch_fn fast = (desc->flags & KFB_FLAG_FORCE_COOP) ? nullptr : find_dareD_launcher(desc->m, desc->p);
+    e = fast ? fast(D, s) : launch_dare(D, false, s);  // even k_states 18..32, k_endog 1: tensor-core mapping (kf_rowsD.cuh)
     if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
     if (e != cudaSuccess) return cuda_fail(e);
   }

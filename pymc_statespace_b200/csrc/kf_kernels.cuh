@@ -260,6 +260,21 @@ __global__ void kf_dare_kernel(const __grid_constant__ DareArgs D, int arena_dou
 }
 cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s);
 
+// steady-state covariance on the warp-per-draw tensor-core mapping (kf_rowsD.cuh: rowsD_dare), even k_states 18..32
+template <int M, int P>
+__global__ void __launch_bounds__(128, 1) kf_dareD_kernel(const __grid_constant__ DareArgs D) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int per_unit = DareDLayout<M, P>::doubles;
+  const int warp = threadIdx.x >> 5;
+  const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (u >= D.nD) return;
+  rowsD_dare<M, P>(D.T.p + u * D.T.bs, D.Z.p + u * D.Z.bs, D.H.p + u * D.H.bs, D.C.p + u * D.C.bs, D.Pss + u * M * M,
+                   D.Gss + u * P * P, D.info ? D.info + u : nullptr, kf_dyn_smem + (size_t)warp * per_unit,
+                   threadIdx.x & 31);
+}
+typedef cudaError_t (*dare_launch_fn)(const DareArgs& D, cudaStream_t s);
+dare_launch_fn find_dareD_launcher(int m, int p);
+
 template <bool WARP>
 __global__ void __launch_bounds__(WARP ? 128 : 256) kf_smoother_kernel(const __grid_constant__ SmoothArgs S, int arena_doubles) {
   extern __shared__ __align__(16) double kf_dyn_smem[];

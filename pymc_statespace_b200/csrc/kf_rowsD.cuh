@@ -861,4 +861,184 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ steady state (DARE)
+// The same fixed-point iteration as kf_dare.cuh (Riccati recursion from above, then Newton-Hewer with squared-Smith
+// doubling; reference call: scipy.linalg.solve_discrete_are, filters/kalman_filter.py:384, utils/pytensor_scipy.py:28-35)
+// on the warp-per-draw tensor-core mapping of this file: a Riccati step IS the forward step above without data
+// (P' = L P L^T + Kp H Kp^T + C), a Newton-Hewer iterate solves P = L P L^T + (C + Kp H Kp^T) for the gain of the current
+// P, and a Smith doubling is three tile products (S1 = A X, X += S1 A^T, A <- A A).  Config 4 (k_states 30, 8,192 draws):
+// 99.5 ms on the generic CTA-per-draw kernels (29 % of a steady_state evaluation) -> see profiles/r2_ncu_rowsD.md.
+template <int M, int P>
+struct DareDLayout {
+  static constexpr int LD = rowsD_LD, MS = 32 * LD;
+  static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), MP32 = 32 * P;
+  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, X = Lm + MS, Xs = X + MS, Z = Xs + MS, H = Z + MPE,
+                       Mm = H + PP + (PP & 1), Kp = Mm + MP32, a = Kp + MPE, KH = a + 32, END = KH + MPE;
+  static constexpr int doubles = (END + 1) & ~1;
+};
+
+// acc <- D (the inverse of mm32_store)
+template <int LD>
+__device__ __forceinline__ void mm32_load(double (&acc)[4][4][2], const double* D, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int J = 0; J < 4; ++J) {
+      const double2 x = *reinterpret_cast<const double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1));
+      acc[I][J][0] = x.x;
+      acc[I][J][1] = x.y;
+    }
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+
+template <int M, int P>
+__device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp, const double* Cp, double* Pss, double* Gssg,
+                           int* info_out, double* sm, int lane) {
+  using L = DareDLayout<M, P>;
+  constexpr int LD = L::LD;
+  const bool act = lane < M;
+  const int i = act ? lane : 0;
+  const int si = rowsD_swz(i);
+  for (int k = lane; k < L::doubles; k += 32) sm[k] = 0.0;  // zero padding everywhere, a = 0
+  __syncwarp();
+  for (int k = lane; k < M * M; k += 32) {
+    const int rr = k / M, cc = k - rr * M;
+    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
+  }
+  for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
+  for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
+  double Cs[M];  // the lane's row of sym(C)
+  double scale = 1.0;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    Cs[j] = 0.5 * (Cp[i * M + j] + Cp[j * M + i]);
+    scale = fmax(scale, fmax(fabs(Cp[i * M + j]), fabs(Cp[j * M + i])));
+  }
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) scale = fmax(scale, fabs(Hp[k]));
+  scale = warp_max(scale);
+  if (act) sm[L::Pm + rowsD_el(i, i)] = 1.0e4 * scale;
+  __syncwarp();
+
+  double yt[P], dv[P], Gss[P * P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) yt[j] = dv[j] = 0.0;
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Gss[k] = 0.0;
+  RowDGain<M, P> g;
+  int info = 0;
+  // the lane's row of sym(Kp H Kp^T) + sym(C): the constant term of the step / of the Lyapunov equation
+  auto rhs_row = [&](double (&S)[M]) {
+    double KH[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      KH[j] = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) KH[j] = fma(g.Kp[k], sm[L::H + k * P + j], KH[j]);
+      if (act) sm[L::KH + i * P + j] = KH[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s = Cs[j];
+#pragma unroll
+      for (int k = 0; k < P; ++k) s = fma(0.5, fma(KH[k], sm[L::Kp + j * P + k], sm[L::KH + j * P + k] * g.Kp[k]), s);
+      S[j] = s;
+    }
+  };
+  // (1) Riccati recursion from above: every iterate >= P_ss, so every gain is stabilising
+  const int n0 = 2 * M + 24;
+  for (int k = 0; k < n0; ++k) {
+    rowsD_gain<M, P, MK_STD, L>(sm, yt, 1.0, dv, Gss, i, act, g);
+    if (!g.ok) info = 1;
+    double S[M], U[M];
+    rhs_row(S);
+    {
+      double c4[4][4][2];
+      mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Pm, lane);
+      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+      __syncwarp();
+      mm32<false, true, LD, true, true>(c4, sm + L::X, sm + L::Lm, lane);
+      mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
+    }
+    __syncwarp();
+    rowD_load_symU<M>(U, sm + L::X, i, si);
+#pragma unroll
+    for (int j = 0; j < M; ++j) S[j] += U[j];
+    if (act) rowD_store<M>(sm + L::Pm + i * LD, si, S);
+    __syncwarp();
+  }
+  // (2) Newton-Hewer: P <- Lyapunov(L(P), C + Kp H Kp^T), each Lyapunov equation by squared-Smith doubling
+  bool converged = false;
+  for (int it = 0; it < 60 && !converged && info == 0; ++it) {
+    rowsD_gain<M, P, MK_STD, L>(sm, yt, 1.0, dv, Gss, i, act, g);
+    if (!g.ok) { info = 1; break; }
+    {
+      double S[M];
+      rhs_row(S);
+      if (act) rowD_store<M>(sm + L::Xs + i * LD, si, S);
+    }
+    __syncwarp();
+    bool ok = false;
+    for (int db = 0; db < 64; ++db) {  // Xs <- sum_k A^k Xs A^kT, A = Lm (destroyed)
+      double Ar[M], mx = 0.0;
+      rowD_load<M>(Ar, sm + L::Lm + i * LD, si);
+#pragma unroll
+      for (int j = 0; j < M; ++j) mx = fmax(mx, fabs(Ar[j]));
+      mx = warp_max(mx);
+      if (!(mx < 1.0e150)) break;
+      if (mx < 1.0e-11) { ok = true; break; }
+      double c4[4][4][2];
+      mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Xs, lane);  // S1 = A Xs
+      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+      __syncwarp();
+      mm32_load<LD>(c4, sm + L::Xs, lane);
+      mm32<false, true, LD, false>(c4, sm + L::X, sm + L::Lm, lane);  // Xs += S1 A^T
+      mm32_store<LD>(sm + L::Xs, c4, 1.0, lane);
+      mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Lm, lane);  // A <- A A
+      mm32_store<LD>(sm + L::Lm, c4, 1.0, lane);
+      __syncwarp();
+    }
+    if (!ok) { info = 1; break; }
+    double Pn[M], Po[M], diff = 0.0, mag = 0.0;
+    rowD_load<M>(Pn, sm + L::Xs + i * LD, si);
+    rowD_load<M>(Po, sm + L::Pm + i * LD, si);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      diff = fmax(diff, fabs(Pn[j] - Po[j]));
+      mag = fmax(mag, fabs(Pn[j]));
+      Pn[j] = 0.5 * (Pn[j] + colD(sm + L::Xs, j, i));  // symmetrise: keeps the iteration on the symmetric manifold
+    }
+    diff = warp_max(diff);
+    mag = warp_max(mag);
+    if (act) rowD_store<M>(sm + L::Pm + i * LD, si, Pn);
+    __syncwarp();
+    converged = diff <= 4.0e-15 * mag;
+  }
+  if (!converged) info = 1;
+  // Gss = (Z Pss Z^T + H)^-1
+  rowsD_gain<M, P, MK_STD, L>(sm, yt, 1.0, dv, Gss, i, act, g);
+  if (!g.ok) info = 1;
+  if (act) {
+    double Pr[M];
+    rowD_load<M>(Pr, sm + L::Pm + i * LD, si);
+#pragma unroll
+    for (int j = 0; j < M; ++j) Pss[i * M + j] = info ? nan("") : Pr[j];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < P * P; ++k) Gssg[k] = info ? nan("") : g.Fi[k];
+    if (info_out) *info_out = info;
+  }
+}
+
 }  // namespace kfb

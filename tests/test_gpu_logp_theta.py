@@ -441,3 +441,41 @@ def test_sizes_between_instantiations_are_padded_exactly(period, kind):
     # the full-output call reports the model's own states only
     out = padded.filter(th, outputs=("filtered_states", "predicted_covs", "loglik"))
     assert tuple(out["filtered_states"].shape) == (B, n, m) and tuple(out["predicted_covs"].shape) == (B, n + 1, m, m)
+
+
+@pytest.mark.parametrize("m", [18, 30, 32])
+def test_tensor_core_dare_matches_generic_solver_and_reports_failure(m):
+    """steady_state at even k_states 18..32, k_endog 1: the forward DARE solve runs on the warp-per-draw tensor-core
+    mapping (kf_rowsD.cuh: rowsD_dare).  Same fixed point as the generic solver (force_coop) and as scipy's
+    solve_discrete_are (the oracle), and an unobservable explosive state is reported as KFB_INFO_DARE_FAILED."""
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KFB_INFO_DARE_FAILED
+    from oracle import kalman_numpy as kn
+    from tests.helpers import random_system
+
+    rng = np.random.default_rng(300 + m)
+    B, n, p, r = 5, 12, 1, 3
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1) for _ in range(B)]
+    Ts = np.stack([s[3] for s in systems])
+    Ts[3] = 0.0
+    Ts[3][np.arange(m), np.arange(m)] = 0.5
+    Ts[3][m - 1, m - 1] = 1.5                      # explosive state ...
+    Zs = np.stack([s[4] for s in systems])
+    Zs[3][0, m - 1] = 0.0                          # ... that is not observed (and T is diagonal): no stabilising solution
+    f = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")  # noqa: E731
+    stack = lambda i: f(np.stack([s[i] for s in systems]))  # noqa: E731
+    y = systems[0][0]
+    res = {}
+    for force in (False, True):
+        bk = BatchedKalman("steady_state", n, m, p, r, n_draws=B, force_coop=force)
+        out = bk.forward(f(y[..., 0]), stack(1), stack(2), f(Ts), f(Zs), stack(5), stack(6), stack(7))
+        res[force] = (out["loglik"].cpu().numpy(), out["info"].cpu().numpy())
+    for force in (False, True):
+        ll, info = res[force]
+        assert info[3] == KFB_INFO_DARE_FAILED and np.isnan(ll[3]), force
+        assert (np.delete(info, 3) == 0).all()
+    ok = [0, 1, 2, 4]
+    assert np.abs(res[False][0][ok] - res[True][0][ok]).max() < 1e-10 * np.abs(res[True][0][ok]).max()
+    for b in (0, 4):
+        ref = kn.kalman_filter("steady_state", y, *systems[b][1:])
+        assert abs(res[False][0][b] - float(ref[4])) < 1e-9 * abs(float(ref[4]))
