@@ -25,6 +25,10 @@ coopT_launch_fn coopT_launcher_m5(int p, int mk);
 coopT_launch_fn coopT_launcher_m6(int p, int mk);
 coopT_launch_fn coopT_launcher_m7(int p, int mk);
 coopT_launch_fn coopT_launcher_m8(int p, int mk);
+coopT_launch_fn coopT_launcher_m10(int p, int mk);
+coopT_launch_fn coopT_launcher_m12(int p, int mk);
+coopT_launch_fn coopT_launcher_m14(int p, int mk);
+coopT_launch_fn coopT_launcher_m16(int p, int mk);
 coopT_launch_fn coopT_launcher_m18(int p, int mk);
 coopT_launch_fn coopT_launcher_m20(int p, int mk);
 coopT_launch_fn coopT_launcher_m22(int p, int mk);
@@ -34,6 +38,10 @@ coopT_launch_fn coopT_launcher_m28(int p, int mk);
 coopT_launch_fn coopT_launcher_m30(int p, int mk);
 coopT_launch_fn coopT_launcher_m32(int p, int mk);
 
+dare_launch_fn dareD_launcher_m10(int p);
+dare_launch_fn dareD_launcher_m12(int p);
+dare_launch_fn dareD_launcher_m14(int p);
+dare_launch_fn dareD_launcher_m16(int p);
 dare_launch_fn dareD_launcher_m18(int p);
 dare_launch_fn dareD_launcher_m20(int p);
 dare_launch_fn dareD_launcher_m22(int p);
@@ -45,6 +53,10 @@ dare_launch_fn dareD_launcher_m32(int p);
 
 dare_launch_fn find_dareD_launcher(int m, int p) {
   switch (m) {
+    case 10: return dareD_launcher_m10(p);
+    case 12: return dareD_launcher_m12(p);
+    case 14: return dareD_launcher_m14(p);
+    case 16: return dareD_launcher_m16(p);
     case 18: return dareD_launcher_m18(p);
     case 20: return dareD_launcher_m20(p);
     case 22: return dareD_launcher_m22(p);
@@ -63,6 +75,10 @@ coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
     case 6: return coopT_launcher_m6(p, mk);
     case 7: return coopT_launcher_m7(p, mk);
     case 8: return coopT_launcher_m8(p, mk);
+    case 10: return coopT_launcher_m10(p, mk);
+    case 12: return coopT_launcher_m12(p, mk);
+    case 14: return coopT_launcher_m14(p, mk);
+    case 16: return coopT_launcher_m16(p, mk);
     case 18: return coopT_launcher_m18(p, mk);
     case 20: return coopT_launcher_m20(p, mk);
     case 22: return coopT_launcher_m22(p, mk);

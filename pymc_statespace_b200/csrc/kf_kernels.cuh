@@ -198,8 +198,11 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kf_rowsU_kernel(const __grid
 
 // Fused row-per-lane, warp-per-unit programs for large systems with the m^3 products on the FP64 tensor cores
 // (kf_rowsD.cuh); MK = MK_STD or MK_STEADY.  BWD = adjoint, NEED_T = with T-bar.
+#ifndef KFB_ROWSH_MINB
+#define KFB_ROWSH_MINB 4  // 16 x 16 tiles (k_states 10..16): 16 warps per SM, <= 128 registers (seasonal period 12: 3 -> 273 ms, 4 -> 277, 5 -> 295, 6 -> 311)
+#endif
 template <int M, int P, int MK, bool BWD, bool NEED_T>
-__global__ void __launch_bounds__(128, 1) kf_rowsD_kernel(const __grid_constant__ KfArgs A) {
+__global__ void __launch_bounds__(128, M <= 16 ? KFB_ROWSH_MINB : 1) kf_rowsD_kernel(const __grid_constant__ KfArgs A) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   constexpr int per_unit = BWD ? RowsDLayout<M, P, NEED_T>::bwd_doubles : RowsDLayout<M, P, false>::fwd_doubles;
   const int warp = threadIdx.x >> 5;
@@ -262,7 +265,7 @@ cudaError_t launch_dare(const DareArgs& D, bool bwd, cudaStream_t s);
 
 // steady-state covariance on the warp-per-draw tensor-core mapping (kf_rowsD.cuh: rowsD_dare), even k_states 18..32
 template <int M, int P>
-__global__ void __launch_bounds__(128, 1) kf_dareD_kernel(const __grid_constant__ DareArgs D) {
+__global__ void __launch_bounds__(128, M <= 16 ? 4 : 1) kf_dareD_kernel(const __grid_constant__ DareArgs D) {
   extern __shared__ __align__(16) double kf_dyn_smem[];
   constexpr int per_unit = DareDLayout<M, P>::doubles;
   const int warp = threadIdx.x >> 5;

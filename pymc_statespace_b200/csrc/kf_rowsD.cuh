@@ -1,61 +1,48 @@
-// kf_rowsD.cuh - large systems (16 < k_states <= 32, even; k_endog <= 3; MK_STD; static matrices; shared observation
-// stream; config 4 of BASELINE.json: trend + seasonal, k_states = 30): one WARP per unit, the m x m x m products on the
-// FP64 TENSOR CORES (mma.sync.m8n8k4.f64, "DMMA"), everything else row-per-lane as in kf_rows.cuh / kf_rowsL.cuh.
+// kf_rowsD.cuh - mid-size and large systems (even k_states 10..32; k_endog = 1 instantiated; MK_STD / MK_STEADY; static
+// matrices; shared observation stream; config 4 of BASELINE.json: trend + seasonal, k_states = 30): one WARP per unit, the
+// m x m x m products on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, "DMMA"), everything else row-per-lane as in kf_rows.cuh.
 //
 // Why: with DFMA every multiply-add needs at least one operand from shared memory and a broadcast load delivers one
-// double per wavefront, so the warp-per-unit DFMA kernel (kf_rowsL.cuh) sits at 94 % of the shared-memory wavefront
-// peak with the fp64 pipe 35 % active (profiles/r1_ncu_rowsL.md).  A DMMA consumes one A and one B element per lane for
-// eight multiply-adds per lane, and a fragment is reused for four tiles: ~0.06 shared-memory operands per multiply-add.
-// tools/dmma_probe.cu measured 37.1 TFLOP/s for register-operand DMMA on this B200 - the same as the DFMA peak - already
-// at one warp per SM sub-partition with four independent accumulator tiles.
+// double per wavefront, so the warp-per-unit DFMA kernel of round 1 (tools/attic/kf_rowsL.cuh) sat at 94 % of the
+// shared-memory wavefront peak with the fp64 pipe 35 % active (profiles/r1_ncu_rowsL.md).  A DMMA consumes one A and one
+// B element per lane for eight multiply-adds per lane, and a fragment is reused for NT tiles: ~0.06 shared-memory operands
+// per multiply-add.  tools/dmma_probe.cu measured 37.1 TFLOP/s for register-operand DMMA on this B200 - the same as the
+// DFMA peak - already at one warp per SM sub-partition with four independent accumulator tiles.
 //
-// Matrices live in shared memory as 32 x 32 tiles-of-8 with leading dimension LD = 34 doubles: rows 16-byte aligned and
-// LD/2 odd, so the row-per-lane 16-byte accesses of a quarter warp fall on 8 distinct bank groups (LD = 36 makes the
-// fragment loads conflict-free instead but 2-way conflicts every row access: measured 357 ms vs 326 ms per evaluation of
-// config 4; LD = 38: 332 ms).  Rows / columns >= m are zero and stay zero (products of zero padding).
-// Transposed operands cost nothing: A^T / B^T just swap the two fragment access patterns.
+// Matrices live in shared memory as NT x NT tiles of 8 x 8 (NT = 4 for k_states 18..32, NT = 2 for 10..16) with leading
+// dimension 8 NT + 2 (LD = 36 at NT = 4 makes the fragment loads conflict-free instead but 2-way conflicts every row
+// access: measured 357 ms vs 326 ms per evaluation of config 4; LD = 38: 332 ms).  Rows / columns >= m are zero and stay
+// zero (products of zero padding).  Transposed operands cost nothing: A^T / B^T just swap the two fragment access patterns.
 #pragma once
 #include "kf_core.cuh"
 #include "kf_rows.cuh"
 
 namespace kfb {
 
-// Tile layout.  Default (KFB_ROWSD_SWZ = 0): leading dimension 34 - rows 16-byte aligned and LD/2 odd, so the
-// row-per-lane 16-byte accesses are conflict free; fragment loads and tile stores are 2-way conflicted.
-// KFB_ROWSD_SWZ = 1 (kept for A/B runs): LD = 32 and the 16-byte chunks of a row XOR-swizzled,
-//     physical chunk = chunk ^ swz(row),   swz(row) = {0,4,2,6,1,5,3,7}[row & 7],
-// which makes ALL four access patterns bank-conflict free at once (row accesses: 8 consecutive rows -> 8 distinct chunk
-// groups; both mma fragment patterns: 16 distinct 8-byte slots per half warp; 16-byte tile stores) - no padding can
-// (rows need LD/2 odd, tile stores LD/2 = 4 mod 8, fragments LD = 4 mod 16).  Measured SLOWER (347 vs 318 ms per
-// evaluation of config 4): the per-lane swizzled offsets of every row access become ~15 + 40 loop-invariant registers
-// in a kernel already at the 255-register limit (spills 76 -> 316 bytes per thread).
-#ifndef KFB_ROWSD_SWZ
-#define KFB_ROWSD_SWZ 0
-#endif
-constexpr int rowsD_LD = KFB_ROWSD_SWZ ? 32 : 34;
-__host__ __device__ constexpr int rowsD_swz(int row) {
-  return KFB_ROWSD_SWZ ? (((row & 1) << 2) | (row & 2) | ((row >> 2) & 1)) : 0;
-}
-// offset of element (row, col) inside a tile matrix
-__host__ __device__ constexpr int rowsD_el(int row, int col) {
-  return row * rowsD_LD + ((((col >> 1) ^ rowsD_swz(row)) << 1) | (col & 1));
-}
+// Tile geometry: NT x NT tiles of 8 x 8 per matrix (NT = 4: even k_states 18..32; NT = 2: even k_states 10..16 - seasonal
+// periods 12 / SARIMA orders land here), leading dimension LD = 8 NT + 2 doubles: rows 16-byte aligned and LD/2 odd, so
+// the row-per-lane 16-byte accesses of a quarter warp fall on 8 distinct bank groups; fragment loads and tile stores are
+// 2-way conflicted.  (An XOR-swizzled LD = 8 NT layout makes all four access patterns conflict free and was measured
+// slower twice - rounds 1 and 2, profiles/r2_ncu_rowsD.md: the per-access address arithmetic and its registers turn the
+// kernels from wavefront-bound into latency-bound.  It is not in the tree any more.)
+__host__ __device__ constexpr int rowsD_nt(int m) { return m <= 16 ? 2 : 4; }
+__host__ __device__ constexpr int rowsD_ld(int m) { return 8 * rowsD_nt(m) + 2; }
 
 template <int M, int P, bool NEED_T>
 struct RowsDLayout {
-  static_assert(M % 2 == 0 && M > 16 && M <= 32 && P <= 3, "even k_states in 18..32");
-  static constexpr int LD = rowsD_LD, MS = 32 * LD;  // one padded matrix
+  static_assert(M % 2 == 0 && M >= 10 && M <= 32 && P <= 3, "even k_states in 10..32");
+  static constexpr int NT = rowsD_nt(M), TD = 8 * NT, LD = rowsD_ld(M), MS = TD * LD;  // one padded matrix
   static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), ME = M + (M & 1);
-  static constexpr int MP32 = 32 * P;  // vectors that the mma-fragment-layout code reads by padded row (rows >= M stay 0)
+  static constexpr int MPT = TD * P;  // vectors that the mma-fragment-layout code reads by padded row (rows >= M stay 0)
   static constexpr int KT = M + (M * (M + 1)) / 2, KTP = (KT + 1) & ~1;
-  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MP32,
-                       a = Kp + MPE, END_COMMON = a + 32;
+  static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, Z = Lm + MS, H = Z + MPE, Mm = H + PP + (PP & 1), Kp = Mm + MPT,
+                       a = Kp + MPE, END_COMMON = a + TD;
   // forward only: X (then S2) ; KH rows
   static constexpr int X = END_COMMON, KH = X + MS, END_FWD = KH + MPE;
   // adjoint only: W = Ps L lives in Pm's slot (without T-bar nothing reads P after the gain) or in its own (with T-bar:
   // T-bar += 2 W P).  lz: (P0 + P0^T) Z^T, t = 0 only.  Mb: the rank-p part of P-bar, kept apart from L^T W.
-  static constexpr int Pb = END_COMMON, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MP32, lz = PK + MPE, TMs = lz + MPE,
-                       ab = TMs + MPE, Mb = ab + 32, Xb = Mb + MPE, END_BWD = Xb + (NEED_T ? MS : 0),
+  static constexpr int Pb = END_COMMON, Kb = Pb + MS, TMb = Kb + MPE, PK = TMb + MPT, lz = PK + MPE, TMs = lz + MPE,
+                       ab = TMs + MPE, Mb = ab + TD, Xb = Mb + MPE, END_BWD = Xb + (NEED_T ? MS : 0),
                        W = NEED_T ? Xb : Pm;
   // The tape entry of the NEXT step is staged in Lm's slot, which is free from the last product of a step (phase 3) to
   // the next step's gain: no staging buffer of its own, 37.5 instead of 41.5 KB per unit = 6 instead of 5 units per SM.
@@ -71,121 +58,99 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 #endif
 }
 
-// acc (32 x 32, as 4 x 4 tiles of 8 x 8 in mma fragment layout: lane holds [8I + lane/4][8J + 2 (lane%4) + {0,1}])
+// acc (8 NT x 8 NT, as NT x NT tiles of 8 x 8 in mma fragment layout: lane holds [8I + lane/4][8J + 2 (lane%4) + {0,1}])
 //   = op(A) op(B),  op = transpose if TA / TB.  A, B: padded row-major matrices (leading dimension LD) in shared memory.
 // ZERO = false: accumulate onto acc.  UPPER: only the tiles I <= J (the result is symmetric and its consumer reads it
-// through rowD_load_symU): 10 instead of 16 tile products.
-template <bool TA, bool TB, int LD, bool ZERO = true, bool UPPER = false>
-__device__ __forceinline__ void mm32(double (&acc)[4][4][2], const double* A, const double* B, int lane) {
+// through rowD_load_symU): 10 instead of 16 tile products at NT = 4.
+template <bool TA, bool TB, int LD, bool ZERO = true, bool UPPER = false, int NT = (LD - 2) / 8>
+__device__ __forceinline__ void mm32(double (&acc)[NT][NT][2], const double* A, const double* B, int lane) {
   const int r = lane >> 2, c = lane & 3;
   // "N" pattern: element (row 8X + r, col 4kk + c) ; "T" pattern: element (row 4kk + c, col 8X + r)
   //   A: N, A^T: T (a[row][k] = A[k][row]) ; B: T pattern on B (b[k][col] = B[k][col]), B^T: N pattern on B
-  const int sr = rowsD_swz(r);                                          // swizzle of rows 8X + r
-  const int gc = KFB_ROWSD_SWZ ? (((c & 1) << 2) | (c & 2)) : 0;        // swizzle of rows 4kk + c = gc | (kk & 1)
-  const double* nA = A + r * LD + (c & 1);
-  const double* nB = B + r * LD + (c & 1);
-  const double* tA = A + c * LD + (r & 1);
-  const double* tB = B + c * LD + (r & 1);
+  const double* nA = A + r * LD + c;
+  const double* nB = B + r * LD + c;
+  const double* tA = A + c * LD + r;
+  const double* tB = B + c * LD + r;
   if (ZERO) {
 #pragma unroll
-    for (int I = 0; I < 4; ++I)
+    for (int I = 0; I < NT; ++I)
 #pragma unroll
-      for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+      for (int J = 0; J < NT; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
   }
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk) {
-    double af[4], bf[4];
-    const int nofs = ((2 * kk + (c >> 1)) ^ sr) << 1;  // N pattern: chunk 2kk + c/2 of the lane's row
-    const int st = gc | (KFB_ROWSD_SWZ ? (kk & 1) : 0);
+  for (int kk = 0; kk < 2 * NT; ++kk) {
+    double af[NT], bf[NT];
 #pragma unroll
-    for (int I = 0; I < 4; ++I)
-      af[I] = TA ? tA[(4 * kk) * LD + (((4 * I + (r >> 1)) ^ st) << 1)] : nA[(8 * I) * LD + nofs];
+    for (int I = 0; I < NT; ++I) af[I] = TA ? tA[(4 * kk) * LD + 8 * I] : nA[(8 * I) * LD + 4 * kk];
 #pragma unroll
-    for (int J = 0; J < 4; ++J)
-      bf[J] = TB ? nB[(8 * J) * LD + nofs] : tB[(4 * kk) * LD + (((4 * J + (r >> 1)) ^ st) << 1)];
+    for (int J = 0; J < NT; ++J) bf[J] = TB ? nB[(8 * J) * LD + 4 * kk] : tB[(4 * kk) * LD + 8 * J];
 #pragma unroll
-    for (int I = 0; I < 4; ++I)
+    for (int I = 0; I < NT; ++I)
 #pragma unroll
-      for (int J = 0; J < 4; ++J)
+      for (int J = 0; J < NT; ++J)
         if (!UPPER || I <= J) dmma884(acc[I][J][0], acc[I][J][1], af[I], bf[J]);
   }
 }
 
-// D = alpha * acc (full 32 x 32 including the zero padding; UPPER: the tiles I <= J only)
-template <int LD, bool UPPER = false>
-__device__ __forceinline__ void mm32_store(double* D, const double (&acc)[4][4][2], double alpha, int lane) {
-  // D may be one of the product's own operands (X <- X L^T, Xb <- Ps Xb): every fragment load is
+// D = alpha * acc (the full padded matrix including the zero padding; UPPER: the tiles I <= J only)
+template <int LD, bool UPPER = false, int NT = (LD - 2) / 8>
+__device__ __forceinline__ void mm32_store(double* D, const double (&acc)[NT][NT][2], double alpha, int lane) {
+  // D may be one of the product's own operands (X <- X L^T, A <- A A): every fragment load is
   // behind an mma.sync that consumed it, but make the ordering explicit (and visible to racecheck)
   __syncwarp();
   const int r = lane >> 2, c = lane & 3;
 #pragma unroll
-  for (int I = 0; I < 4; ++I)
+  for (int I = 0; I < NT; ++I)
 #pragma unroll
-    for (int J = 0; J < 4; ++J)
+    for (int J = 0; J < NT; ++J)
       if (!UPPER || I <= J)
-        *reinterpret_cast<double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1)) =
-            make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
+        *reinterpret_cast<double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c) = make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
 }
 
-// Swizzled layout only: the per-lane chunk offsets (j ^ swz(row)) of the row accesses must NOT be kept as loop
-// invariants (15 + 40 registers in kernels at the 255-register limit: the round-1 A/B lost on spills).  An empty
-// volatile asm makes the lane's swizzle value opaque at every use, so ptxas re-derives each offset with one LOP3 next to
-// its access (issue slots are < 20 % busy in these kernels) instead of hoisting it.
-__device__ __forceinline__ int rowsD_fresh(int x) {
-#if KFB_ROWSD_SWZ && defined(__CUDA_ARCH__)
-  asm volatile("" : "+r"(x));
-#endif
-  return x;
+// row i of a tile matrix: rowp = &mat[i * LD]; chunk j = elements 2j, 2j + 1
+__device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int j) {
+  return reinterpret_cast<const double2*>(rowp + 2 * j);
 }
-// row i of a tile matrix: rowp = &mat[i * LD], si = rowsD_swz(i); chunk j of the row lives at rowp + ((j ^ si) << 1)
-__device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int si, int j) {
-  return reinterpret_cast<const double2*>(rowp + ((j ^ si) << 1));
-}
-__device__ __forceinline__ double2* rowD_chunk(double* rowp, int si, int j) {
-  return reinterpret_cast<double2*>(rowp + ((j ^ si) << 1));
-}
+__device__ __forceinline__ double2* rowD_chunk(double* rowp, int j) { return reinterpret_cast<double2*>(rowp + 2 * j); }
 template <int M>
-__device__ __forceinline__ void rowD_store(double* rowp, int si, const double (&v)[M]) {
-  si = rowsD_fresh(si);
+__device__ __forceinline__ void rowD_store(double* rowp, const double (&v)[M]) {
 #pragma unroll
-  for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, si, j) = make_double2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, j) = make_double2(v[2 * j], v[2 * j + 1]);
 }
 template <int M>
-__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, int si) {
-  si = rowsD_fresh(si);
+__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp) {
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
-    const double2 x = *rowD_chunk(rowp, si, j);
+    const double2 x = *rowD_chunk(rowp, j);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
 }
 // element (row j, column i) of a tile matrix, j a compile-time constant after unrolling: the lane's COLUMN accesses
+template <int LD>
 __device__ __forceinline__ double colD(const double* mat, int j, int i) {
-  i = rowsD_fresh(i);
-  return mat[j * rowsD_LD + ((((i >> 1) ^ rowsD_swz(j)) << 1) | (i & 1))];
+  return mat[j * LD + i];
 }
 
 // The lane's row i of sym(U) for a matrix U = A^T S A (S symmetric) of which only the 8 x 8 tiles I <= J were computed
 // (mm32<.., UPPER>): entries right of the lane's diagonal tile come from its row, entries left of it from its column
 // (the mirrored tile), the diagonal tile is averaged.  Exactly symmetric by construction, and the loads of the tiles a
 // lane does not need are predicated off (whole 8-lane groups: fewer shared-memory wavefronts than the full row + column).
-template <int M>
-__device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat, int i, int si) {
+template <int M, int LD>
+__device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat, int i) {
   const int ti = i >> 3;
-  const double* rowp = mat + i * rowsD_LD;
-  si = rowsD_fresh(si);
+  const double* rowp = mat + i * LD;
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
     double2 x = make_double2(0.0, 0.0);
-    if (((2 * j) >> 3) >= ti) x = *rowD_chunk(rowp, si, j);
+    if (((2 * j) >> 3) >= ti) x = *rowD_chunk(rowp, j);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
 #pragma unroll
   for (int j = 0; j < M; ++j) {
     if ((j >> 3) <= ti) {
-      const double cj = colD(mat, j, i);
+      const double cj = colD<LD>(mat, j, i);
       v[j] = ((j >> 3) < ti) ? cj : 0.5 * (v[j] + cj);
     }
   }
@@ -220,7 +185,6 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
                                            const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g,
                                            bool full_det = false) {
   constexpr int LD = L::LD;
-  const int si = rowsD_swz(i);
   // ---- A: Mm row (own P row x Z rows), v (every lane)
   {
     double Mr[P][4], vr[P][4];  // four partial sums each (see dot4)
@@ -232,10 +196,9 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     }
     const double* pr = sm + L::Pm + i * LD;
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
-    const int sA = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 pk = *rowD_chunk(pr, sA, k), ak = av[k];
+      const double2 pk = *rowD_chunk(pr, k), ak = av[k];
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -265,10 +228,9 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
 #pragma unroll
     for (int j = 0; j < P; ++j) Tq[j][0] = Tq[j][1] = Tq[j][2] = Tq[j][3] = 0.0;
     const double* tr = sm + L::T + i * LD;
-    const int sB = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = *rowD_chunk(tr, sB, k);
+      const double2 tk = *rowD_chunk(tr, k);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -311,21 +273,20 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
   {
     const double* tr = sm + L::T + i * LD;
     double* lr = sm + L::Lm + i * LD;
-    const int sC = rowsD_fresh(si);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      double2 lk = *rowD_chunk(tr, sC, k);
+      double2 lk = *rowD_chunk(tr, k);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
         lk.x = fma(-g.Kp[e], z.x, lk.x);
         lk.y = fma(-g.Kp[e], z.y, lk.y);
       }
-      if (act) *rowD_chunk(lr, sC, k) = lk;
+      if (act) *rowD_chunk(lr, k) = lk;
     }
     if (PADL && act) {  // the row's zero padding (Lm's slot doubles as the adjoint's tape staging buffer)
 #pragma unroll
-      for (int k = M / 2; k < 16; ++k) *rowD_chunk(lr, sC, k) = make_double2(0.0, 0.0);
+      for (int k = M / 2; k < L::TD / 2; ++k) *rowD_chunk(lr, k) = make_double2(0.0, 0.0);
     }
   }
   if (act) {
@@ -344,7 +305,6 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   const long long draw = u / A.n_series;
   const bool act = lane < M;
   const int i = act ? lane : 0;
-  const int si = rowsD_swz(i);
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
   const double* Hp = A.H.p + draw * A.H.bs;
@@ -357,8 +317,8 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
-    sm[L::Pm + rowsD_el(rr, cc)] = P0p[k];
+    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::Pm + rr * LD + cc] = P0p[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -398,10 +358,9 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
       double aq[4] = {ci, 0.0, 0.0, 0.0};
       const double* tr = sm + L::T + i * LD;
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
-      const int sT = rowsD_fresh(si);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = *rowD_chunk(tr, sT, k), ak = av[k];
+        const double2 tk = *rowD_chunk(tr, k), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -433,7 +392,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;  // L = T when nothing is observed
     // ---- X = L P, then S2raw = X L^T (tensor cores); S2raw overwrites X (all fragment loads of X are behind its mma's)
     {
-      double c4[4][4][2];
+      double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, Lsrc, sm + L::Pm, lane);
       mm32_store<LD>(sm + L::X, c4, 1.0, lane);
       __syncwarp();
@@ -447,7 +406,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     const bool taped = tp && t + 1 < n;
     {
       double S[M];
-      rowD_load_symU<M>(S, sm + L::X, i, si);
+      rowD_load_symU<M, LD>(S, sm + L::X, i);
 #pragma unroll
       for (int j = 0; j < M; ++j) S[j] += Cs[j];
       if (observed) {
@@ -459,7 +418,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
         }
       }
       if (act) {
-        rowD_store<M>(sm + L::Pm + i * LD, si, S);
+        rowD_store<M>(sm + L::Pm + i * LD, S);
         sm[L::a + i] = an;
         if (taped) {
           tp[i] = an;
@@ -501,7 +460,6 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   const long long draw = u / A.n_series;
   const bool act = lane < M;
   const int i = act ? lane : 0;
-  const int si = rowsD_swz(i);
   const int fr = lane >> 2, fc = lane & 3;  // mma fragment coordinates
   const double* Tp = A.T.p + draw * A.T.bs;
   const double* Zp = A.Z.p + draw * A.Z.bs;
@@ -512,7 +470,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   if (n >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(n - 2) * KT, lane);
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
+    sm[L::T + rr * LD + cc] = Tp[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -532,7 +490,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   }
   // gradient accumulators: the lane's row of Cb in registers; HALF of T-bar in mma fragment layout (lane holds
   // [8I + fr][8J + 2 fc + {0,1}]); lanes < P hold rows of Hb; cb (row), db (lane)
-  constexpr int TI = NEED_T ? 4 : 1;
+  constexpr int TI = NEED_T ? L::NT : 1;
   double Cb[M], Tacc[TI][TI][2], Hb[P], cb = 0.0, db = 0.0, abi = 0.0;
 #pragma unroll
   for (int j = 0; j < M; ++j) Cb[j] = 0.0;
@@ -553,7 +511,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
       for (int k = lane; k < M * M; k += 32) {
         const int rr = k / M, cc = k - rr * M;
-        sm[L::Pm + rowsD_el(rr, cc)] = P0p[k];
+        sm[L::Pm + rr * LD + cc] = P0p[k];
       }
       if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
     } else {
@@ -568,7 +526,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           const int lo = i < j ? i : j, hi = i < j ? j : i;
           Pr[j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
         }
-        rowD_store<M>(sm + L::Pm + i * LD, si, Pr);
+        rowD_store<M>(sm + L::Pm + i * LD, Pr);
       }
       // (every lane has read the staging buffer before the sync below; the gain may overwrite it)
     }
@@ -592,9 +550,9 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
     if (t == 0) {  // P0 may be any matrix: L-bar = W (P + P^T); for t >= 1 the taped P is symmetric: P + P^T = 2 P
       double S0[M];
-      rowD_load<M>(S0, sm + L::Pm + i * LD, si);
+      rowD_load<M>(S0, sm + L::Pm + i * LD);
 #pragma unroll
-      for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD(sm + L::Pm, j, i));
+      for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD<LD>(sm + L::Pm, j, i));
       if (observed) {  // lz = (P + P^T) Z^T rows
 #pragma unroll
         for (int e = 0; e < P; ++e) {
@@ -606,14 +564,14 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         }
       }
       __syncwarp();
-      if (NEED_T && act) rowD_store<M>(sm + L::Pm + i * LD, si, S0);
+      if (NEED_T && act) rowD_store<M>(sm + L::Pm + i * LD, S0);
       __syncwarp();
     }
     // ---- 1: Ps = sym(P-bar') = symU(L^T W of the step above) + sym(Mb Z), in place ; Cb += Ps
     cb += abi;
     double Ps[M];  // without T-bar the row stays in registers for phase 2; with it (64 more accumulators) it is re-read
     {
-      rowD_load_symU<M>(Ps, sm + L::Pb, i, si);
+      rowD_load_symU<M, LD>(Ps, sm + L::Pb, i);
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         const double mi = 0.5 * sm[L::Mb + i * P + k], zi = 0.5 * sm[L::Z + k * M + i];
@@ -623,16 +581,16 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
       for (int j = 0; j < M; ++j) Cb[j] += Ps[j];
       __syncwarp();  // every lane has read its row and column of P-bar'
-      if (act) rowD_store<M>(sm + L::Pb + i * LD, si, Ps);
+      if (act) rowD_store<M>(sm + L::Pb + i * LD, Ps);
     }
     __syncwarp();  // Ps visible
     // ---- 2: W = Ps L (tensor cores) ; PK = Ps Kp, T^T ab (row-wise, independent of the product: they sit between its
     //         last mma and its store - a DMMA issues once per ~16 cycles, the scheduler fills the gaps)
     double PK[P], Kb[P], abn;
     {
-      double c4[4][4][2];
+      double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
-      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD, si);
+      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y2) {  // (Kp is stale but unused when nothing is observed)
@@ -641,7 +599,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         });
       }
       abn = dot4<M>(0.0, [&](int k, double& x, double& y2) {
-        x = colD(sm + L::T, k, i);
+        x = colD<LD>(sm + L::T, k, i);
         y2 = sm[L::ab + k];
       });
       mm32_store<LD>(sm + L::W, c4, 1.0, lane);  // without T-bar: Pm's slot (its fragment loads... none: P is not an operand)
@@ -663,7 +621,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     if (observed) {
       double Wr[M];
-      rowD_load<M>(Wr, sm + L::W + i * LD, si);
+      rowD_load<M>(Wr, sm + L::W + i * LD);
       const double* m2 = (t == 0) ? sm + L::lz : sm + L::Mm;
       const double sc = (t == 0) ? 1.0 : 2.0;
 #pragma unroll
@@ -688,7 +646,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     // ---- 3: L^T W (tensor cores, upper tiles) -> Pb (Ps rows were last read above, by their owners, before this point
     //         in program order of every lane; the store follows the last mma, which all lanes execute together)
     __syncwarp();  // Kb visible; all row reads of Ps and W done
-    double c4p[4][4][2];
+    double c4p[L::NT][L::NT][2];
     mm32<true, false, LD, true, true>(c4p, Lsrc, sm + L::W, lane);  // stored after the row-wise block below
     __syncwarp();  // last use of Lm in this step: stage the tape entry of step t-1 in its slot
     if (t >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(t - 2) * KT, lane);
@@ -766,7 +724,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         double s = dot4<M>(0.0, [&](int k, double& x, double& y2) {
-          x = colD(sm + L::T, k, i);
+          x = colD<LD>(sm + L::T, k, i);
           y2 = sm[L::TMb + k * P + e];
         });
 #pragma unroll
@@ -816,7 +774,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   // ---- write-out (row i by lane i): P-bar = symU(L^T W) + Mb Z of step 0
   {
     double Pf[M];
-    rowD_load_symU<M>(Pf, sm + L::Pb, i, si);
+    rowD_load_symU<M, LD>(Pf, sm + L::Pb, i);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       const double mi = sm[L::Mb + i * P + k];
@@ -871,22 +829,22 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 // 99.5 ms on the generic CTA-per-draw kernels (29 % of a steady_state evaluation) -> see profiles/r2_ncu_rowsD.md.
 template <int M, int P>
 struct DareDLayout {
-  static constexpr int LD = rowsD_LD, MS = 32 * LD;
-  static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), MP32 = 32 * P;
+  static constexpr int NT = rowsD_nt(M), TD = 8 * NT, LD = rowsD_ld(M), MS = TD * LD;
+  static constexpr int MP = M * P, PP = P * P, MPE = MP + (MP & 1), MPT = TD * P;
   static constexpr int T = 0, Pm = T + MS, Lm = Pm + MS, X = Lm + MS, Xs = X + MS, Z = Xs + MS, H = Z + MPE,
-                       Mm = H + PP + (PP & 1), Kp = Mm + MP32, a = Kp + MPE, KH = a + 32, END = KH + MPE;
+                       Mm = H + PP + (PP & 1), Kp = Mm + MPT, a = Kp + MPE, KH = a + TD, END = KH + MPE;
   static constexpr int doubles = (END + 1) & ~1;
 };
 
 // acc <- D (the inverse of mm32_store)
-template <int LD>
-__device__ __forceinline__ void mm32_load(double (&acc)[4][4][2], const double* D, int lane) {
+template <int LD, int NT = (LD - 2) / 8>
+__device__ __forceinline__ void mm32_load(double (&acc)[NT][NT][2], const double* D, int lane) {
   const int r = lane >> 2, c = lane & 3;
 #pragma unroll
-  for (int I = 0; I < 4; ++I)
+  for (int I = 0; I < NT; ++I)
 #pragma unroll
-    for (int J = 0; J < 4; ++J) {
-      const double2 x = *reinterpret_cast<const double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz(r)) << 1));
+    for (int J = 0; J < NT; ++J) {
+      const double2 x = *reinterpret_cast<const double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c);
       acc[I][J][0] = x.x;
       acc[I][J][1] = x.y;
     }
@@ -907,12 +865,11 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
   constexpr int LD = L::LD;
   const bool act = lane < M;
   const int i = act ? lane : 0;
-  const int si = rowsD_swz(i);
   for (int k = lane; k < L::doubles; k += 32) sm[k] = 0.0;  // zero padding everywhere, a = 0
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rowsD_el(rr, cc)] = Tp[k];
+    sm[L::T + rr * LD + cc] = Tp[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -926,7 +883,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
 #pragma unroll
   for (int k = 0; k < P * P; ++k) scale = fmax(scale, fabs(Hp[k]));
   scale = warp_max(scale);
-  if (act) sm[L::Pm + rowsD_el(i, i)] = 1.0e4 * scale;
+  if (act) sm[L::Pm + i * LD + i] = 1.0e4 * scale;
   __syncwarp();
 
   double yt[P], dv[P], Gss[P * P];
@@ -963,7 +920,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     double S[M], U[M];
     rhs_row(S);
     {
-      double c4[4][4][2];
+      double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Pm, lane);
       mm32_store<LD>(sm + L::X, c4, 1.0, lane);
       __syncwarp();
@@ -971,10 +928,10 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
       mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
     }
     __syncwarp();
-    rowD_load_symU<M>(U, sm + L::X, i, si);
+    rowD_load_symU<M, LD>(U, sm + L::X, i);
 #pragma unroll
     for (int j = 0; j < M; ++j) S[j] += U[j];
-    if (act) rowD_store<M>(sm + L::Pm + i * LD, si, S);
+    if (act) rowD_store<M>(sm + L::Pm + i * LD, S);
     __syncwarp();
   }
   // (2) Newton-Hewer: P <- Lyapunov(L(P), C + Kp H Kp^T), each Lyapunov equation by squared-Smith doubling
@@ -985,19 +942,19 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     {
       double S[M];
       rhs_row(S);
-      if (act) rowD_store<M>(sm + L::Xs + i * LD, si, S);
+      if (act) rowD_store<M>(sm + L::Xs + i * LD, S);
     }
     __syncwarp();
     bool ok = false;
     for (int db = 0; db < 64; ++db) {  // Xs <- sum_k A^k Xs A^kT, A = Lm (destroyed)
       double Ar[M], mx = 0.0;
-      rowD_load<M>(Ar, sm + L::Lm + i * LD, si);
+      rowD_load<M>(Ar, sm + L::Lm + i * LD);
 #pragma unroll
       for (int j = 0; j < M; ++j) mx = fmax(mx, fabs(Ar[j]));
       mx = warp_max(mx);
       if (!(mx < 1.0e150)) break;
       if (mx < 1.0e-11) { ok = true; break; }
-      double c4[4][4][2];
+      double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Xs, lane);  // S1 = A Xs
       mm32_store<LD>(sm + L::X, c4, 1.0, lane);
       __syncwarp();
@@ -1010,17 +967,17 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     }
     if (!ok) { info = 1; break; }
     double Pn[M], Po[M], diff = 0.0, mag = 0.0;
-    rowD_load<M>(Pn, sm + L::Xs + i * LD, si);
-    rowD_load<M>(Po, sm + L::Pm + i * LD, si);
+    rowD_load<M>(Pn, sm + L::Xs + i * LD);
+    rowD_load<M>(Po, sm + L::Pm + i * LD);
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       diff = fmax(diff, fabs(Pn[j] - Po[j]));
       mag = fmax(mag, fabs(Pn[j]));
-      Pn[j] = 0.5 * (Pn[j] + colD(sm + L::Xs, j, i));  // symmetrise: keeps the iteration on the symmetric manifold
+      Pn[j] = 0.5 * (Pn[j] + colD<LD>(sm + L::Xs, j, i));  // symmetrise: keeps the iteration on the symmetric manifold
     }
     diff = warp_max(diff);
     mag = warp_max(mag);
-    if (act) rowD_store<M>(sm + L::Pm + i * LD, si, Pn);
+    if (act) rowD_store<M>(sm + L::Pm + i * LD, Pn);
     __syncwarp();
     converged = diff <= 4.0e-15 * mag;
   }
@@ -1030,7 +987,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
   if (!g.ok) info = 1;
   if (act) {
     double Pr[M];
-    rowD_load<M>(Pr, sm + L::Pm + i * LD, si);
+    rowD_load<M>(Pr, sm + L::Pm + i * LD);
 #pragma unroll
     for (int j = 0; j < M; ++j) Pss[i * M + j] = info ? nan("") : Pr[j];
   }

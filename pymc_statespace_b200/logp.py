@@ -167,13 +167,13 @@ def logp_and_grad_in_waves(spec: StateSpaceSpec, data, theta: torch.Tensor, filt
 class KalmanLogp:
     def __init__(self, spec: StateSpaceSpec, data, n_draws: int, filter_type: str = "standard",
                  strict_reference: bool = True, device="cuda", force_coop: bool = False, pad_to_fused: bool = True):
-        # sizes between the fused instantiations (k_states 9..31 outside {18, 20, .., 32}; e.g. seasonal models of period
-        # 12 or 24): embed the model in the next instantiated size - exact (models.pad_spec) and far cheaper than the
-        # generic run-time-dims kernels, because the tensor-core kernels work on zero-padded 32 x 32 tiles anyway
+        # sizes between the fused instantiations (odd k_states in 9..31; e.g. seasonal models of period 12 or 24): embed
+        # the model in the next instantiated (even) size - exact (models.pad_spec) and far cheaper than the generic
+        # run-time-dims kernels, because the tensor-core kernels work on zero-padded 16 x 16 / 32 x 32 tiles anyway
         self.k_states_model = spec.k_states
         if (pad_to_fused and spec.k_endog == 1 and 8 < spec.k_states < 32 and spec.k_states not in FUSED_K_STATES
                 and filter_type in ("standard", "single", "cholesky", "steady_state")):
-            spec = pad_spec(spec, min(k for k in FUSED_K_STATES if k >= max(spec.k_states, 18)))
+            spec = pad_spec(spec, min(k for k in FUSED_K_STATES if k >= spec.k_states))
         self.spec = spec
         self.device = torch.device(device)
         self.lib = load()

@@ -211,14 +211,14 @@ def trend_seasonal_spec(period: int = 29) -> StateSpaceSpec:
     return StateSpaceSpec(m, 1, r, 4, base, maps, False, ("sigma2_level", "sigma2_slope", "sigma2_seasonal", "sigma2_obs"))
 
 
-FUSED_K_STATES = tuple(range(1, 9)) + tuple(range(18, 33, 2))  # sizes with fused hot-path kernels in libkfb200.so
+FUSED_K_STATES = tuple(range(1, 9)) + tuple(range(10, 33, 2))  # sizes with fused hot-path kernels in libkfb200.so
 
 
 def pad_spec(spec: StateSpaceSpec, k_states: int) -> StateSpaceSpec:
     """The same model embedded in ``k_states`` >= spec.k_states states: the extra states have zero rows / columns in
     T, Z, R, c, a0, P0, so they stay identically zero (mean and covariance), never reach an observation and leave logp,
     every per-step output of the original states and every d logp / d theta unchanged - exactly (the padded products only
-    add zeros).  Used by ``KalmanLogp`` to run e.g. a 13-state seasonal model (period 12) on the 18-state tensor-core
+    add zeros).  Used by ``KalmanLogp`` to run e.g. a 13-state seasonal model (period 12) on the 14-state tensor-core
     kernels instead of the generic run-time-dims kernels."""
     m, m2, p, r = spec.k_states, int(k_states), spec.k_endog, spec.k_posdef
     if m2 < m:

@@ -89,12 +89,12 @@ def varmax20_workload(n_draws=262144, n=1000, k=3, missing_frac=0.1, seed=1):
     return spec, y, theta
 
 
-def trend_seasonal_workload(n_draws=8192, n=2000, seed=1):
-    """config[3]: trend + period-29 seasonal, k_states=30; theta = 4 variances."""
-    spec = trend_seasonal_spec(29)
+def trend_seasonal_workload(n_draws=8192, n=2000, seed=1, period=29):
+    """config[3]: trend + period-29 seasonal, k_states=30; theta = 4 variances.  (``period`` 12 -> 13 states, ...)"""
+    spec = trend_seasonal_spec(period)
     rng = np.random.default_rng(seed)
     theta = np.exp(rng.normal(np.log([0.1, 0.01, 0.05, 0.5]), 0.2, size=(n_draws, 4)))
     rs = np.random.default_rng(0)
     t = np.arange(n)
-    y = 0.01 * t + np.sin(2 * np.pi * t / 29) + np.cumsum(rs.normal(0, 0.3, n)) + rs.normal(0, 0.7, n)
+    y = 0.01 * t + np.sin(2 * np.pi * t / period) + np.cumsum(rs.normal(0, 0.3, n)) + rs.normal(0, 0.7, n)
     return spec, y[:, None], theta

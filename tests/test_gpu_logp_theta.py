@@ -401,7 +401,8 @@ def test_status_codes_for_non_stationary_draws_and_failed_dare():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("period,kind", [(12, "standard"), (24, "standard"), (12, "steady_state"), (7, "standard")])
+@pytest.mark.parametrize("period,kind", [(12, "standard"), (24, "standard"), (12, "steady_state"), (7, "standard"),
+                                         (9, "standard"), (15, "standard"), (16, "steady_state")])
 def test_sizes_between_instantiations_are_padded_exactly(period, kind):
     """Seasonal models whose k_states falls between the fused instantiations (period 12 -> 13 states, period 24 -> 25):
     KalmanLogp embeds them in the next instantiated size (models.pad_spec: extra states identically zero).  logp and
@@ -420,7 +421,7 @@ def test_sizes_between_instantiations_are_padded_exactly(period, kind):
     plain = KalmanLogp(spec, y, n_draws=B, filter_type=kind, pad_to_fused=False)
     m = spec.k_states
     assert plain.spec.k_states == m and padded.k_states_model == m
-    assert padded.spec.k_states == (m if m in FUSED_K_STATES else min(k for k in FUSED_K_STATES if k >= max(m, 18)))
+    assert padded.spec.k_states == (m if m in FUSED_K_STATES else min(k for k in FUSED_K_STATES if k >= m))
     lp1, g1 = padded.logp_and_grad(th)
     lp0, g0 = plain.logp_and_grad(th)
     assert int((padded.info != 0).sum()) == 0 and int((plain.info != 0).sum()) == 0
@@ -443,9 +444,9 @@ def test_sizes_between_instantiations_are_padded_exactly(period, kind):
     assert tuple(out["filtered_states"].shape) == (B, n, m) and tuple(out["predicted_covs"].shape) == (B, n + 1, m, m)
 
 
-@pytest.mark.parametrize("m", [18, 30, 32])
+@pytest.mark.parametrize("m", [10, 16, 18, 30, 32])
 def test_tensor_core_dare_matches_generic_solver_and_reports_failure(m):
-    """steady_state at even k_states 18..32, k_endog 1: the forward DARE solve runs on the warp-per-draw tensor-core
+    """steady_state at even k_states 10..32, k_endog 1: the forward DARE solve runs on the warp-per-draw tensor-core
     mapping (kf_rowsD.cuh: rowsD_dare).  Same fixed point as the generic solver (force_coop) and as scipy's
     solve_discrete_are (the oracle), and an unobservable explosive state is reported as KFB_INFO_DARE_FAILED."""
     from pymc_statespace_b200 import BatchedKalman

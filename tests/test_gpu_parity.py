@@ -294,7 +294,8 @@ def test_subwarp_kernels_many_units_not_multiple_of_group():
 @pytest.mark.parametrize("wrt", [("a0", "P0", "T", "R", "H", "Q", "c", "d"), ("a0", "P0", "R", "H", "Q", "c", "d"), ("H", "Q")],
                          ids=["with_Tbar", "no_Tbar", "HQ_only"])
 @pytest.mark.parametrize("dims", [(5, 1, 2), (5, 3, 2), (6, 2, 3), (6, 3, 3), (7, 3, 2), (8, 1, 1), (8, 3, 3), (30, 1, 3),
-                                  (18, 1, 2), (20, 1, 1), (22, 1, 3), (24, 1, 2), (26, 1, 2), (28, 1, 3), (32, 1, 2)],
+                                  (18, 1, 2), (20, 1, 1), (22, 1, 3), (24, 1, 2), (26, 1, 2), (28, 1, 3), (32, 1, 2),
+                                  (10, 1, 2), (12, 1, 3), (14, 1, 1), (16, 1, 2)],
                          ids=lambda d: "m%dp%dr%d" % d)
 def test_fused_row_kernels_hot_path(dims, wrt):
     """The theta-level hot path of mid-size / large systems: loglik-only forward + adjoint WITHOUT Z-bar go through the
@@ -305,7 +306,7 @@ def test_fused_row_kernels_hot_path(dims, wrt):
     m, p, r = dims
     rng = np.random.default_rng(1000 + 10 * m + p)
     B, n = 13, 24
-    systems = [random_system(rng, m, p, r, n, scale_T=0.25 if m < 18 else 0.1) for _ in range(B)]
+    systems = [random_system(rng, m, p, r, n, scale_T=0.25 if m < 10 else 0.1) for _ in range(B)]
     y = random_system(rng, m, p, r, n, n_missing=3)[0]
     cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
     stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
@@ -337,7 +338,8 @@ def test_fused_row_kernels_hot_path(dims, wrt):
 
 
 @pytest.mark.parametrize("wrt", [("a0", "T", "R", "H", "Q", "c", "d"), ("R", "H", "Q")], ids=["with_Tbar", "no_Tbar"])
-@pytest.mark.parametrize("dims", [(30, 1, 3), (6, 3, 3), (5, 1, 2), (8, 2, 2), (18, 1, 2), (24, 1, 3)], ids=lambda d: "m%dp%dr%d" % d)
+@pytest.mark.parametrize("dims", [(30, 1, 3), (6, 3, 3), (5, 1, 2), (8, 2, 2), (18, 1, 2), (24, 1, 3), (10, 1, 2), (16, 1, 3)],
+                         ids=lambda d: "m%dp%dr%d" % d)
 def test_fused_row_kernels_steady_state(dims, wrt):
     """SteadyStateFilter through the fused row kernels (MK_STEADY instantiations of kf_rows.cuh for k_states 5..8 and of the
     tensor-core kf_rowsD.cuh for k_states = 30) + DARE kernels; no Z-bar."""
@@ -346,7 +348,7 @@ def test_fused_row_kernels_steady_state(dims, wrt):
     m, p, r = dims
     rng = np.random.default_rng(77 + m)
     B, n = 11, 20
-    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m >= 18 else 0.25) for _ in range(B)]
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m >= 10 else 0.25) for _ in range(B)]
     y = systems[0][0]
     cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
     stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
@@ -367,7 +369,7 @@ def test_fused_row_kernels_steady_state(dims, wrt):
 
 
 @pytest.mark.parametrize("n", [1, 2])
-@pytest.mark.parametrize("dims", [(6, 3, 3), (30, 1, 3)], ids=lambda d: "m%dp%dr%d" % d)
+@pytest.mark.parametrize("dims", [(6, 3, 3), (30, 1, 3), (12, 1, 2)], ids=lambda d: "m%dp%dr%d" % d)
 def test_fused_row_kernels_very_short_series(dims, n):
     """n = 1: no tape at all; n = 2: a single tape entry (the prefetch / double-buffer edge cases of the fused kernels)."""
     from pymc_statespace_b200 import BatchedKalman
@@ -375,7 +377,7 @@ def test_fused_row_kernels_very_short_series(dims, n):
     m, p, r = dims
     rng = np.random.default_rng(300 + m + n)
     B = 3
-    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m >= 18 else 0.25) for _ in range(B)]
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m >= 10 else 0.25) for _ in range(B)]
     y = systems[0][0]
     stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
     for kind in ("standard", "steady_state"):

@@ -20,12 +20,13 @@ def main():
     strict = not (len(sys.argv) > 5 and sys.argv[5] == "corrected")
     if cfg == "varmax":
         spec, y, theta = syn.varmax20_workload(draws or 16384, n or 1000)
-    elif cfg == "seasonal":
-        spec, y, theta = syn.trend_seasonal_workload(draws or 1024, n or 2000)
+    elif cfg.startswith("seasonal"):  # "seasonal" = period 29 (config 4); "seasonal12" = period 12 (13 states), ...
+        spec, y, theta = syn.trend_seasonal_workload(draws or 1024, n or 2000, period=int(cfg[8:] or 29))
     else:
         spec, y, theta = syn.arma21_workload(draws or (1 << 20), n or 1000)
     B, T = theta.shape[0], y.shape[0]
-    model = KalmanLogp(spec, y, n_draws=B, filter_type=kind, strict_reference=strict)
+    model = KalmanLogp(spec, y, n_draws=B, filter_type=kind, strict_reference=strict,
+                       pad_to_fused=not os.environ.get("KFB_NO_PAD"))
     th = torch.as_tensor(theta, device="cuda")
     times = []
     for it in range(4):
