@@ -48,7 +48,8 @@ class BatchedKalman:
 
     def __init__(self, kind: str, n: int, m: int, p: int, r: int, n_draws: int, n_series: int = 1,
                  strict_reference: bool = True, time_varying: Iterable[str] = (), device="cuda",
-                 force_coop: bool = False, generic_adjoint: bool = False, z_unit0: bool = False, h_zero: bool = False):
+                 force_coop: bool = False, generic_adjoint: bool = False, z_unit0: bool = False, h_zero: bool = False,
+                 pad_odd: bool = True):
         kind = kind.lower()
         if kind not in FILTER_KIND:
             raise NotImplementedError("The following are valid filter types: " + ", ".join(FILTER_KIND))
@@ -72,6 +73,15 @@ class BatchedKalman:
         self._held = None
         self._ws = None
         self._saved = False
+        # Odd k_states in 9..31 have no fused kernels of their own: the loglik (+ gradient) hot path runs the same model
+        # embedded in k_states + 1 states (the extra state has zero rows / columns everywhere, stays identically zero and
+        # adds only zeros to every product - exact, cf. models.pad_spec) on the tensor-core row kernels.
+        self._inner = None
+        self._via_inner = False
+        if (pad_odd and not force_coop and m % 2 == 1 and 9 <= m <= 31 and p == 1 and not self.time_varying
+                and self.n_series == 1 and kind in ("standard", "single", "cholesky", "steady_state")):
+            self._inner = BatchedKalman(kind, n, m + 1, p, r, n_draws, n_series, strict_reference, (), device,
+                                        generic_adjoint=generic_adjoint, pad_odd=False)
 
     # ------------------------------------------------------------------ helpers
     def _canon(self, name, t):
@@ -115,6 +125,10 @@ class BatchedKalman:
                 check_info=False, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``out``: optional caller-owned result buffers (name -> contiguous tensor of the documented shape, "info"
         included); anything not given is allocated.  Lets a captured CUDA graph write straight into a staging buffer."""
+        self._via_inner = self._inner is not None and set(outputs) <= {"loglik"} and y.ndim <= 3 and y.shape[0] == self.n
+        if self._via_inner:
+            return self._inner.forward(y, *self._pad_inputs(a0, P0, T, Z, R, H, Q, c), d=d, outputs=outputs,
+                                       save_for_backward=save_for_backward, check_info=check_info, out=out)
         if y.ndim >= 2 and y.shape[-1] == 1 and y.shape[-2] == self.p and y.ndim in (3, 4) and y.shape[-3] == self.n:
             y = y[..., 0]  # reference layout data[n,p,1]
         if not (y.is_cuda and y.dtype == torch.float64):
@@ -161,6 +175,18 @@ class BatchedKalman:
             self.raise_on_info(out["info"])
         return out
 
+    def _pad_inputs(self, a0, P0, T, Z, R, H, Q, c):
+        from torch.nn.functional import pad
+
+        m = self.m
+
+        def vec(t):  # [.., m] or [.., m, 1]
+            if t is None:
+                return None
+            return pad(t, (0, 0, 0, 1)) if (t.ndim >= 2 and t.shape[-1] == 1 and t.shape[-2] == m) else pad(t, (0, 1))
+
+        return (vec(a0), pad(P0, (0, 1, 0, 1)), pad(T, (0, 1, 0, 1)), pad(Z, (0, 1)), pad(R, (0, 0, 0, 1)), H, Q, vec(c))
+
     def _buffer(self, t, shape, dtype, name):
         if t is None:
             return torch.empty(shape, dtype=dtype, device=self.device)
@@ -191,6 +217,22 @@ class BatchedKalman:
                  wrt: Iterable[str] = MATRIX_NAMES, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Per-unit gradients of  sum_u (g_loglik[u] * loglik[u] + sum_t g_ll_obs[u,t] * ll_obs[u,t]).
         ``out``: optional caller-owned gradient buffers (see ``forward``)."""
+        if self._via_inner:
+            m, wrt = self.m, tuple(wrt)
+            g = self._inner.backward(g_loglik, g_ll_obs, wrt)
+            cut = {"a0": lambda t: t[:, :m], "c": lambda t: t[:, :m], "P0": lambda t: t[:, :m, :m], "T": lambda t: t[:, :m, :m],
+                   "Z": lambda t: t[:, :, :m], "R": lambda t: t[:, :m, :]}
+            res = {}
+            for k in wrt:
+                t = cut[k](g[k]) if k in cut else g[k]
+                buf = (out or {}).get(k)
+                if buf is not None:
+                    buf = self._buffer(buf, t.shape, torch.float64, k)
+                    buf.copy_(t)
+                    res[k] = buf
+                else:
+                    res[k] = t.contiguous()
+            return res
         if not self._saved:
             raise RuntimeError("backward() needs a preceding forward(..., save_for_backward=True)")
         U, n = self.units, self.n

@@ -197,7 +197,7 @@ class KalmanLogp:
         h_zero = p == 1 and not spec.maps.get("H") and not np.any(np.asarray(spec.base["H"]))
         self.kalman = BatchedKalman(filter_type, self.n, spec.k_states, spec.k_endog, spec.k_posdef, n_draws=self.B,
                                     strict_reference=strict_reference, device=device, force_coop=force_coop,
-                                    z_unit0=z_unit0, h_zero=h_zero)
+                                    z_unit0=z_unit0, h_zero=h_zero, pad_odd=pad_to_fused)
         m, pp, r = spec.k_states, spec.k_endog, spec.k_posdef
         self._shape = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (pp, m), "R": (m, r), "H": (pp, pp), "Q": (r, r),
                        "c": (m,), "d": (pp,)}

@@ -718,3 +718,39 @@ def test_fused_row_kernels_univariate(dims, wrt):
                 got = res[False][1][k][b].reshape(gref[k].shape)
                 scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
                 assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b, n)
+
+
+@pytest.mark.parametrize("kind", ["standard", "steady_state"])
+@pytest.mark.parametrize("m", [9, 13, 25, 31])
+def test_odd_k_states_run_padded_on_the_fused_kernels(m, kind):
+    """Matrix-level calls with an odd k_states in 9..31 (seasonal period 12 -> 13 states): BatchedKalman embeds the model
+    in k_states + 1 states for the loglik + gradient hot path (zero rows / columns: exact) instead of falling to the
+    run-time-dims kernels.  Same numbers as the unpadded generic path and as the oracle; shapes are the caller's."""
+    from pymc_statespace_b200 import BatchedKalman
+
+    rng = np.random.default_rng(500 + m)
+    B, n, p, r = 7, 18, 1, 2
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1) for _ in range(B)]
+    y = random_system(rng, m, p, r, n, n_missing=2)[0]
+    cs = rng.normal(size=(B, m))
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    wrt = ("a0", "P0", "T", "R", "H", "Q", "c") if kind == "standard" else ("a0", "T", "R", "H", "Q", "c")
+    res = {}
+    for padded in (True, False):
+        bk = BatchedKalman(kind, n, m, p, r, n_draws=B, pad_odd=padded)
+        assert (bk._inner is not None) == padded
+        out = bk.forward(_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7), c=_dev(cs),
+                         outputs=("loglik",), save_for_backward=True)
+        g = bk.backward(wrt=wrt)
+        assert int(out["info"].abs().max()) == 0
+        res[padded] = (out["loglik"].cpu().numpy(), {k: g[k].cpu().numpy() for k in wrt})
+    tol = 1e-7 if kind == "steady_state" else 1e-9
+    assert np.abs(res[True][0] - res[False][0]).max() < 1e-11 * np.abs(res[False][0]).max()
+    for k in wrt:
+        assert res[True][1][k].shape == res[False][1][k].shape, k
+        assert rel_err(res[True][1][k], res[False][1][k]) < tol, k
+    args = (y,) + tuple(systems[3][1:])
+    ref, gref = kt.loglik_and_grads(kind, *args, c=cs[3][:, None])
+    assert abs(res[True][0][3] - ref) < RTOL * abs(ref)
+    for k in wrt:
+        assert rel_err(res[True][1][k][3].reshape(gref[k].shape), gref[k]) < (1e-7 if kind == "steady_state" else RTOL), k
