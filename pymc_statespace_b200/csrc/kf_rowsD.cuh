@@ -117,11 +117,13 @@ __device__ __forceinline__ void rowD_store(double* rowp, const double (&v)[M]) {
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, j) = make_double2(v[2 * j], v[2 * j + 1]);
 }
+// act = false (a lane without a row, lanes >= k_states): no load is issued - 16-byte accesses are served per quarter warp,
+// so at k_states <= 16 the idle half of the warp would otherwise double the wavefronts of every row load.
 template <int M>
-__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp) {
+__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, bool act = true) {
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
-    const double2 x = *rowD_chunk(rowp, j);
+    const double2 x = act ? *rowD_chunk(rowp, j) : make_double2(0.0, 0.0);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
@@ -137,8 +139,8 @@ __device__ __forceinline__ double colD(const double* mat, int j, int i) {
 // (the mirrored tile), the diagonal tile is averaged.  Exactly symmetric by construction, and the loads of the tiles a
 // lane does not need are predicated off (whole 8-lane groups: fewer shared-memory wavefronts than the full row + column).
 template <int M, int LD>
-__device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat, int i) {
-  const int ti = i >> 3;
+__device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat, int i, bool act = true) {
+  const int ti = act ? (i >> 3) : 4;  // a lane without a row loads nothing from the row part
   const double* rowp = mat + i * LD;
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
@@ -198,7 +200,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 pk = *rowD_chunk(pr, k), ak = av[k];
+      const double2 pk = act ? *rowD_chunk(pr, k) : make_double2(0.0, 0.0), ak = av[k];
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -230,7 +232,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     const double* tr = sm + L::T + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = *rowD_chunk(tr, k);
+      const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -275,7 +277,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     double* lr = sm + L::Lm + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      double2 lk = *rowD_chunk(tr, k);
+      double2 lk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
@@ -360,7 +362,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = *rowD_chunk(tr, k), ak = av[k];
+        const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -406,7 +408,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
     const bool taped = tp && t + 1 < n;
     {
       double S[M];
-      rowD_load_symU<M, LD>(S, sm + L::X, i);
+      rowD_load_symU<M, LD>(S, sm + L::X, i, act);
 #pragma unroll
       for (int j = 0; j < M; ++j) S[j] += Cs[j];
       if (observed) {
@@ -550,7 +552,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
     if (t == 0) {  // P0 may be any matrix: L-bar = W (P + P^T); for t >= 1 the taped P is symmetric: P + P^T = 2 P
       double S0[M];
-      rowD_load<M>(S0, sm + L::Pm + i * LD);
+      rowD_load<M>(S0, sm + L::Pm + i * LD, act);
 #pragma unroll
       for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD<LD>(sm + L::Pm, j, i));
       if (observed) {  // lz = (P + P^T) Z^T rows
@@ -571,7 +573,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     cb += abi;
     double Ps[M];  // without T-bar the row stays in registers for phase 2; with it (64 more accumulators) it is re-read
     {
-      rowD_load_symU<M, LD>(Ps, sm + L::Pb, i);
+      rowD_load_symU<M, LD>(Ps, sm + L::Pb, i, act);
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         const double mi = 0.5 * sm[L::Mb + i * P + k], zi = 0.5 * sm[L::Z + k * M + i];
@@ -590,7 +592,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     {
       double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
-      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD);
+      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD, act);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y2) {  // (Kp is stale but unused when nothing is observed)
@@ -621,7 +623,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     if (observed) {
       double Wr[M];
-      rowD_load<M>(Wr, sm + L::W + i * LD);
+      rowD_load<M>(Wr, sm + L::W + i * LD, act);
       const double* m2 = (t == 0) ? sm + L::lz : sm + L::Mm;
       const double sc = (t == 0) ? 1.0 : 2.0;
 #pragma unroll
@@ -774,7 +776,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   // ---- write-out (row i by lane i): P-bar = symU(L^T W) + Mb Z of step 0
   {
     double Pf[M];
-    rowD_load_symU<M, LD>(Pf, sm + L::Pb, i);
+    rowD_load_symU<M, LD>(Pf, sm + L::Pb, i, act);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       const double mi = sm[L::Mb + i * P + k];
@@ -928,7 +930,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
       mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
     }
     __syncwarp();
-    rowD_load_symU<M, LD>(U, sm + L::X, i);
+    rowD_load_symU<M, LD>(U, sm + L::X, i, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) S[j] += U[j];
     if (act) rowD_store<M>(sm + L::Pm + i * LD, S);
@@ -948,7 +950,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     bool ok = false;
     for (int db = 0; db < 64; ++db) {  // Xs <- sum_k A^k Xs A^kT, A = Lm (destroyed)
       double Ar[M], mx = 0.0;
-      rowD_load<M>(Ar, sm + L::Lm + i * LD);
+      rowD_load<M>(Ar, sm + L::Lm + i * LD, act);
 #pragma unroll
       for (int j = 0; j < M; ++j) mx = fmax(mx, fabs(Ar[j]));
       mx = warp_max(mx);
@@ -967,8 +969,8 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     }
     if (!ok) { info = 1; break; }
     double Pn[M], Po[M], diff = 0.0, mag = 0.0;
-    rowD_load<M>(Pn, sm + L::Xs + i * LD);
-    rowD_load<M>(Po, sm + L::Pm + i * LD);
+    rowD_load<M>(Pn, sm + L::Xs + i * LD, act);
+    rowD_load<M>(Po, sm + L::Pm + i * LD, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       diff = fmax(diff, fabs(Pn[j] - Po[j]));
@@ -987,7 +989,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
   if (!g.ok) info = 1;
   if (act) {
     double Pr[M];
-    rowD_load<M>(Pr, sm + L::Pm + i * LD);
+    rowD_load<M>(Pr, sm + L::Pm + i * LD, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) Pss[i * M + j] = info ? nan("") : Pr[j];
   }
