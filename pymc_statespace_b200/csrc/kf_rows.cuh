@@ -38,10 +38,12 @@ struct RowsLayout {
   // forward only
   static constexpr int S2 = END_COMMON, END_FWD = S2 + MM;
   // adjoint only (tp: double-buffered cp.async landing zone for the packed tape entry)
-  static constexpr int Pb = END_COMMON, X = Pb + MM, TMb = X, W = NZ ? X + MM : Pm, Lb = X + 2 * MM,
+  // (W = Ps L has a slot of its own: round 1 formed X = L (P + P^T) there first and kept W in Pm's slot; L-bar = Ps X is now
+  //  computed as W (P + P^T) from the lane's own W rows, so P is still being read when W is stored)
+  static constexpr int Pb = END_COMMON, X = Pb + MM, W = NZ ? X + MM : X, Lb = X + 2 * MM,
                        Kb = NZ ? Lb + MM : X + MM, Mb = Kb + MPE, PK = NZ ? Mb + MPE : Kb + MPE, TMs = PK + MPE,
                        ab = TMs + (ST ? MPE : 0),
-                       Cb = ab + M + (M & 1), tp = Cb + MM, END_BWD = tp + 2 * KTP;
+                       Cb = ab + M + (M & 1), tp = Cb + MM, TMb = tp + 2 * KTP, END_BWD = TMb + MPE;
   // unit stride == 6 (mod 16) doubles = 48 bytes modulo the 128-byte bank row: with 16-byte accesses served a quarter
   // warp (two units of 4 lanes) at a time, both the lanes' row blocks (96 bytes apart) and their column blocks (16 bytes
   // apart) of two neighbouring units then fall on distinct bank groups.  Measured: a stride == 0 (mod 4) gave 8-way
@@ -601,7 +603,7 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
       store_rows<M, R, M>(sm + L::Lm, rw, g.Lm);
       __syncwarp(mask);
     }
-    // ---- phase 1: Ps rows (registers), X = L (P + P^T) rows ; Cb, cb
+    // ---- phase 1: Ps rows (registers) ; Cb, cb
     double Ps[R][M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -613,49 +615,42 @@ __device__ void rows_backward(const KfArgs& A, long long u, double* sm, int l, u
     accumulate_rows<M, R, M>(sm + L::Cb, rw, Ps);
 #pragma unroll
     for (int q = 0; q < R; ++q) cb[q] += abi[q];
-    {
-      double Xr[R][M];
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        double s[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) s[q] = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          const double b = sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k];
-#pragma unroll
-          for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < R; ++q) Xr[q][j] = s[q];
-      }
-      store_rows<M, R, M>(sm + L::X, rw, Xr);
-    }
-    __syncwarp(mask);
-    // ---- phase 2: Lb = Ps X, W = Ps L, T^T ab, (observed) PK = Ps Kp, Kb
+    // ---- phase 2: W = Ps L, Lb = Ps L (P + P^T) = W (P + P^T) from the lane's own W rows (round 1: X = L (P + P^T) rows
+    //      through shared memory, then Ps X: one m^3 product, one row store and one sync more per step), T^T ab,
+    //      (observed) PK = Ps Kp, Kb
     double Lb[R][M], PK[R][P], Kb[R][P], abn[R];
     {
     double Wr[R][M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      double s[R], s2[R];
+      double s2[R];
 #pragma unroll
-      for (int q = 0; q < R; ++q) s[q] = s2[q] = 0.0;
+      for (int q = 0; q < R; ++q) s2[q] = 0.0;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        const double bx = sm[L::X + k * M + j], bl = sm[L::Lm + k * M + j];
+        const double bl = sm[L::Lm + k * M + j];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-          s[q] = fma(Ps[q][k], bx, s[q]);
-          s2[q] = fma(Ps[q][k], bl, s2[q]);
-        }
+        for (int q = 0; q < R; ++q) s2[q] = fma(Ps[q][k], bl, s2[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) Wr[q][j] = s2[q];
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double b = sm[L::Pm + k * M + j] + sm[L::Pm + j * M + k];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = fma(Wr[q][k], b, s[q]);
       }
       const double aj = sm[L::a + j];
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         Lb[q][j] = s[q];
         Tb[q][j] += fma(abi[q], aj, s[q]);  // Tb += ab a^T + Lb
-        Wr[q][j] = s2[q];
       }
     }
     store_rows<M, R, M>(sm + L::W, rw, Wr);
