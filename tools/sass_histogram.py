@@ -13,15 +13,19 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNELS = [  # (object glob, demangled-name regex, label)
-    ("kf_p1.o", r"kf_p1_forward_kernel<2, true>", "headline forward: k_endog = 1, k_states = 2, loglik + tape"),
-    ("kf_p1.o", r"kf_p1_adjoint_kernel<2, false, false, false>", "headline adjoint: TMA tape ring"),
-    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 0>", "generic thread-per-unit forward (A/B reference)"),
-    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 2>", "generic thread-per-unit adjoint (cp.async ring)"),
-    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 1>", "full-output forward (filtered / predicted moments)"),
+    ("kf_p1.o", r"kf_p1_forward_kernel<2, true, true, true>", "headline forward: k_endog = 1, k_states = 2, loglik + tape (Z = e0, H = 0 promised)"),
+    ("kf_p1.o", r"kf_p1_adjoint_kernel<2, false, false, false, true, true>", "headline adjoint: TMA tape ring (Z = e0, H = 0 promised)"),
+    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 0, false>", "generic thread-per-unit forward (A/B reference)"),
+    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 2, false>", "generic thread-per-unit adjoint (cp.async ring)"),
+    ("kf_thread_m2.o", r"kf_thread_kernel<2, 1, 0, 1, false>", "full-output forward (filtered / predicted moments)"),
     ("kf_coopT_m6.o", r"kf_rows_kernel<6, 3, 4, 0, false, false>", "config 3 forward: fused rows, k_states = 6"),
     ("kf_coopT_m6.o", r"kf_rows_kernel<6, 3, 4, 0, true, false>", "config 3 adjoint: fused rows"),
     ("kf_coopT_m30.o", r"kf_rowsD_kernel<30, 1, 0, false, false>", "config 4 forward: DMMA tile products"),
     ("kf_coopT_m30.o", r"kf_rowsD_kernel<30, 1, 0, true, false>", "config 4 adjoint: DMMA tile products"),
+    ("kf_coopT_m30.o", r"kf_rowsD_kernel<30, 1, 0, true, true>", "config 4 adjoint with T-bar: T-bar accumulated on the tensor cores"),
+    ("kf_coopT_m30.o", r"kf_dareD_kernel<30, 1>", "steady-state covariance (DARE) on the tensor cores, k_states = 30"),
+    ("kf_coopT_m14.o", r"kf_rowsD_kernel<14, 1, 0, false, false>", "k_states 14 forward: 16 x 16 tiles"),
+    ("kf_coopT_m14.o", r"kf_rowsD_kernel<14, 1, 0, true, false>", "k_states 14 adjoint: 16 x 16 tiles"),
 ]
 SHOW = ("UBLKCP", "SYNCS", "LDGSTS", "DFMA", "DMUL", "DADD", "DSETP", "DMMA", "MUFU", "LDS", "STS", "LDG", "LD", "STG",
         "SHFL", "BAR", "WARPSYNC", "BRA", "FSEL", "IMAD", "IADD3")
