@@ -33,3 +33,20 @@ out = bk.forward(dev(yy), dev(a0), dev(P0), dev(T), dev(Z), dev(R), dev(H), dev(
 gg = bk.backward(wrt=("a0", "P0", "T", "R", "H", "Q"))
 torch.cuda.synchronize()
 print("k30 with T-bar: loglik sum", float(out["loglik"].sum()), "gT abs sum", float(gg["T"].abs().sum()))
+
+# round 2: steady state (DARE on the tensor cores) at k_states 30, and the 16 x 16 tile kernels (k_states 13 -> 14)
+for period, kind in ((29, "steady_state"), (12, "standard"), (12, "steady_state")):
+    spec, y, theta = trend_seasonal_workload(n_draws=6, n=12, period=period)
+    m = KalmanLogp(spec, y, n_draws=6, filter_type=kind)
+    lp, g = m.logp_and_grad(torch.as_tensor(theta, device="cuda"))
+    torch.cuda.synchronize()
+    print("period", period, kind, "logp sum", float(lp.sum()), "grad abs sum", float(g.abs().sum()))
+B, n, mm, p, r = 5, 10, 12, 1, 2
+T = rng.normal(size=(B, mm, mm)) * 0.1 / np.sqrt(mm); Z = rng.normal(size=(B, p, mm)); R = rng.normal(size=(B, mm, r))
+H = np.tile(np.eye(p) * 0.5, (B, 1, 1)); Q = np.tile(np.eye(r) * 0.3, (B, 1, 1))
+a0 = rng.normal(size=(B, mm)); P0 = np.tile(np.eye(mm), (B, 1, 1)); yy = rng.normal(size=(n, p)); yy[3] = np.nan
+bk = BatchedKalman("standard", n, mm, p, r, n_draws=B)
+out = bk.forward(dev(yy), dev(a0), dev(P0), dev(T), dev(Z), dev(R), dev(H), dev(Q), outputs=("loglik",), save_for_backward=True)
+gg = bk.backward(wrt=("a0", "P0", "T", "R", "H", "Q"))
+torch.cuda.synchronize()
+print("k12 with T-bar: loglik sum", float(out["loglik"].sum()), "gT abs sum", float(gg["T"].abs().sum()))
