@@ -213,6 +213,17 @@ __global__ void __launch_bounds__(128, M <= 16 ? KFB_ROWSH_MINB : 1) kf_rowsD_ke
   else rowsD_forward<M, P, MK>(A, u, sm, threadIdx.x & 31);
 }
 
+// same mapping, all six outputs of the reference (rowsD_forward_full)
+template <int M, int P, int MK>
+__global__ void __launch_bounds__(128, M <= 16 ? KFB_ROWSH_MINB : 1) kf_rowsDfull_kernel(const __grid_constant__ KfArgs A) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int per_unit = RowsDLayout<M, P, false>::fwd_doubles;
+  const int warp = threadIdx.x >> 5;
+  const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (u >= A.U) return;
+  rowsD_forward_full<M, P, MK>(A, u, kf_dyn_smem + (size_t)warp * per_unit, threadIdx.x & 31);
+}
+
 // ---- steady-state (DARE) kernels: one warp or one CTA per draw / unit (kf_dare.cuh) ----
 struct DareArgs {
   long long nD, U, n_series;

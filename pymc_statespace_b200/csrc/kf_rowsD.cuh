@@ -182,7 +182,8 @@ struct RowDGain {
 // v, Mm | TM, F, F^-1, w, quad, Kp, Lm for an observed step (row-per-lane).  Leaves Mm, Kp, Lm in shared memory (visible
 // after the trailing sync); returns the lane's Kp row and (every lane) v, F^-1, w.
 // MK_STEADY: the gain matrix is the fixed Gss = (Z Pss Z^T + H)^-1 instead of F^-1 (F is still factorised for log det).
-template <int M, int P, int MK, class L, bool PADL = false>
+// IDT: T := I, i.e. the FILTER gain K = P Z^T F^-1 and A = I - K Z in Kp / Lm (full-output forward pass).
+template <int M, int P, int MK, class L, bool PADL = false, bool IDT = false>
 __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], double d_sign, const double (&dv)[P],
                                            const double (&Gss)[P * P], int i, bool act, RowDGain<M, P>& g,
                                            bool full_det = false) {
@@ -232,7 +233,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     const double* tr = sm + L::T + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
+      const double2 tk = (act && !IDT) ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
 #pragma unroll
     for (int k = 0; k < P * P; ++k) Fr[k] = (Fq[k][0] + Fq[k][1]) + (Fq[k][2] + Fq[k][3]);
 #pragma unroll
-    for (int j = 0; j < P; ++j) TM[j] = (Tq[j][0] + Tq[j][1]) + (Tq[j][2] + Tq[j][3]);
+    for (int j = 0; j < P; ++j) TM[j] = IDT ? sm[L::Mm + i * P + j] : (Tq[j][0] + Tq[j][1]) + (Tq[j][2] + Tq[j][3]);
   }
   g.ok = ldl_inverse(Fr, g.Fi, Lr, Lir, g.piv, P);
   if (MK == MK_STD && P > 1 && full_det && g.ok) g.ok = lu_pivots(Fr, Lr, g.piv, P);  // det of the full matrix (t = 0)
@@ -277,7 +278,8 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     double* lr = sm + L::Lm + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      double2 lk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
+      double2 lk = IDT ? make_double2(i == 2 * k ? 1.0 : 0.0, i == 2 * k + 1 ? 1.0 : 0.0)
+                       : (act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0));
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
@@ -443,6 +445,195 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ forward, all outputs
+// The reference's six outputs (filtered / predicted moments, ll_obs: kalman_filter.py:166-193) need the two-stage form:
+//     A = I - K Z,  P_f = A P A^T + K H K^T (Joseph, :255-284),  a_f = a + K v ;  P' = sym(T P_f T^T + C),  a' = T a_f + c
+// = four tile products per observed step (A P, the upper tiles of (A P) A^T, T P_f, the upper tiles of (T P_f) T^T), two
+// per unobserved one.  Output rows are written by their lanes as 16-byte stores: a warp writes each m x m matrix as one
+// contiguous run.  (Round 1 / 2 ran this request on the generic CTA-per-unit kernels: 0.32 TB/s at k_states 30.)
+template <int M>
+__device__ __forceinline__ void rowG_store(double* dst, const double (&v)[M]) {
+#pragma unroll
+  for (int j = 0; j < M / 2; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(v[2 * j], v[2 * j + 1]);
+}
+
+template <int M, int P, int MK>
+__device__ void rowsD_forward_full(const KfArgs& A, long long u, double* sm, int lane) {
+  using L = RowsDLayout<M, P, false>;
+  constexpr int KT = L::KT, LD = L::LD;
+  const int n = A.n;
+  const long long draw = u / A.n_series;
+  const bool act = lane < M;
+  const int i = act ? lane : 0;
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* Cp = A.C.p + draw * A.C.bs;
+  const double* P0g = A.P0.p + draw * A.P0.bs;
+  const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : P0g;  // steady: the recursion starts at Pss
+  double Gss[P * P];
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
+  for (int k = lane; k < L::fwd_doubles; k += 32) sm[k] = 0.0;  // zero padding everywhere
+  __syncwarp();
+  for (int k = lane; k < M * M; k += 32) {
+    const int rr = k / M, cc = k - rr * M;
+    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::Pm + rr * LD + cc] = P0p[k];
+  }
+  for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
+  for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
+  const double a0i = A.a0.p[draw * A.a0.bs + i];
+  if (act) sm[L::a + i] = a0i;
+  double Cs[M];  // the lane's row of sym(C), C = R Q R^T (static): registers
+#pragma unroll
+  for (int j = 0; j < M; ++j) Cs[j] = 0.5 * (Cp[i * M + j] + Cp[j * M + i]);
+  const double ci = (act && A.c.p) ? A.c.p[draw * A.c.bs + i] : 0.0;
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
+  // row 0 of the predicted moments = the caller's a0 / P0 (steady state: P0 is reported but not used, :397)
+  if (act) {
+    if (A.ps) A.ps[u * (long long)(n + 1) * M + i] = a0i;
+    if (A.pc) {
+      double r0[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) r0[j] = P0g[i * M + j];
+      rowG_store<M>(A.pc + (u * (long long)(n + 1)) * M * M + i * M, r0);
+    }
+  }
+  __syncwarp();
+
+  const double* y = A.y.p;
+  double llsum = 0.0;
+  int info = 0;
+  double* tp = A.tape ? A.tape + u * (long long)(n - 1) * KT : nullptr;
+  RowDGain<M, P> g;
+  double yt[P], ynx[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[j];
+
+  for (int t = 0; t < n; ++t) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t + 1 < n ? t + 1 : t) * P + j];
+    }
+    int nm = 0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) nm += (yt[j] != yt[j]) ? 1 : 0;
+    const bool observed = (nm == 0);
+    double af = sm[L::a + i], ll = 0.0;
+    if (observed) {
+      // K, A = I - K Z (in Kp / Lm), v, F^-1
+      rowsD_gain<M, P, MK, L, false, true>(sm, yt, A.d_sign, dv, Gss, i, act, g, t == 0);
+      if (!g.ok && info == 0) info = t + 1;
+      double ld = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) ld += log(g.piv[k]);
+      ll = g.ok ? -0.5 * (A.ll_const + ld + g.quad) : nan("");
+#pragma unroll
+      for (int k = 0; k < P; ++k) af = fma(g.Kp[k], g.v[k], af);
+      double KH[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        KH[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) KH[j] = fma(g.Kp[k], sm[L::H + k * P + j], KH[j]);
+        if (act) sm[L::KH + i * P + j] = KH[j];
+      }
+      // P_f = A P A^T + K H K^T
+      {
+        double c4[L::NT][L::NT][2];
+        mm32<false, false, LD>(c4, sm + L::Lm, sm + L::Pm, lane);
+        mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+        __syncwarp();
+        mm32<false, true, LD, true, true>(c4, sm + L::X, sm + L::Lm, lane);
+        mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
+      }
+      __syncwarp();
+      double S[M];
+      rowD_load_symU<M, LD>(S, sm + L::X, i, act);
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+          S[j] = fma(0.5, fma(KH[k], sm[L::Kp + j * P + k], sm[L::KH + j * P + k] * g.Kp[k]), S[j]);
+      }
+      if (act) {
+        rowD_store<M>(sm + L::Pm + i * LD, S);
+        if (A.fc) rowG_store<M>(A.fc + (u * (long long)n + t) * M * M + i * M, S);
+      }
+    } else {
+      if (nm != P && info == 0) info = -(t + 1);
+      if (act && A.fc) {
+        double S[M];
+        rowD_load<M>(S, sm + L::Pm + i * LD, act);
+        rowG_store<M>(A.fc + (u * (long long)n + t) * M * M + i * M, S);
+      }
+    }
+    llsum += ll;
+    if (act) {
+      sm[L::a + i] = af;
+      if (A.fs) A.fs[(u * (long long)n + t) * M + i] = af;
+    }
+    if (lane == 0 && A.ll_obs) A.ll_obs[u * (long long)n + t] = ll;
+    __syncwarp();  // a_f and P_f visible
+    // predict: a' = T a_f + c ; P' = sym(T P_f T^T + C)
+    double an;
+    {
+      double aq[4] = {ci, 0.0, 0.0, 0.0};
+      const double* tr = sm + L::T + i * LD;
+      const double2* av = reinterpret_cast<const double2*>(sm + L::a);
+#pragma unroll
+      for (int k = 0; k < M / 2; ++k) {
+        const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0), ak = av[k];
+        const int q = (k & 1) * 2;
+        aq[q] = fma(tk.x, ak.x, aq[q]);
+        aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
+      }
+      an = (aq[0] + aq[1]) + (aq[2] + aq[3]);
+    }
+    {
+      double c4[L::NT][L::NT][2];
+      mm32<false, false, LD>(c4, sm + L::T, sm + L::Pm, lane);
+      mm32_store<LD>(sm + L::X, c4, 1.0, lane);
+      __syncwarp();
+      mm32<false, true, LD, true, true>(c4, sm + L::X, sm + L::T, lane);
+      mm32_store<LD, true>(sm + L::X, c4, 1.0, lane);
+    }
+    __syncwarp();
+    const bool taped = tp && t + 1 < n;
+    {
+      double S[M];
+      rowD_load_symU<M, LD>(S, sm + L::X, i, act);
+#pragma unroll
+      for (int j = 0; j < M; ++j) S[j] += Cs[j];
+      if (act) {
+        rowD_store<M>(sm + L::Pm + i * LD, S);
+        sm[L::a + i] = an;
+        if (A.ps) A.ps[(u * (long long)(n + 1) + t + 1) * M + i] = an;
+        if (A.pc) rowG_store<M>(A.pc + (u * (long long)(n + 1) + t + 1) * M * M + i * M, S);
+        if (taped) {
+          tp[i] = an;
+          double* trow = tp + M + i * M - (i * (i - 1)) / 2 - i;
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+            if (j >= i) trow[j] = S[j];
+        }
+      }
+    }
+    if (taped) tp += KT;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (info != 0) llsum = nan("");
+    if (A.loglik) A.loglik[u] = llsum;
+    if (MK == MK_STEADY && A.dare_info && A.dare_info[u / A.n_series] != 0) info = KF_INFO_DARE_FAILED;
+    if (A.info) A.info[u] = info;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ adjoint
 // Per step (going backwards), with Ps = sym(P-bar') the symmetrised cotangent of the step above:
