@@ -181,6 +181,25 @@ __global__ void __launch_bounds__(128, (RowsCfg<M, P, G>::R > 1) ? 1 : (BWD ? (N
   else rows_forward<M, P, G, MK>(A, u, sm, l, mask);
 }
 
+// same mapping, all six outputs of the reference (rows_forward_full)
+template <int M, int P, int G, int MK>
+__global__ void __launch_bounds__(128, 1) kf_rowsfull_kernel(const __grid_constant__ KfArgs A) {
+  extern __shared__ __align__(16) double kf_dyn_smem[];
+  constexpr int per_unit = RowsLayout<M, P>::fwd_doubles;
+  constexpr int UPW = RowsCfg<M, P, G>::UPW;
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int grp = lane32 / G, l = lane32 - grp * G;
+  if (grp >= UPW) {
+    grp = 0;
+    l = G;
+  }
+  const int slot = warp * UPW + grp;
+  const long long u = (long long)blockIdx.x * ((blockDim.x >> 5) * UPW) + slot;
+  if (u >= A.U) return;
+  const unsigned mask = __activemask();
+  rows_forward_full<M, P, G, MK>(A, u, kf_dyn_smem + (size_t)slot * per_unit, l, mask);
+}
+
 // Fused UnivariateFilter programs (kf_rowsU.cuh): 8 lanes per unit, 4 units per warp.  BWD = adjoint (no Z-bar).
 template <int M, int P, bool BWD>
 __global__ void __launch_bounds__(128, BWD ? 2 : 3) kf_rowsU_kernel(const __grid_constant__ KfArgs A) {

@@ -460,6 +460,231 @@ __device__ void rows_forward(const KfArgs& A, long long u, double* sm, int l, un
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, all outputs
+// The reference's six outputs (kalman_filter.py:166-193) on the same mapping: two-stage form
+//     A = I - K Z,  P_f = A P A^T + K H K^T,  a_f = a + K v ;  P' = sym(T P_f T^T + C),  a' = T a_f + c
+// (rows_gain with T := I yields the filter gain K and A).  MK_STD / MK_STEADY.  Rows go out as 16-byte stores, a unit's
+// matrix as one contiguous run.  (Before: the generic sub-warp kernels, 0.73 TB/s written at k_states 6.)
+template <int M, int P, int G, int MK>
+__device__ void rows_forward_full(const KfArgs& A, long long u, double* sm, int l, unsigned mask) {
+  using L = RowsLayout<M, P>;
+  constexpr int R = RowsCfg<M, P, G>::R;
+  constexpr int KT = L::KT;
+  const int n = A.n;
+  const long long draw = u / A.n_series;
+  const RowIdx<M, R> rw(l);
+  const double* Tp = A.T.p + draw * A.T.bs;
+  const double* Zp = A.Z.p + draw * A.Z.bs;
+  const double* Hp = A.H.p + draw * A.H.bs;
+  const double* Cp = A.C.p + draw * A.C.bs;
+  const double* P0g = A.P0.p + draw * A.P0.bs;
+  const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : P0g;  // steady: the recursion starts at Pss
+  const double* a0p = A.a0.p + draw * A.a0.bs;
+  double Gss[P * P];
+#pragma unroll
+  for (int k = 0; k < P * P; ++k) Gss[k] = (MK == MK_STEADY) ? A.Gss.p[draw * A.Gss.bs + k] : 0.0;
+  if (l < G) {
+    for (int k = l; k < M * M; k += G) {
+      sm[L::T + k] = Tp[k];
+      sm[L::Pm + k] = P0p[k];
+    }
+    for (int k = l; k < P * M; k += G) sm[L::Z + k] = Zp[k];
+    for (int k = l; k < P * P; k += G) sm[L::H + k] = Hp[k];
+  }
+  double Tr[R][M], Cr[R][M], Pr[R][M], ci[R], af[R];
+  {
+    double r0[R][M];  // row 0 of the predicted moments = the caller's a0 / P0 (steady state: reported, not used, :397)
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        Tr[q][j] = Tp[rw.c[q] * M + j];
+        Cr[q][j] = Cp[rw.c[q] * M + j];
+        Pr[q][j] = P0p[rw.c[q] * M + j];
+        r0[q][j] = P0g[rw.c[q] * M + j];
+      }
+      ci[q] = (rw.a[q] && A.c.p) ? A.c.p[draw * A.c.bs + rw.r[q]] : 0.0;
+      af[q] = a0p[rw.c[q]];
+      if (rw.a[q]) sm[L::a + rw.r[q]] = af[q];
+    }
+    if (l < G) {
+      if (A.ps) store_block<M, R>(A.ps + u * (long long)(n + 1) * M, rw, af);
+      if (A.pc) store_rows<M, R, M>(A.pc + u * (long long)(n + 1) * M * M, rw, r0);
+    }
+  }
+  double dv[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) dv[j] = A.d.p ? A.d.p[draw * A.d.bs + j] : 0.0;
+  __syncwarp(mask);
+  auto idt = [&](int q, int k) { return rw.c[q] == k ? 1.0 : 0.0; };
+
+  const double* y = A.y.p;
+  double llsum = 0.0;
+  int info = 0;
+  double* tp = A.tape ? A.tape + u * (long long)(n - 1) * KT : nullptr;
+  RowGain<M, P, R> g;
+  double yt[P], ynx[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) ynx[j] = y[j];
+  for (int t = 0; t < n; ++t) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      yt[j] = ynx[j];
+      ynx[j] = y[(long long)(t + 1 < n ? t + 1 : t) * P + j];
+    }
+    const int nm = rows_count_missing<P>(yt);
+    double S1[R][M], S2[R][M], ll = 0.0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) af[q] = sm[L::a + rw.c[q]];
+    if (nm == 0) {
+      rows_gain<M, P, R, MK>(sm, yt, A.d_sign, dv, mask, rw, idt, Pr, Gss, g, t == 0);  // K (in Kp), A = I - K Z (in Lm)
+      if (!g.ok && info == 0) info = t + 1;
+      double ld = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) ld += log(g.piv[k]);
+      ll = g.ok ? -0.5 * (A.ll_const + ld + g.quad) : nan("");
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) af[q] = fma(g.Kp[q][k], g.v[k], af[q]);
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) {  // S1 = A P
+        double s[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Pm + k * M + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(g.Lm[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) S1[q][j] = s[q];
+      }
+      double KH[R][P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        double s[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::H + k * P + j];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(g.Kp[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) KH[q][j] = s[q];
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) {  // P_f = S1 A^T + (K H) K^T
+        double s[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double b = sm[L::Lm + j * M + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(S1[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const double b = sm[L::Kp + j * P + k];
+#pragma unroll
+          for (int q = 0; q < R; ++q) s[q] = fma(KH[q][k], b, s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) Pr[q][j] = s[q];
+      }
+      __syncwarp(mask);  // every lane has read P (S1) and A, K: P_f may replace P
+      store_rows<M, R, M>(sm + L::Pm, rw, Pr);
+    } else if (nm != P && info == 0) {
+      info = -(t + 1);
+    }
+    llsum += ll;
+    if (l < G) {
+      if (A.fs) store_block<M, R>(A.fs + (u * (long long)n + t) * M, rw, af);
+      if (A.fc) store_rows<M, R, M>(A.fc + (u * (long long)n + t) * M * M, rw, Pr);
+    }
+    store_block<M, R>(sm + L::a, rw, af);
+    if (l == 0 && A.ll_obs) A.ll_obs[u * (long long)n + t] = ll;
+    __syncwarp(mask);  // a_f and P_f visible
+    // ---- predict: a' = T a_f + c ; P' = sym(T P_f T^T + C)
+    double an[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) an[q] = ci[q];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double ak = sm[L::a + k];
+#pragma unroll
+      for (int q = 0; q < R; ++q) an[q] = fma(Tr[q][k], ak, an[q]);
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double b = sm[L::Pm + k * M + j];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = fma(Tr[q][k], b, s[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) S1[q][j] = s[q];
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) s[q] = Cr[q][j];
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double b = sm[L::T + j * M + k];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = fma(S1[q][k], b, s[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) S2[q][j] = s[q];
+    }
+    store_rows<M, R, M>(sm + L::S2, rw, S2);
+    __syncwarp(mask);
+    const bool taped = tp && t + 1 < n;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double col[R];
+      lane_block<M, R>(sm + L::S2 + j * M, rw, col);
+#pragma unroll
+      for (int q = 0; q < R; ++q) Pr[q][j] = 0.5 * (S2[q][j] + col[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+      if (rw.a[q]) {
+        const int i = rw.r[q];
+        if (taped) tp[i] = an[q];
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+          if (taped && j >= i) tp[M + i * M - (i * (i - 1)) / 2 + (j - i)] = Pr[q][j];
+      }
+    store_block<M, R>(sm + L::a, rw, an);
+    store_rows<M, R, M>(sm + L::Pm, rw, Pr);
+    if (l < G) {
+      if (A.ps) store_block<M, R>(A.ps + (u * (long long)(n + 1) + t + 1) * M, rw, an);
+      if (A.pc) store_rows<M, R, M>(A.pc + (u * (long long)(n + 1) + t + 1) * M * M, rw, Pr);
+    }
+    if (taped) tp += KT;
+    __syncwarp(mask);
+  }
+  if (l == 0) {
+    if (info != 0) llsum = nan("");
+    if (A.loglik) A.loglik[u] = llsum;
+    if (MK == MK_STEADY && A.dare_info && A.dare_info[u / A.n_series] != 0) info = KF_INFO_DARE_FAILED;
+    if (A.info) A.info[u] = info;
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------ adjoint
 // Asynchronous copy of one packed tape entry (KT doubles) into shared memory, G lanes cooperating (LDGSTS).
 template <int KT, int G>

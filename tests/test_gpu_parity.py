@@ -757,18 +757,22 @@ def test_odd_k_states_run_padded_on_the_fused_kernels(m, kind):
 
 
 @pytest.mark.parametrize("kind", ["standard", "steady_state"])
-@pytest.mark.parametrize("dims", [(12, 1, 2), (16, 1, 3), (30, 1, 3)], ids=lambda d: "m%dp%dr%d" % d)
+@pytest.mark.parametrize("dims", [(12, 1, 2), (16, 1, 3), (30, 1, 3), (5, 1, 2), (6, 3, 3), (7, 2, 2), (8, 3, 3)],
+                         ids=lambda d: "m%dp%dr%d" % d)
 def test_full_outputs_on_the_tensor_core_mapping(dims, kind):
-    """All six outputs of the reference (kalman_filter.py:166-193) at even k_states 10..32, k_endog 1, run
-    rowsD_forward_full (two-stage form as tile products).  Every output against the oracle, with missing rows, c and d;
+    """All six outputs of the reference (kalman_filter.py:166-193) at k_states 5..8 (rows_forward_full, 4 lanes x 2 rows)
+    and at even k_states 10..32, k_endog 1 (rowsD_forward_full, two-stage form as tile products).  Every output against the oracle, with missing rows, c and d;
     the tape written by this kernel feeds the fused adjoint (same gradients as after a loglik-only forward)."""
     from pymc_statespace_b200 import BatchedKalman
 
     m, p, r = dims
     rng = np.random.default_rng(900 + m)
     B, n = 5, 14
-    systems = [random_system(rng, m, p, r, n, scale_T=0.1) for _ in range(B)]
-    y = random_system(rng, m, p, r, n, n_missing=3)[0]
+    B = 5 if m >= 10 else 13  # k_states 5..8: 8 units per warp - a partial second warp
+    systems = [random_system(rng, m, p, r, n, scale_T=0.1 if m >= 10 else 0.25) for _ in range(B)]
+    # (the as-coded steady-state filter, K = P Z^T F_ss^-1 with the CURRENT P, loses positive definiteness after missing
+    #  rows for most random systems with k_endog > 1: it is exercised on complete data)
+    y = random_system(rng, m, p, r, n, n_missing=0 if kind == "steady_state" else 3)[0]
     cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, p))
     stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
     ins = (_dev(y[..., 0]), stack(1), stack(2), stack(3), stack(4), stack(5), stack(6), stack(7))
@@ -776,8 +780,15 @@ def test_full_outputs_on_the_tensor_core_mapping(dims, kind):
     out = bk.forward(*ins, c=_dev(cs), d=_dev(ds), outputs=ALL_OUT, save_for_backward=True)
     wrt = ("a0", "T", "R", "H", "Q", "c")
     g_full = bk.backward(wrt=wrt)
-    assert int(out["info"].abs().max()) == 0
-    for b in (0, 4):
+    # units are flagged exactly like on the generic kernels; the good ones are compared with them and with the oracle
+    info = out["info"].cpu().numpy()
+    gen = BatchedKalman(kind, n, m, p, r, n_draws=B, force_coop=True).forward(*ins, c=_dev(cs), d=_dev(ds), outputs=ALL_OUT)
+    assert (info == gen["info"].cpu().numpy()).all()
+    good = np.nonzero(info == 0)[0]
+    assert len(good) == B
+    for k in ALL_OUT:
+        assert rel_err(out[k][good].cpu().numpy(), gen[k][good].cpu().numpy()) < 1e-9, k
+    for b in (good[0], good[len(good) // 2], good[-1]):
         ref = kn.kalman_filter(kind, y, *systems[b][1:], c=cs[b][:, None], d=ds[b][:, None])
         got = [out[k][b].cpu().numpy() for k in ALL_OUT]
         for name, a, e in zip(ALL_OUT, got, ref):
@@ -785,6 +796,7 @@ def test_full_outputs_on_the_tensor_core_mapping(dims, kind):
             assert rel_err(a.reshape(e.shape), e) < RTOL, (name, b)
     out2 = bk.forward(*ins, c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
     g_hot = bk.backward(wrt=wrt)
-    assert float((out2["loglik"] - out["loglik"]).abs().max()) < 1e-10 * float(out["loglik"].abs().max())
+    gi = torch.as_tensor(good, device="cuda")
+    assert float((out2["loglik"][gi] - out["loglik"][gi]).abs().max()) < 1e-10 * float(out["loglik"][gi].abs().max())
     for k in wrt:
-        assert rel_err(g_full[k].cpu().numpy(), g_hot[k].cpu().numpy()) < (1e-7 if kind == "steady_state" else 1e-9), k
+        assert rel_err(g_full[k][gi].cpu().numpy(), g_hot[k][gi].cpu().numpy()) < (1e-7 if kind == "steady_state" else 1e-9), k
