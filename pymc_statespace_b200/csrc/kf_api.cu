@@ -91,6 +91,21 @@ coopT_launch_fn find_coopT_launcher(int m, int p, int mk) {
   }
 }
 
+smoother_launch_fn smoother_thread_m1();
+smoother_launch_fn smoother_thread_m2();
+smoother_launch_fn smoother_thread_m3();
+smoother_launch_fn smoother_thread_m4();
+
+smoother_launch_fn find_smoother_thread_launcher(int m) {
+  switch (m) {
+    case 1: return smoother_thread_m1();
+    case 2: return smoother_thread_m2();
+    case 3: return smoother_thread_m3();
+    case 4: return smoother_thread_m4();
+    default: return nullptr;
+  }
+}
+
 thread_launch_fn find_thread_launcher(int m, int p, int mk, bool tv) {
   switch (m) {
     case 1: return thread_launcher_m1(p, mk, tv);
@@ -356,7 +371,8 @@ kfb_status kfb_smoother(int64_t n_draws, int64_t n_series, int32_t n, int32_t m,
   S.T = MatArg{T, T_bs, 0};
   S.C = MatArg{(const double*)workspace, C_batched ? (long long)m * m : 0, 0};
   S.fs = filtered_states; S.fc = filtered_covs; S.ss = smoothed_states; S.sc = smoothed_covs;
-  e = launch_smoother(S, s);
+  const smoother_launch_fn per_thread = find_smoother_thread_launcher(m);
+  e = per_thread ? per_thread(S, s) : launch_smoother(S, s);
   if (e == cudaErrorInvalidConfiguration) return KFB_ERR_UNSUPPORTED;
   return e == cudaSuccess ? KFB_OK : cuda_fail(e);
 }

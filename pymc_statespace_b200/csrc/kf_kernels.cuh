@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(WARP ? 128 : 256) kf_smoother_kernel(const __g
 }
 cudaError_t launch_smoother(const SmoothArgs& S, cudaStream_t s);
 
+// k_states <= 4: one unit per thread, everything in registers, no synchronisation (the same smoother_unit program)
+template <int M>
+__global__ void __launch_bounds__(128) kf_smoother_thread_kernel(const __grid_constant__ SmoothArgs S) {
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= S.U) return;
+  ThreadCtx<M, 1> x{nullptr, nullptr, (int)threadIdx.x, (int)blockDim.x};
+  smoother_unit(x, S, u);
+}
+typedef cudaError_t (*smoother_launch_fn)(const SmoothArgs& S, cudaStream_t s);
+smoother_launch_fn find_smoother_thread_launcher(int m);
+
 // launchers implemented in kf_thread_m*.cu / kf_coop.cu
 typedef cudaError_t (*thread_launch_fn)(const KfArgs& A, bool bwd, int y_smem_doubles, int bulk_ok, cudaStream_t s);
 thread_launch_fn find_thread_launcher(int m, int p, int mk, bool tv = false);

@@ -4,9 +4,12 @@
 //     a_hat = T a ; P_hat = T P T^T + R Q R^T            (no intercept, no symmetrisation, :99-104)
 //     gain  = (pinv(P_hat) T P)^T                         (:92)
 //     a_s   = a + gain (a_s' - a_hat) ;  P_s = P + gain (P_s' - P_hat) gain^T
-// scanned backwards from the last filtered moment.  pinv(P_hat) is computed from a cyclic-Jacobi eigendecomposition
-// of sym(P_hat) with numpy's cutoff (eigenvalues below 1e-15 * largest are dropped), which is what
-// numpy.linalg.pinv's SVD gives for a symmetric matrix.
+// scanned backwards from the last filtered moment.  pinv(P_hat): when sym(P_hat) is numerically positive definite (every
+// Cholesky pivot positive, smallest / largest > 1e-13) numpy's cutoff drops nothing and pinv(P_hat) = P_hat^-1, so the
+// gain is obtained from a Cholesky solve (m syncs instead of thousands); otherwise - singular or nearly singular P_hat,
+// where the cutoff decides the answer - from a cyclic-Jacobi eigendecomposition of sym(P_hat) with numpy's cutoff
+// (eigenvalues below 1e-15 * largest are dropped), which is what numpy.linalg.pinv's SVD gives for a symmetric matrix.
+// Round 2 timing before / after the fast path and the thread-per-unit instantiation for k_states <= 4: DESIGN.md section 8.
 #pragma once
 #include "kf_core.cuh"
 
@@ -64,6 +67,55 @@ KFB_HD void jacobi_eigen(X& x, TM& Am, TM& V, int m) {
   }
 }
 
+// In-place lower Cholesky factor of the symmetric W (all lanes of the unit cooperate).  True iff every pivot is a positive
+// finite number and min pivot > 1e-13 * max pivot.
+template <class X, class TM>
+KFB_HD bool chol_factor(X& x, TM& W, int m) {
+  double dmin = 1.0e300, dmax = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < m; ++k) {
+    const double d = W[k * m + k];
+    ok = ok && (d > 0.0) && (d < 1.0e300);
+    dmin = fmin(dmin, d);
+    dmax = fmax(dmax, d);
+    const double r = sqrt(ok ? d : 1.0), ri = 1.0 / r;
+    x.sync();  // every lane has read the pivot
+    KFB_FOR(i, m) {
+      if (i >= k) W[i * m + k] = (i == k) ? r : W[i * m + k] * ri;
+    }
+    x.sync();
+    KFB_FOR(idx, m * m) {
+      const int i = x.div_m(idx), j = idx - i * m;
+      if (j > k && i >= j) W[idx] = kf_fma(-W[i * m + k], W[j * m + k], W[idx]);
+    }
+    x.sync();
+  }
+  return ok && dmin > 1.0e-13 * dmax;
+}
+
+// G = (L L^T)^-1 S, column by column (one column per lane: forward, then backward substitution)
+template <class X, class TM>
+KFB_HD void chol_solve(X& x, const TM& Lw, TM& G, const TM& S, int m) {
+  KFB_FOR(j, m) {
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      double s = S[i * m + j];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s = kf_fma(-Lw[i * m + k], G[k * m + j], s);
+      G[i * m + j] = s / Lw[i * m + i];
+    }
+#pragma unroll
+    for (int i = m - 1; i >= 0; --i) {
+      double s = G[i * m + j];
+#pragma unroll
+      for (int k = i + 1; k < m; ++k) s = kf_fma(-Lw[k * m + i], G[k * m + j], s);
+      G[i * m + j] = s / Lw[i * m + i];
+    }
+  }
+  x.sync();
+}
+
 template <class X>
 KFB_HD void smoother_unit(X& x, const SmoothArgs& A, long long u) {
   const int m = x.m(), n = A.n;
@@ -96,23 +148,29 @@ KFB_HD void smoother_unit(X& x, const SmoothArgs& A, long long u) {
       const int i = x.div_m(idx), j = idx - i * m;
       W[idx] = 0.5 * (Ph[idx] + Ph[j * m + i]);
     }
+    KFB_FOR(i, m * m) V[i] = W[i];
     x.sync();
-    jacobi_eigen(x, W, V, m);
-    double lmax = 0.0;
-    KFB_FOR(i, m) lmax = fmax(lmax, fabs(W[i * m + i]));
-    lmax = x.reduce_max(lmax);
-    const double cutoff = 1.0e-15 * lmax;
-    KFB_FOR(idx, m * m) {                                  // Pinv = V diag(1/lambda) V^T
-      const int i = x.div_m(idx), j = idx - i * m;
-      double s = 0.0;
-      for (int k = 0; k < m; ++k) {
-        const double lam = W[k * m + k];
-        if (fabs(lam) > cutoff) s = kf_fma(V[i * m + k] / lam, V[j * m + k], s);
+    if (chol_factor(x, V, m)) {                            // sym(P_hat) positive definite: pinv = inverse
+      chol_solve(x, V, G, S1, m);                          // G = P_hat^-1 T P ; gain = G^T
+    } else {
+      x.sync();
+      jacobi_eigen(x, W, V, m);
+      double lmax = 0.0;
+      KFB_FOR(i, m) lmax = fmax(lmax, fabs(W[i * m + i]));
+      lmax = x.reduce_max(lmax);
+      const double cutoff = 1.0e-15 * lmax;
+      KFB_FOR(idx, m * m) {                                // Pinv = V diag(1/lambda) V^T
+        const int i = x.div_m(idx), j = idx - i * m;
+        double s = 0.0;
+        for (int k = 0; k < m; ++k) {
+          const double lam = W[k * m + k];
+          if (fabs(lam) > cutoff) s = kf_fma(V[i * m + k] / lam, V[j * m + k], s);
+        }
+        Pinv[idx] = s;
       }
-      Pinv[idx] = s;
+      x.sync();
+      gemm<false, false, 0>(x, G, Pinv, S1, m, m, m);      // G = pinv(P_hat) T P ; gain = G^T
     }
-    x.sync();
-    gemm<false, false, 0>(x, G, Pinv, S1, m, m, m);        // G = pinv(P_hat) T P ; gain = G^T
     KFB_FOR(i, m) da[i] = as[i] - ah[i];
     KFB_FOR(i, m * m) W[i] = Ps[i] - Ph[i];
     x.sync();

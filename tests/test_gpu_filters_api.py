@@ -279,3 +279,32 @@ def test_seam_graph_is_reused_and_matches_oracle():
     with pytest.raises(np.linalg.LinAlgError):
         flt.build_graph(yb, a0, P0, T, Z, R, H, Q)
     UnivariateFilter().build_graph(yb, a0, P0, T, Z, R, H, Q)
+
+
+@pytest.mark.parametrize("m", [2, 3, 6])
+def test_smoother_singular_predicted_covariance_uses_pinv(m):
+    """RTS smoother with a SINGULAR P_hat (a state without noise and without initial uncertainty): pinv(P_hat) differs
+    from any inverse, so the kernels must take the eigendecomposition path with numpy's cutoff (kalman_smoother.py:92) and
+    not the Cholesky fast path; regular units of the same batch take the fast path.  k_states 2, 3: thread per unit;
+    6: one warp per unit."""
+    from pymc_statespace_b200 import rts_smoother
+
+    rng = np.random.default_rng(40 + m)
+    B, n, r = 4, 12, 1
+    fs = rng.normal(size=(B, n, m))
+    A = rng.normal(size=(B, n, m, m))
+    fc = A @ np.swapaxes(A, -1, -2) + 0.1 * np.eye(m)
+    T = np.tile(np.eye(m), (B, 1, 1)) * 0.9
+    R = np.zeros((B, m, r))
+    R[:, 0, 0] = 1.0                      # only state 0 is driven by noise
+    Q = np.tile(np.array([[0.5]]), (B, 1, 1))
+    # units 1 and 3: the last state is known exactly at every step -> P_hat has a zero row / column
+    for b in (1, 3):
+        fc[b, :, m - 1, :] = 0.0
+        fc[b, :, :, m - 1] = 0.0
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")  # noqa: E731
+    ss, sc = rts_smoother(dev(T), dev(R), dev(Q), dev(fs), dev(fc))
+    for b in range(B):
+        rs, rc = kn.kalman_smoother(T[b], R[b], Q[b], fs[b][..., None], fc[b])
+        assert rel_err(ss[b].cpu().numpy(), rs[..., 0]) < 1e-8, b
+        assert rel_err(sc[b].cpu().numpy(), rc) < 1e-8, b

@@ -28,3 +28,13 @@ bytes_step = 8 * (2 * m + 2 * m * m) + 8
 gb = B * n * bytes_step / 1e9
 print(json.dumps({"m": m, "p": p, "draws": B, "n": n, "ms": best, "GBps": gb / (best * 1e-3), "frac_of_6543.7": gb / (best * 1e-3) / 6543.7,
                   "steps_per_s": B * n / (best * 1e-3), "bad": int((out["info"] != 0).sum())}))
+if os.environ.get("KFB_SMOOTHER"):
+    from pymc_statespace_b200.engine import rts_smoother
+    best = 1e30
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ss, sc = rts_smoother(args[3], args[5], args[7], out["filtered_states"], out["filtered_covs"]); e1.record()
+        torch.cuda.synchronize()
+        if it: best = min(best, e0.elapsed_time(e1))
+    bytes_s = 8 * 2 * (m + m * m)  # read filtered, write smoothed moments
+    print(json.dumps({"smoother_ms": best, "steps_per_s": B * n / (best * 1e-3), "GBps": B * n * bytes_s / 1e9 / (best * 1e-3)}))
