@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kf_rowsU_kernel(const __grid
 // Fused row-per-lane, warp-per-unit programs for large systems with the m^3 products on the FP64 tensor cores
 // (kf_rowsD.cuh); MK = MK_STD or MK_STEADY.  BWD = adjoint, NEED_T = with T-bar.
 #ifndef KFB_ROWSH_MINB
-#define KFB_ROWSH_MINB 4  // 16 x 16 tiles (k_states 10..16): 16 warps per SM, <= 128 registers (seasonal period 12: 3 -> 273 ms, 4 -> 277, 5 -> 295, 6 -> 311)
+// 16 x 16 tiles (k_states 10..16): 12 warps per SM, <= 168 registers.  Seasonal period 12, 65,536 x 1000, swizzled tiles:
+// 2 -> 241 ms, 3 -> 231 ms, 4 -> 250 ms (128 registers: the adjoint spills 150-390 bytes per thread).
+#define KFB_ROWSH_MINB 3
 #endif
 template <int M, int P, int MK, bool BWD, bool NEED_T>
 __global__ void __launch_bounds__(128, M <= 16 ? KFB_ROWSH_MINB : 1) kf_rowsD_kernel(const __grid_constant__ KfArgs A) {

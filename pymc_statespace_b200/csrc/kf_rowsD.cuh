@@ -20,13 +20,28 @@
 namespace kfb {
 
 // Tile geometry: NT x NT tiles of 8 x 8 per matrix (NT = 4: even k_states 18..32; NT = 2: even k_states 10..16 - seasonal
-// periods 12 / SARIMA orders land here), leading dimension LD = 8 NT + 2 doubles: rows 16-byte aligned and LD/2 odd, so
-// the row-per-lane 16-byte accesses of a quarter warp fall on 8 distinct bank groups; fragment loads and tile stores are
-// 2-way conflicted.  (An XOR-swizzled LD = 8 NT layout makes all four access patterns conflict free and was measured
-// slower twice - rounds 1 and 2, profiles/r2_ncu_rowsD.md: the per-access address arithmetic and its registers turn the
-// kernels from wavefront-bound into latency-bound.  It is not in the tree any more.)
+// periods 12 / SARIMA orders land here).
+//  * NT = 4: leading dimension LD = 34 doubles: rows 16-byte aligned and LD/2 odd, so the row-per-lane 16-byte accesses of a
+//    quarter warp fall on 8 distinct bank groups; fragment loads and tile stores are 2-way conflicted.  (The XOR-swizzled
+//    layout below makes all access patterns conflict free there too and was measured slower twice - rounds 1 and 2,
+//    profiles/r2_ncu_rowsD.md: at 1.5 warps per scheduler its address arithmetic turns the kernels latency-bound.)
+//  * NT = 2: LD = 16 and the 16-byte chunks of a row XOR-swizzled: physical chunk = chunk ^ swz(row),
+//    swz(row) = {0,4,2,6,1,5,3,7}[row & 7].  Row accesses (8 consecutive rows -> 8 distinct chunk groups), both mma
+//    fragment patterns and the 16-byte tile stores are all conflict free.  These kernels run 12-16 warps per SM and sat ON
+//    the shared-memory wavefront roof (93-96 % of the LSU peak), a quarter of it bank conflicts at LD = 18: 478 -> 323
+//    (forward) / 696 -> 537 (adjoint) wavefronts per step together with the predicated row loads; the full-output forward
+//    gained 14 %, the adjoint little (it is then bound by spills at 128 registers: see KFB_ROWSH_MINB).
 __host__ __device__ constexpr int rowsD_nt(int m) { return m <= 16 ? 2 : 4; }
-__host__ __device__ constexpr int rowsD_ld(int m) { return 8 * rowsD_nt(m) + 2; }
+__host__ __device__ constexpr int rowsD_ld(int m) { return m <= 16 ? 16 : 34; }
+template <int LD>
+__host__ __device__ constexpr int rowsD_swz(int row) {
+  return (LD % 8 == 0) ? (((row & 1) << 2) | (row & 2) | ((row >> 2) & 1)) : 0;
+}
+// offset of element (row, col) inside a tile matrix
+template <int LD>
+__host__ __device__ constexpr int rowsD_el(int row, int col) {
+  return row * LD + ((((col >> 1) ^ rowsD_swz<LD>(row)) << 1) | (col & 1));
+}
 
 template <int M, int P, bool NEED_T>
 struct RowsDLayout {
@@ -62,15 +77,18 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 //   = op(A) op(B),  op = transpose if TA / TB.  A, B: padded row-major matrices (leading dimension LD) in shared memory.
 // ZERO = false: accumulate onto acc.  UPPER: only the tiles I <= J (the result is symmetric and its consumer reads it
 // through rowD_load_symU): 10 instead of 16 tile products at NT = 4.
-template <bool TA, bool TB, int LD, bool ZERO = true, bool UPPER = false, int NT = (LD - 2) / 8>
+template <bool TA, bool TB, int LD, bool ZERO = true, bool UPPER = false, int NT = LD / 8>
 __device__ __forceinline__ void mm32(double (&acc)[NT][NT][2], const double* A, const double* B, int lane) {
+  constexpr bool SWZ = (LD % 8 == 0);
   const int r = lane >> 2, c = lane & 3;
   // "N" pattern: element (row 8X + r, col 4kk + c) ; "T" pattern: element (row 4kk + c, col 8X + r)
   //   A: N, A^T: T (a[row][k] = A[k][row]) ; B: T pattern on B (b[k][col] = B[k][col]), B^T: N pattern on B
-  const double* nA = A + r * LD + c;
-  const double* nB = B + r * LD + c;
-  const double* tA = A + c * LD + r;
-  const double* tB = B + c * LD + r;
+  const int sr = rowsD_swz<LD>(r);                          // swizzle of rows 8X + r
+  const int gc = SWZ ? (((c & 1) << 2) | (c & 2)) : 0;      // swizzle of rows 4kk + c = gc | (kk & 1)
+  const double* nA = A + r * LD + (c & 1);
+  const double* nB = B + r * LD + (c & 1);
+  const double* tA = A + c * LD + (r & 1);
+  const double* tB = B + c * LD + (r & 1);
   if (ZERO) {
 #pragma unroll
     for (int I = 0; I < NT; ++I)
@@ -80,10 +98,14 @@ __device__ __forceinline__ void mm32(double (&acc)[NT][NT][2], const double* A, 
 #pragma unroll
   for (int kk = 0; kk < 2 * NT; ++kk) {
     double af[NT], bf[NT];
+    const int nofs = ((2 * kk + (c >> 1)) ^ sr) << 1;  // N pattern: chunk 2kk + c/2 of the lane's row
+    const int st = gc | (SWZ ? (kk & 1) : 0);
 #pragma unroll
-    for (int I = 0; I < NT; ++I) af[I] = TA ? tA[(4 * kk) * LD + 8 * I] : nA[(8 * I) * LD + 4 * kk];
+    for (int I = 0; I < NT; ++I)
+      af[I] = TA ? tA[(4 * kk) * LD + (((4 * I + (r >> 1)) ^ st) << 1)] : nA[(8 * I) * LD + nofs];
 #pragma unroll
-    for (int J = 0; J < NT; ++J) bf[J] = TB ? nB[(8 * J) * LD + 4 * kk] : tB[(4 * kk) * LD + 8 * J];
+    for (int J = 0; J < NT; ++J)
+      bf[J] = TB ? nB[(8 * J) * LD + nofs] : tB[(4 * kk) * LD + (((4 * J + (r >> 1)) ^ st) << 1)];
 #pragma unroll
     for (int I = 0; I < NT; ++I)
 #pragma unroll
@@ -93,7 +115,7 @@ __device__ __forceinline__ void mm32(double (&acc)[NT][NT][2], const double* A, 
 }
 
 // D = alpha * acc (the full padded matrix including the zero padding; UPPER: the tiles I <= J only)
-template <int LD, bool UPPER = false, int NT = (LD - 2) / 8>
+template <int LD, bool UPPER = false, int NT = LD / 8>
 __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[NT][NT][2], double alpha, int lane) {
   // D may be one of the product's own operands (X <- X L^T, A <- A A): every fragment load is
   // behind an mma.sync that consumed it, but make the ordering explicit (and visible to racecheck)
@@ -104,26 +126,31 @@ __device__ __forceinline__ void mm32_store(double* D, const double (&acc)[NT][NT
 #pragma unroll
     for (int J = 0; J < NT; ++J)
       if (!UPPER || I <= J)
-        *reinterpret_cast<double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c) = make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
+        *reinterpret_cast<double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz<LD>(r)) << 1)) =
+            make_double2(alpha * acc[I][J][0], alpha * acc[I][J][1]);
 }
 
-// row i of a tile matrix: rowp = &mat[i * LD]; chunk j = elements 2j, 2j + 1
-__device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int j) {
-  return reinterpret_cast<const double2*>(rowp + 2 * j);
+// row i of a tile matrix: rowp = &mat[i * LD]; logical chunk j (elements 2j, 2j + 1) lives at chunk j ^ swz(i)
+template <int LD>
+__device__ __forceinline__ const double2* rowD_chunk(const double* rowp, int i, int j) {
+  return reinterpret_cast<const double2*>(rowp + ((j ^ rowsD_swz<LD>(i)) << 1));
 }
-__device__ __forceinline__ double2* rowD_chunk(double* rowp, int j) { return reinterpret_cast<double2*>(rowp + 2 * j); }
-template <int M>
-__device__ __forceinline__ void rowD_store(double* rowp, const double (&v)[M]) {
+template <int LD>
+__device__ __forceinline__ double2* rowD_chunk(double* rowp, int i, int j) {
+  return reinterpret_cast<double2*>(rowp + ((j ^ rowsD_swz<LD>(i)) << 1));
+}
+template <int M, int LD>
+__device__ __forceinline__ void rowD_store(double* rowp, int i, const double (&v)[M]) {
 #pragma unroll
-  for (int j = 0; j < M / 2; ++j) *rowD_chunk(rowp, j) = make_double2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < M / 2; ++j) *rowD_chunk<LD>(rowp, i, j) = make_double2(v[2 * j], v[2 * j + 1]);
 }
 // act = false (a lane without a row, lanes >= k_states): no load is issued - 16-byte accesses are served per quarter warp,
 // so at k_states <= 16 the idle half of the warp would otherwise double the wavefronts of every row load.
-template <int M>
-__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, bool act = true) {
+template <int M, int LD>
+__device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, int i, bool act = true) {
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
-    const double2 x = act ? *rowD_chunk(rowp, j) : make_double2(0.0, 0.0);
+    const double2 x = act ? *rowD_chunk<LD>(rowp, i, j) : make_double2(0.0, 0.0);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
@@ -131,7 +158,7 @@ __device__ __forceinline__ void rowD_load(double (&v)[M], const double* rowp, bo
 // element (row j, column i) of a tile matrix, j a compile-time constant after unrolling: the lane's COLUMN accesses
 template <int LD>
 __device__ __forceinline__ double colD(const double* mat, int j, int i) {
-  return mat[j * LD + i];
+  return mat[j * LD + ((((i >> 1) ^ rowsD_swz<LD>(j)) << 1) | (i & 1))];
 }
 
 // The lane's row i of sym(U) for a matrix U = A^T S A (S symmetric) of which only the 8 x 8 tiles I <= J were computed
@@ -145,7 +172,7 @@ __device__ __forceinline__ void rowD_load_symU(double (&v)[M], const double* mat
 #pragma unroll
   for (int j = 0; j < M / 2; ++j) {
     double2 x = make_double2(0.0, 0.0);
-    if (((2 * j) >> 3) >= ti) x = *rowD_chunk(rowp, j);
+    if (((2 * j) >> 3) >= ti) x = *rowD_chunk<LD>(rowp, i, j);
     v[2 * j] = x.x;
     v[2 * j + 1] = x.y;
   }
@@ -201,7 +228,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 pk = act ? *rowD_chunk(pr, k) : make_double2(0.0, 0.0), ak = av[k];
+      const double2 pk = act ? *rowD_chunk<LD>(pr, i, k) : make_double2(0.0, 0.0), ak = av[k];
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -233,7 +260,7 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
     const double* tr = sm + L::T + i * LD;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-      const double2 tk = (act && !IDT) ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0);
+      const double2 tk = (act && !IDT) ? *rowD_chunk<LD>(tr, i, k) : make_double2(0.0, 0.0);
       const int q = (k & 1) * 2;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -279,18 +306,18 @@ __device__ __forceinline__ void rowsD_gain(double* sm, const double (&yt)[P], do
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
       double2 lk = IDT ? make_double2(i == 2 * k ? 1.0 : 0.0, i == 2 * k + 1 ? 1.0 : 0.0)
-                       : (act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0));
+                       : (act ? *rowD_chunk<LD>(tr, i, k) : make_double2(0.0, 0.0));
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         const double2 z = *reinterpret_cast<const double2*>(sm + L::Z + e * M + 2 * k);
         lk.x = fma(-g.Kp[e], z.x, lk.x);
         lk.y = fma(-g.Kp[e], z.y, lk.y);
       }
-      if (act) *rowD_chunk(lr, k) = lk;
+      if (act) *rowD_chunk<LD>(lr, i, k) = lk;
     }
     if (PADL && act) {  // the row's zero padding (Lm's slot doubles as the adjoint's tape staging buffer)
 #pragma unroll
-      for (int k = M / 2; k < L::TD / 2; ++k) *rowD_chunk(lr, k) = make_double2(0.0, 0.0);
+      for (int k = M / 2; k < L::TD / 2; ++k) *rowD_chunk<LD>(lr, i, k) = make_double2(0.0, 0.0);
     }
   }
   if (act) {
@@ -321,8 +348,8 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
-    sm[L::Pm + rr * LD + cc] = P0p[k];
+    sm[L::T + rowsD_el<LD>(rr, cc)] = Tp[k];
+    sm[L::Pm + rowsD_el<LD>(rr, cc)] = P0p[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -364,7 +391,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0), ak = av[k];
+        const double2 tk = act ? *rowD_chunk<LD>(tr, i, k) : make_double2(0.0, 0.0), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -422,7 +449,7 @@ __device__ void rowsD_forward(const KfArgs& A, long long u, double* sm, int lane
         }
       }
       if (act) {
-        rowD_store<M>(sm + L::Pm + i * LD, S);
+        rowD_store<M, LD>(sm + L::Pm + i * LD, i, S);
         sm[L::a + i] = an;
         if (taped) {
           tp[i] = an;
@@ -479,8 +506,8 @@ __device__ void rowsD_forward_full(const KfArgs& A, long long u, double* sm, int
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
-    sm[L::Pm + rr * LD + cc] = P0p[k];
+    sm[L::T + rowsD_el<LD>(rr, cc)] = Tp[k];
+    sm[L::Pm + rowsD_el<LD>(rr, cc)] = P0p[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -562,14 +589,14 @@ __device__ void rowsD_forward_full(const KfArgs& A, long long u, double* sm, int
           S[j] = fma(0.5, fma(KH[k], sm[L::Kp + j * P + k], sm[L::KH + j * P + k] * g.Kp[k]), S[j]);
       }
       if (act) {
-        rowD_store<M>(sm + L::Pm + i * LD, S);
+        rowD_store<M, LD>(sm + L::Pm + i * LD, i, S);
         if (A.fc) rowG_store<M>(A.fc + (u * (long long)n + t) * M * M + i * M, S);
       }
     } else {
       if (nm != P && info == 0) info = -(t + 1);
       if (act && A.fc) {
         double S[M];
-        rowD_load<M>(S, sm + L::Pm + i * LD, act);
+        rowD_load<M, LD>(S, sm + L::Pm + i * LD, i, act);
         rowG_store<M>(A.fc + (u * (long long)n + t) * M * M + i * M, S);
       }
     }
@@ -588,7 +615,7 @@ __device__ void rowsD_forward_full(const KfArgs& A, long long u, double* sm, int
       const double2* av = reinterpret_cast<const double2*>(sm + L::a);
 #pragma unroll
       for (int k = 0; k < M / 2; ++k) {
-        const double2 tk = act ? *rowD_chunk(tr, k) : make_double2(0.0, 0.0), ak = av[k];
+        const double2 tk = act ? *rowD_chunk<LD>(tr, i, k) : make_double2(0.0, 0.0), ak = av[k];
         const int q = (k & 1) * 2;
         aq[q] = fma(tk.x, ak.x, aq[q]);
         aq[q + 1] = fma(tk.y, ak.y, aq[q + 1]);
@@ -611,7 +638,7 @@ __device__ void rowsD_forward_full(const KfArgs& A, long long u, double* sm, int
 #pragma unroll
       for (int j = 0; j < M; ++j) S[j] += Cs[j];
       if (act) {
-        rowD_store<M>(sm + L::Pm + i * LD, S);
+        rowD_store<M, LD>(sm + L::Pm + i * LD, i, S);
         sm[L::a + i] = an;
         if (A.ps) A.ps[(u * (long long)(n + 1) + t + 1) * M + i] = an;
         if (A.pc) rowG_store<M>(A.pc + (u * (long long)(n + 1) + t + 1) * M * M + i * M, S);
@@ -663,7 +690,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
   if (n >= 2) rows_tape_prefetch<KT, 32>(sm + L::tp, tape + (long long)(n - 2) * KT, lane);
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::T + rowsD_el<LD>(rr, cc)] = Tp[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -704,7 +731,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
       const double* P0p = (MK == MK_STEADY) ? A.Pss.p + draw * A.Pss.bs : A.P0.p + draw * A.P0.bs;
       for (int k = lane; k < M * M; k += 32) {
         const int rr = k / M, cc = k - rr * M;
-        sm[L::Pm + rr * LD + cc] = P0p[k];
+        sm[L::Pm + rowsD_el<LD>(rr, cc)] = P0p[k];
       }
       if (act) sm[L::a + i] = A.a0.p[draw * A.a0.bs + i];
     } else {
@@ -719,7 +746,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
           const int lo = i < j ? i : j, hi = i < j ? j : i;
           Pr[j] = tq[M + lo * M - (lo * (lo - 1)) / 2 + (hi - lo)];
         }
-        rowD_store<M>(sm + L::Pm + i * LD, Pr);
+        rowD_store<M, LD>(sm + L::Pm + i * LD, i, Pr);
       }
       // (every lane has read the staging buffer before the sync below; the gain may overwrite it)
     }
@@ -743,7 +770,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     const double* Lsrc = observed ? sm + L::Lm : sm + L::T;
     if (t == 0) {  // P0 may be any matrix: L-bar = W (P + P^T); for t >= 1 the taped P is symmetric: P + P^T = 2 P
       double S0[M];
-      rowD_load<M>(S0, sm + L::Pm + i * LD, act);
+      rowD_load<M, LD>(S0, sm + L::Pm + i * LD, i, act);
 #pragma unroll
       for (int j = 0; j < M; ++j) S0[j] = 0.5 * (S0[j] + colD<LD>(sm + L::Pm, j, i));
       if (observed) {  // lz = (P + P^T) Z^T rows
@@ -757,7 +784,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
         }
       }
       __syncwarp();
-      if (NEED_T && act) rowD_store<M>(sm + L::Pm + i * LD, S0);
+      if (NEED_T && act) rowD_store<M, LD>(sm + L::Pm + i * LD, i, S0);
       __syncwarp();
     }
     // ---- 1: Ps = sym(P-bar') = symU(L^T W of the step above) + sym(Mb Z), in place ; Cb += Ps
@@ -774,7 +801,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
 #pragma unroll
       for (int j = 0; j < M; ++j) Cb[j] += Ps[j];
       __syncwarp();  // every lane has read its row and column of P-bar'
-      if (act) rowD_store<M>(sm + L::Pb + i * LD, Ps);
+      if (act) rowD_store<M, LD>(sm + L::Pb + i * LD, i, Ps);
     }
     __syncwarp();  // Ps visible
     // ---- 2: W = Ps L (tensor cores) ; PK = Ps Kp, T^T ab (row-wise, independent of the product: they sit between its
@@ -783,7 +810,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     {
       double c4[L::NT][L::NT][2];
       mm32<false, false, LD>(c4, sm + L::Pb, Lsrc, lane);
-      if constexpr (NEED_T) rowD_load<M>(Ps, sm + L::Pb + i * LD, act);
+      if constexpr (NEED_T) rowD_load<M, LD>(Ps, sm + L::Pb + i * LD, i, act);
 #pragma unroll
       for (int e = 0; e < P; ++e) {
         PK[e] = dot4<M>(0.0, [&](int k, double& x, double& y2) {  // (Kp is stale but unused when nothing is observed)
@@ -814,7 +841,7 @@ __device__ void rowsD_backward(const KfArgs& A, long long u, double* sm, int lan
     }
     if (observed) {
       double Wr[M];
-      rowD_load<M>(Wr, sm + L::W + i * LD, act);
+      rowD_load<M, LD>(Wr, sm + L::W + i * LD, i, act);
       const double* m2 = (t == 0) ? sm + L::lz : sm + L::Mm;
       const double sc = (t == 0) ? 1.0 : 2.0;
 #pragma unroll
@@ -1030,14 +1057,14 @@ struct DareDLayout {
 };
 
 // acc <- D (the inverse of mm32_store)
-template <int LD, int NT = (LD - 2) / 8>
+template <int LD, int NT = LD / 8>
 __device__ __forceinline__ void mm32_load(double (&acc)[NT][NT][2], const double* D, int lane) {
   const int r = lane >> 2, c = lane & 3;
 #pragma unroll
   for (int I = 0; I < NT; ++I)
 #pragma unroll
     for (int J = 0; J < NT; ++J) {
-      const double2 x = *reinterpret_cast<const double2*>(D + (8 * I + r) * LD + 8 * J + 2 * c);
+      const double2 x = *reinterpret_cast<const double2*>(D + (8 * I + r) * LD + (((4 * J + c) ^ rowsD_swz<LD>(r)) << 1));
       acc[I][J][0] = x.x;
       acc[I][J][1] = x.y;
     }
@@ -1062,7 +1089,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
   __syncwarp();
   for (int k = lane; k < M * M; k += 32) {
     const int rr = k / M, cc = k - rr * M;
-    sm[L::T + rr * LD + cc] = Tp[k];
+    sm[L::T + rowsD_el<LD>(rr, cc)] = Tp[k];
   }
   for (int k = lane; k < P * M; k += 32) sm[L::Z + k] = Zp[k];
   for (int k = lane; k < P * P; k += 32) sm[L::H + k] = Hp[k];
@@ -1076,7 +1103,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
 #pragma unroll
   for (int k = 0; k < P * P; ++k) scale = fmax(scale, fabs(Hp[k]));
   scale = warp_max(scale);
-  if (act) sm[L::Pm + i * LD + i] = 1.0e4 * scale;
+  if (act) sm[L::Pm + rowsD_el<LD>(i, i)] = 1.0e4 * scale;
   __syncwarp();
 
   double yt[P], dv[P], Gss[P * P];
@@ -1124,7 +1151,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     rowD_load_symU<M, LD>(U, sm + L::X, i, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) S[j] += U[j];
-    if (act) rowD_store<M>(sm + L::Pm + i * LD, S);
+    if (act) rowD_store<M, LD>(sm + L::Pm + i * LD, i, S);
     __syncwarp();
   }
   // (2) Newton-Hewer: P <- Lyapunov(L(P), C + Kp H Kp^T), each Lyapunov equation by squared-Smith doubling
@@ -1135,13 +1162,13 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     {
       double S[M];
       rhs_row(S);
-      if (act) rowD_store<M>(sm + L::Xs + i * LD, S);
+      if (act) rowD_store<M, LD>(sm + L::Xs + i * LD, i, S);
     }
     __syncwarp();
     bool ok = false;
     for (int db = 0; db < 64; ++db) {  // Xs <- sum_k A^k Xs A^kT, A = Lm (destroyed)
       double Ar[M], mx = 0.0;
-      rowD_load<M>(Ar, sm + L::Lm + i * LD, act);
+      rowD_load<M, LD>(Ar, sm + L::Lm + i * LD, i, act);
 #pragma unroll
       for (int j = 0; j < M; ++j) mx = fmax(mx, fabs(Ar[j]));
       mx = warp_max(mx);
@@ -1160,8 +1187,8 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     }
     if (!ok) { info = 1; break; }
     double Pn[M], Po[M], diff = 0.0, mag = 0.0;
-    rowD_load<M>(Pn, sm + L::Xs + i * LD, act);
-    rowD_load<M>(Po, sm + L::Pm + i * LD, act);
+    rowD_load<M, LD>(Pn, sm + L::Xs + i * LD, i, act);
+    rowD_load<M, LD>(Po, sm + L::Pm + i * LD, i, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       diff = fmax(diff, fabs(Pn[j] - Po[j]));
@@ -1170,7 +1197,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
     }
     diff = warp_max(diff);
     mag = warp_max(mag);
-    if (act) rowD_store<M>(sm + L::Pm + i * LD, Pn);
+    if (act) rowD_store<M, LD>(sm + L::Pm + i * LD, i, Pn);
     __syncwarp();
     converged = diff <= 4.0e-15 * mag;
   }
@@ -1180,7 +1207,7 @@ __device__ void rowsD_dare(const double* Tp, const double* Zp, const double* Hp,
   if (!g.ok) info = 1;
   if (act) {
     double Pr[M];
-    rowD_load<M>(Pr, sm + L::Pm + i * LD, act);
+    rowD_load<M, LD>(Pr, sm + L::Pm + i * LD, i, act);
 #pragma unroll
     for (int j = 0; j < M; ++j) Pss[i * M + j] = info ? nan("") : Pr[j];
   }
