@@ -70,6 +70,25 @@ struct ThreadCtx {
     constexpr int w = out_width(ARR), off = out_off(ARR);
     const long long rows = (ARR == O_PS || ARR == O_PC) ? n + 1 : n;
     const long long r0 = (ARR == O_PS || ARR == O_PC) ? t0 + 1 : t0;
+    if constexpr (COUNT > 0 && (32 % (COUNT * w)) == 0) {
+      // The run of one unit divides the warp: lane -> (unit within the iteration, element) is fixed, so the shared-memory
+      // source is one per-lane pointer plus an immediate and the global destination one per-lane pointer bumped by a
+      // uniform stride - 4 instead of ~15 instructions per store (the generic index arithmetic below was half of the
+      // full-output kernel's 460 instructions per step).
+      constexpr int Lr = COUNT * w, UPI = 32 / Lr;  // doubles per unit, units per iteration
+      const int ul = lane / Lr, e = lane - ul * Lr, sidx = e / w, i = e - sidx * w;
+      const double* src = ostage + (size_t)(sidx * OUT_W + off + i) * OUT_LD + ul;
+      double* dst = base + ((warp_u0 + ul) * rows + r0) * w + e;
+      const long long stride = (long long)UPI * rows * w;
+      const long long left = A.U - warp_u0;
+      const int nvalid = left < 32 ? (int)left : 32;  // units of this warp that exist
+#pragma unroll
+      for (int it = 0; it < Lr; ++it) {
+        if (it * UPI + ul < nvalid) *dst = src[it * UPI];
+        dst += stride;
+      }
+      return;
+    }
     const int Lc = (COUNT > 0 ? COUNT : count) * w;  // contiguous doubles per unit
 #pragma unroll
     for (int it = 0; it < (COUNT > 0 ? COUNT * w : OUT_K * w); ++it) {

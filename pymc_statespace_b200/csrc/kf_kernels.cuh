@@ -5,6 +5,7 @@
 #include "kf_ctx.cuh"
 #include "kf_dare.cuh"
 #include "kf_pred.cuh"
+#include "kf_p1.cuh"
 #include "kf_rows.cuh"
 #include "kf_rowsD.cuh"
 #include "kf_rowsU.cuh"
@@ -66,10 +67,12 @@ __device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
   }
 }
 
-// a padding lane of the last warp in the full-output kernel: same program on the last unit's inputs
-template <int MK, int MODE, class X>
-__device__ __forceinline__ void run_unit_padded(X& x, const KfArgs& B, long long u_last) {
-  run_unit<MK, MODE>(x, B, u_last);
+// full-output forward of the thread-per-unit kernels: one observed series + standard-family filter + static matrices run
+// the step written for that case (kf_p1.cuh: forward_full_p1), everything else the generic two-stage program
+template <int M, int P, int MK, bool TV, class X>
+__device__ __forceinline__ void run_unit_full(X& x, const KfArgs& A, long long u) {
+  if constexpr (P == 1 && MK == MK_STD && !TV) p1::forward_full_p1<M>(x, A, u);
+  else run_unit<MK, 1>(x, A, u);
 }
 
 // 65,536 units (the headline batch) need 443 resident threads per SM for a single wave: the pipelined adjoint of the
@@ -97,10 +100,10 @@ __global__ void __launch_bounds__(KFB_THREAD_BLOCK)
     if (u >= A.U) {
       KfArgs B = A;  // padding lane: compute, store nothing of its own
       B.loglik = nullptr; B.info = nullptr; B.tape = nullptr;
-      run_unit_padded<MK, MODE>(x, B, A.U - 1);
+      run_unit_full<M, P, MK, TV>(x, B, A.U - 1);  // a padding lane of the last warp: same program on the last unit's inputs
       return;
     }
-    run_unit<MK, MODE>(x, A, u);
+    run_unit_full<M, P, MK, TV>(x, A, u);
     return;
   }
   if (u >= A.U) return;
