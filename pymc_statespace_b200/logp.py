@@ -271,6 +271,22 @@ class KalmanLogp:
                     out[k] = out[k][..., :m, :m].contiguous()
         return out
 
+    def smooth(self, theta):
+        """Filtered moments -> RTS smoother for every draw: the batched counterpart of ``build_statespace_graph`` +
+        ``build_smoother_graph`` (reference core/statespace.py:146-200, filters/kalman_smoother.py:56-104).
+        Returns (smoothed_states [B, n, m], smoothed_covs [B, n, m, m], filter outputs dict)."""
+        from .engine import rts_smoother
+
+        mats = self._scatter(self._check_theta(theta))
+        out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("filtered_states", "filtered_covs", "loglik"))
+        ss, sc = rts_smoother(mats["T"], mats["R"], mats["Q"], out["filtered_states"], out["filtered_covs"])
+        m = self.k_states_model
+        if m != self.spec.k_states:  # padded model: the model's own states
+            ss, sc = ss[..., :m].contiguous(), sc[..., :m, :m].contiguous()
+            out["filtered_states"] = out["filtered_states"][..., :m].contiguous()
+            out["filtered_covs"] = out["filtered_covs"][..., :m, :m].contiguous()
+        return ss, sc, out
+
     def logp(self, theta) -> torch.Tensor:
         mats = self._scatter(self._check_theta(theta))
         out = self.kalman.forward(self.y, *[mats[k] for k in MATRICES], outputs=("loglik",))

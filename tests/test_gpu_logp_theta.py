@@ -480,3 +480,46 @@ def test_tensor_core_dare_matches_generic_solver_and_reports_failure(m):
     for b in (0, 4):
         ref = kn.kalman_filter("steady_state", y, *systems[b][1:])
         assert abs(res[False][0][b] - float(ref[4])) < 1e-9 * abs(float(ref[4]))
+
+
+@pytest.mark.gpu
+def test_theta_level_smoother_matches_oracle():
+    """KalmanLogp.smooth: filter + RTS smoother for every draw (reference build_statespace_graph + build_smoother_graph);
+    VARMAX(2,0) with measurement error (fused row kernels + warp-per-unit smoother) and the 13-state seasonal model (padded
+    to the 14-state tensor-core kernels).  (Models without measurement error, e.g. BayesianARMA, make P_hat singular to
+    rounding at most steps: cond 1e15..1e18, where numpy's own pinv and an eigendecomposition pinv differ by 1e-5..1e-2 -
+    no value test is meaningful there.)"""
+    from oracle import kalman_numpy as kn
+    from pymc_statespace_b200.logp import KalmanLogp
+    from pymc_statespace_b200.models import trend_seasonal_spec
+    from pymc_statespace_b200.synthetic import varmax20_workload
+
+    cases = []
+    spec, y, theta = varmax20_workload(12, 40)
+    cases.append((spec, y, theta, 1e-7))
+    spec = trend_seasonal_spec(12)
+    rng = np.random.default_rng(3)
+    theta = np.exp(rng.normal(np.log([0.1, 0.01, 0.05, 0.5]), 0.2, size=(6, 4)))
+    y = (np.sin(2 * np.pi * np.arange(40) / 12) + np.cumsum(rng.normal(0, 0.3, 40)) + rng.normal(0, 0.7, 40))[:, None]
+    cases.append((spec, y, theta, 1e-6))  # pinv of a covariance whose state noise has rank 3: cond * eps
+    for spec, y, theta, tol in cases:
+        B = theta.shape[0]
+        model = KalmanLogp(spec, y, n_draws=B)
+        ss, sc, out = model.smooth(torch.as_tensor(theta, device="cuda"))
+        m = model.k_states_model
+        assert tuple(ss.shape) == (B, y.shape[0], m) and tuple(sc.shape) == (B, y.shape[0], m, m)
+        for b in (0, B - 1):
+            mats = spec.matrices(theta[b])
+            args = [np.asarray(mats[k], dtype=float) for k in ("a0", "P0", "T", "Z", "R", "H", "Q")]
+            if spec.stationary_initialization:
+                import scipy.linalg as sl
+
+                args[1] = sl.solve_discrete_lyapunov(args[2], args[4] @ args[6] @ args[4].T)
+            o = kn.kalman_filter("standard", np.asarray(y, dtype=float).reshape(len(y), -1, 1), args[0].reshape(-1, 1), *args[1:])
+            rs, rc = kn.kalman_smoother(args[2], args[4], args[6], o[0], o[2])
+            assert rel_err_np(ss[b].cpu().numpy(), rs[..., 0]) < tol
+            assert rel_err_np(sc[b].cpu().numpy(), rc) < tol
+
+
+def rel_err_np(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
