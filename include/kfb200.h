@@ -61,7 +61,7 @@ enum {
 
 /* info[] codes beyond "t + 1" / "-(t + 1)" (no series is this long) */
 #define KFB_INFO_DARE_FAILED 0x40000001    /* steady_state: Riccati / Newton-Hewer iteration failed for this draw      */
-#define KFB_INFO_BAD_STRUCTURE 0x40000003   /* a KFB_FLAG_Z_UNIT0 / KFB_FLAG_H_ZERO promise does not hold for this unit        */
+#define KFB_INFO_BAD_STRUCTURE 0x40000003   /* a KFB_FLAG_Z_UNIT0 / _H_ZERO / _T_COMPANION promise does not hold for this unit */
 #define KFB_INFO_NOT_STATIONARY 0x40000002 /* set by the host layer (KalmanLogp): stationary P0 requested but the      */
                                            /* Lyapunov doubling did not converge (spectral radius of T >= 1)            */
 
@@ -78,6 +78,9 @@ enum {
  * BayesianARMA has obs_cov = 0. */
 #define KFB_FLAG_Z_UNIT0 8u   /* Z = [1, 0, .., 0] for every draw                                   */
 #define KFB_FLAG_H_ZERO 16u   /* H = 0 for every draw (only honoured together with KFB_FLAG_Z_UNIT0) */
+#define KFB_FLAG_T_COMPANION 32u /* T = [t | e_0 .. e_{m-2}] for every draw: only the first column carries parameters
+                                    (BayesianARMA / SARIMAX, reference models/SARIMAX.py:59-98).  Only honoured together
+                                    with the two flags above; the columns >= 1 of the T gradient are then returned as 0 */
 
 typedef struct kfb_desc {
   int32_t filter_kind;

@@ -198,7 +198,8 @@ static void fill_args(const kfb_desc* d, const kfb_inputs* in, const Plan& pl, c
   A->ll_const = pl.ll_const;
   A->d_sign = pl.d_sign;
   if (d->p == 1 && !d->Z_ts && !d->H_ts)
-    A->struct_flags = ((d->flags & KFB_FLAG_Z_UNIT0) ? 1 : 0) | ((d->flags & KFB_FLAG_H_ZERO) ? 2 : 0);
+    A->struct_flags = ((d->flags & KFB_FLAG_Z_UNIT0) ? 1 : 0) | ((d->flags & KFB_FLAG_H_ZERO) ? 2 : 0) |
+                      ((d->flags & KFB_FLAG_T_COMPANION) ? 4 : 0);
 }
 
 static kfb_status cuda_fail(cudaError_t e) {

@@ -103,7 +103,7 @@ struct RingTape {
 constexpr int P1_WPC = KFB_P1_WPC;      // warps per CTA (the observation stream is staged once per CTA)
 constexpr int P1_SLOTS = KFB_P1_SLOTS;  // ring slots per warp (SLOTS - 1 entries in flight)
 
-template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, bool ZU = false, bool H0 = false>
+template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = false>
 __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
     kf_p1_adjoint_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
   backward_unit_p1<M, NEED_Z, NEED_H, HAS_GOBS, RingTape<M, P1_SLOTS>, ZU, H0>(A, store ? u : A.U - 1, store, yp, tape);
 }
 
-template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, bool ZU = false, bool H0 = false>
+template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = false>
 static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   constexpr int KT = Dim<M>::KT;
   const int block = 32 * P1_WPC;
@@ -148,6 +148,10 @@ static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_
 template <int M>
 static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   const bool z = A.gZ != nullptr, h = A.gH != nullptr, g = A.g_ll_obs != nullptr;
+  if (!z && !h && (A.struct_flags & 7) == 7) {  // + companion T (ARMA / SARIMAX): only column 0 of T-bar exists
+    return g ? launch_one<M, false, false, true, 2, true>(A, ysm, bulk_ok, s)
+             : launch_one<M, false, false, false, 2, true>(A, ysm, bulk_ok, s);
+  }
   if (!z && !h && (A.struct_flags & 1)) {  // structured design row (and observation variance): fewer products per step
     const bool h0 = (A.struct_flags & 2) != 0;
     if (g) return h0 ? launch_one<M, false, false, true, true, true>(A, ysm, bulk_ok, s)
@@ -204,7 +208,7 @@ struct BulkSink {
   }
 };
 
-template <int M, bool SAVE, bool ZU = false, bool H0 = false>
+template <int M, bool SAVE, int ZU = 0, bool H0 = false>
 __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     kf_p1_forward_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
   forward_unit_p1<M, SAVE, ZU, H0>(A, u, true, yp, tp, tstep);
 }
 
-template <int M, bool SAVE, bool ZU = false, bool H0 = false>
+template <int M, bool SAVE, int ZU = 0, bool H0 = false>
 static cudaError_t launch_fwd_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   const int block = 64;
   const unsigned grid = (unsigned)((A.U + block - 1) / block);
@@ -260,6 +264,8 @@ static cudaError_t launch_fwd_one(const KfArgs& A, int ysm, int bulk_ok, cudaStr
 
 template <int M>
 static cudaError_t launch_fwd_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
+  if ((A.struct_flags & 7) == 7)
+    return A.tape ? launch_fwd_one<M, true, 2, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 2, true>(A, ysm, bulk_ok, s);
   if (A.struct_flags & 1) {
     if (A.struct_flags & 2)
       return A.tape ? launch_fwd_one<M, true, true, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, true, true>(A, ysm, bulk_ok, s);

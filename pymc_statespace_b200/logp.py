@@ -195,9 +195,14 @@ class KalmanLogp:
         z_unit0 = (p == 1 and not spec.maps.get("Z") and np.array_equal(
             np.asarray(spec.base["Z"], dtype=np.float64).ravel(), np.eye(spec.k_states)[0]))
         h_zero = p == 1 and not spec.maps.get("H") and not np.any(np.asarray(spec.base["H"]))
+        # T in companion form with parameters in its first column only (BayesianARMA / SARIMAX, models/SARIMAX.py:59-98)
+        mT = spec.k_states
+        Tb = np.asarray(spec.base["T"], dtype=np.float64).reshape(mT, mT)
+        t_companion = (z_unit0 and h_zero and mT >= 2 and np.array_equal(Tb[:, 1:], np.eye(mT)[:, :mT - 1])
+                       and all(fi % mT == 0 for _, fi in spec.maps.get("T", [])))
         self.kalman = BatchedKalman(filter_type, self.n, spec.k_states, spec.k_endog, spec.k_posdef, n_draws=self.B,
                                     strict_reference=strict_reference, device=device, force_coop=force_coop,
-                                    z_unit0=z_unit0, h_zero=h_zero, pad_odd=pad_to_fused)
+                                    z_unit0=z_unit0, h_zero=h_zero, pad_odd=pad_to_fused, t_companion=t_companion)
         m, pp, r = spec.k_states, spec.k_endog, spec.k_posdef
         self._shape = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (pp, m), "R": (m, r), "H": (pp, pp), "Q": (r, r),
                        "c": (m,), "d": (pp,)}

@@ -148,6 +148,9 @@ def test_full_size_all_draws_match_c_port():
     assert np.abs(lg - ll).max() / np.abs(ll).max() < 1e-11 and (np.abs(lg / ll - 1) < 1e-9).all()
     for k in ("a0", "P0", "T"):
         got, ref = g[k].cpu().numpy().reshape(B, -1), gc[k].reshape(B, -1)
+        if k == "T":  # companion T promised by the model (KFB_FLAG_T_COMPANION): only its first column has a gradient
+            assert np.abs(got.reshape(B, 2, 2)[:, :, 1]).max() == 0.0
+            got, ref = got.reshape(B, 2, 2)[:, :, 0], ref.reshape(B, 2, 2)[:, :, 0]
         err = np.abs(got - ref).max(axis=1) / np.maximum(np.abs(ref).max(axis=1), 1e-300)
         assert err.max() < 1e-8, (k, int(err.argmax()), err.max())
 

@@ -800,3 +800,64 @@ def test_full_outputs_on_the_tensor_core_mapping(dims, kind):
     assert float((out2["loglik"][gi] - out["loglik"][gi]).abs().max()) < 1e-10 * float(out["loglik"][gi].abs().max())
     for k in wrt:
         assert rel_err(g_full[k][gi].cpu().numpy(), g_hot[k][gi].cpu().numpy()) < (1e-7 if kind == "steady_state" else 1e-9), k
+
+
+@pytest.mark.parametrize("m", [2, 3, 4])
+def test_p1_companion_T_promise(m):
+    """KFB_FLAG_T_COMPANION (with Z = e0, H = 0: every BayesianARMA / SARIMAX model, models/SARIMAX.py:59-98): the k_endog = 1
+    kernels skip the products with the known unit columns of T.  Same loglik and gradients as the kernels without the
+    promise on every unit (the T gradient in its first column - the other columns are constants of the model and come back
+    as zero), with and without a per-step cotangent, missing rows, non-symmetric P0, c and d; oracle parity on a few units;
+    a T that is not in companion form is reported per unit."""
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KFB_INFO_BAD_STRUCTURE
+
+    rng = np.random.default_rng(170 + m)
+    B, n, r = 45, 33, 1
+    systems = [list(random_system(rng, m, 1, r, n)) for _ in range(B)]
+    Tc = np.zeros((B, m, m))
+    Tc[:, :, 1:] = np.eye(m)[:, :m - 1]
+    Tc[:, :, 0] = rng.uniform(-0.5, 0.5, size=(B, m)) / np.arange(1, m + 1)   # AR coefficients in the first column
+    y = random_system(rng, m, 1, r, n, n_missing=3)[0]
+    y[[0, n - 1]] = np.nan
+    for s in systems:
+        s[2] = s[2] + 0.05 * rng.normal(size=(m, m))  # non-symmetric P0
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    Z, H = np.eye(m)[:1], np.zeros((1, 1))
+    cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, 1))
+    w = rng.normal(size=(B, n))
+    wrt = ("a0", "P0", "T", "R", "Q", "c", "d")
+    for gobs in (None, w):
+        res = {}
+        for flagged in (False, True):
+            bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True, h_zero=True, t_companion=flagged)
+            out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), _dev(Tc), _dev(Z), stack(5), _dev(H), stack(7),
+                             c=_dev(cs), d=_dev(ds), outputs=("loglik",), save_for_backward=True)
+            g = bk.backward(g_loglik=None if gobs is None else _dev(np.full(B, 0.5)),
+                            g_ll_obs=None if gobs is None else _dev(gobs), wrt=wrt)
+            assert int((out["info"] != 0).sum()) == 0
+            res[flagged] = {k: v.cpu().numpy() for k, v in g.items()}
+            res[flagged]["loglik"] = out["loglik"].cpu().numpy()
+        assert np.abs(res[True]["T"][:, :, 1:]).max() == 0.0
+        res[False]["T"][:, :, 1:] = 0.0
+        for k in res[True]:
+            scale = np.abs(res[False][k]).max()
+            assert np.abs(res[True][k] - res[False][k]).max() / scale < 1e-12, (k, gobs is None)
+        for b in (0, 44):
+            args = (y, systems[b][1], systems[b][2], Tc[b], Z, systems[b][5], H, systems[b][7])
+            ll_ref, gref = kt.loglik_and_grads("standard", *args, c=cs[b][:, None], d=ds[b][:, None],
+                                               g_ll_obs=None if gobs is None else 0.5 + gobs[b])
+            if gobs is None:
+                assert abs(res[True]["loglik"][b] - ll_ref) < RTOL * abs(ll_ref)
+            gref["T"][:, 1:] = 0.0
+            for k in wrt:
+                got = res[True][k][b].reshape(gref[k].shape)
+                scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+                assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b)
+    # false promise: unit 5 has a T that is not in companion form
+    Tb = Tc.copy()
+    Tb[5, m - 1, m - 1] = 0.3
+    bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True, h_zero=True, t_companion=True)
+    out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), _dev(Tb), _dev(Z), stack(5), _dev(H), stack(7))
+    info = out["info"].cpu().numpy()
+    assert info[5] == KFB_INFO_BAD_STRUCTURE and (np.delete(info, 5) == 0).all() and bool(torch.isnan(out["loglik"][5]))
