@@ -397,13 +397,13 @@ def main():
         bwd_gbs = tape_bytes / (ms_bwd * 1e-3) / 1e9
         fwd_gbs = tape_bytes / (ms_fwd * 1e-3) / 1e9
         roof = {
-            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false> (reverse sweep: TMA tape ring)",
+            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false,2,true> (reverse sweep: TMA tape ring; Z = e0, H = 0, companion T promised by the model)",
                         "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bwd_gbs / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("adjoint"), "ms_per_launch": ms_bwd,
                         "algorithmic_bytes_per_launch": tape_bytes,
                         "note": "algorithmic bytes = 40 B/step tape read; ms_per_launch includes the ~8 us R Q R^T adjoint "
                                 "helper launched with it"},
-            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true> (loglik + tape)",
+            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true,2,true> (loglik + tape; Z = e0, H = 0, companion T promised by the model)",
                         "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("forward"), "ms_per_launch": ms_fwd,
                         "algorithmic_bytes_per_launch": tape_bytes,
@@ -438,7 +438,7 @@ def main():
                      "flops_per_step": ALG_FLOPS_PER_STEP,
                      "note": "ALGORITHMIC throughput: the reference algorithm's flop count (BASELINE.md section 3: 442 per "
                              "logp+grad step at k_states=2) divided by time - the kernels execute fewer (predictor form, "
-                             "symmetric storage: ~290 fp64 instruction slots per step), so this is not pipe utilisation"},
+                             "symmetric storage, structure promises: ~190 warp instructions per step pair), so this is not pipe utilisation"},
         }
         if c5 is not None:
             line["c5"] = c5
