@@ -78,6 +78,9 @@ enum {
  * BayesianARMA has obs_cov = 0. */
 #define KFB_FLAG_Z_UNIT0 8u   /* Z = [1, 0, .., 0] for every draw                                   */
 #define KFB_FLAG_H_ZERO 16u   /* H = 0 for every draw (only honoured together with KFB_FLAG_Z_UNIT0) */
+#define KFB_FLAG_NO_MISSING 64u  /* no observation is NaN.  Together with the three flags above the tape of the k_endog = 1
+                                    kernels holds only what varies (a_t and the leading block of P_t: 24 instead of 40
+                                    bytes per step at k_states 2); a missing observation is then reported per unit        */
 #define KFB_FLAG_T_COMPANION 32u /* T = [t | e_0 .. e_{m-2}] for every draw: only the first column carries parameters
                                     (BayesianARMA / SARIMAX, reference models/SARIMAX.py:59-98).  Only honoured together
                                     with the two flags above; the columns >= 1 of the T gradient are then returned as 0 */

@@ -221,12 +221,17 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
     const bool p1_ok = !pl.tv_any && d->y_bs == 0 && d->n_series == 1 && !(d->flags & KFB_FLAG_GENERIC_ADJOINT) &&
                        p1_adjoint_supported(d->m, d->p, pl.mk);
     const bool full = A.ll_obs || A.fs || A.ps || A.fc || A.pc;
+    // all four structure promises on the k_endog = 1 kernels: compressed tape entries (kf_p1.cuh, ZU == 3) - decided from
+    // the descriptor alone, so that the forward pass and the adjoint always agree on the format
+    KfArgs B = A;
+    if (p1_ok && (A.struct_flags & 7) == 7 && (d->flags & KFB_FLAG_NO_MISSING)) B.struct_flags |= 8;
+    if ((B.struct_flags & 8) && bwd && (A.gZ || A.gH)) return KFB_ERR_UNSUPPORTED;  // Z, H were promised constant
     if (p1_ok && bwd)
-      e = launch_p1_adjoint(A, ysm, bulk_ok, s);
+      e = launch_p1_adjoint(B, ysm, bulk_ok, s);
     else if (p1_ok && !full)
-      e = launch_p1_forward(A, ysm, bulk_ok, s);
+      e = launch_p1_forward(B, ysm, bulk_ok, s);
     else
-      e = find_thread_launcher(d->m, d->p, pl.mk, pl.tv_any)(A, bwd, ysm, bulk_ok, s);
+      e = find_thread_launcher(d->m, d->p, pl.mk, pl.tv_any)(B, bwd, ysm, bulk_ok, s);
   } else {
     // sub-warp kernels with compile-time dims need uniform control flow across the units of a warp:
     // static matrices and ONE observation stream shared by every unit

@@ -71,8 +71,12 @@ __device__ __forceinline__ void run_unit(X& x, const KfArgs& A, long long u) {
 // the step written for that case (kf_p1.cuh: forward_full_p1), everything else the generic two-stage program
 template <int M, int P, int MK, bool TV, class X>
 __device__ __forceinline__ void run_unit_full(X& x, const KfArgs& A, long long u) {
-  if constexpr (P == 1 && MK == MK_STD && !TV) p1::forward_full_p1<M>(x, A, u);
-  else run_unit<MK, 1>(x, A, u);
+  if constexpr (P == 1 && MK == MK_STD && !TV) {
+    if (A.struct_flags & 8) p1::forward_full_p1<M, true>(x, A, u);  // compressed tape entries (see kf_api.cu: launch_main)
+    else p1::forward_full_p1<M, false>(x, A, u);
+  } else {
+    run_unit<MK, 1>(x, A, u);
+  }
 }
 
 // 65,536 units (the headline batch) need 443 resident threads per SM for a single wave: the pipelined adjoint of the

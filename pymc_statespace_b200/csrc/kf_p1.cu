@@ -13,9 +13,9 @@
 namespace kfb {
 namespace p1 {
 
-template <int M, int SLOTS>
+template <int M, int SLOTS, int KTE = Dim<M>::KT>
 struct RingTape {
-  static constexpr int KT = Dim<M>::KT;
+  static constexpr int KT = KTE;  // doubles per entry (Dim<M>::KTC for the compressed tape)
   static constexpr unsigned BYTES = KT * 32 * 8;
   static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
   // warp-uniform state (derived from blockIdx and a shuffled warp index so that the compiler keeps it in uniform
@@ -107,7 +107,7 @@ template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = 
 __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
     kf_p1_adjoint_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = Dim<M>::KT;
+  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
@@ -122,16 +122,16 @@ __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
   if (wg * 32 >= A.U) return;                                    // whole warp beyond the batch
   const long long upad = (A.U + 31) & ~31LL;
   const long long tstep = (long long)KT * upad;
-  RingTape<M, P1_SLOTS> tape;
+  RingTape<M, P1_SLOTS, KT> tape;
   tape.init(ring0_s + (unsigned)(warp * P1_SLOTS * KT * 32 * 8), bars_s + (unsigned)(warp * P1_SLOTS * 8),
             A.tape + wg * (KT * 32) + (long long)(A.n - 2) * tstep, tstep, A.n - 1, lane);
   const bool store = u < A.U;
-  backward_unit_p1<M, NEED_Z, NEED_H, HAS_GOBS, RingTape<M, P1_SLOTS>, ZU, H0>(A, store ? u : A.U - 1, store, yp, tape);
+  backward_unit_p1<M, NEED_Z, NEED_H, HAS_GOBS, RingTape<M, P1_SLOTS, KT>, ZU, H0>(A, store ? u : A.U - 1, store, yp, tape);
 }
 
 template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = false>
 static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
-  constexpr int KT = Dim<M>::KT;
+  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
   const int block = 32 * P1_WPC;
   const unsigned grid = (unsigned)((A.U + block - 1) / block);
   const size_t smem = (size_t)((ysm + 15) & ~15) * 8 + (size_t)P1_WPC * P1_SLOTS * (KT * 32 * 8 + 8);
@@ -148,6 +148,10 @@ static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_
 template <int M>
 static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   const bool z = A.gZ != nullptr, h = A.gH != nullptr, g = A.g_ll_obs != nullptr;
+  if (!z && !h && (A.struct_flags & 15) == 15) {  // + no missing observation: compressed tape (a_t, leading block of P_t)
+    return g ? launch_one<M, false, false, true, 3, true>(A, ysm, bulk_ok, s)
+             : launch_one<M, false, false, false, 3, true>(A, ysm, bulk_ok, s);
+  }
   if (!z && !h && (A.struct_flags & 7) == 7) {  // + companion T (ARMA / SARIMAX): only column 0 of T-bar exists
     return g ? launch_one<M, false, false, true, 2, true>(A, ysm, bulk_ok, s)
              : launch_one<M, false, false, false, 2, true>(A, ysm, bulk_ok, s);
@@ -179,23 +183,24 @@ static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t 
 #endif
 template <int M>
 struct BulkSink {
-  static constexpr int KT = Dim<M>::KT;
-  static constexpr unsigned BYTES = KT * 32 * 8;
+  static constexpr unsigned SLOT_BYTES = Dim<M>::KT * 32 * 8;  // staging slot (sized for the full entry)
   unsigned slot0_s;  // shared-window address of this warp's two staging slots
   unsigned lane, par;
+  template <bool CT>
   __device__ __forceinline__ void put(double* tq, const double (&a)[M], const double (&P)[Dim<M>::NS]) {
+    constexpr int KT = CT ? Dim<M>::KTC : Dim<M>::KT;
+    constexpr unsigned BYTES = KT * 32 * 8;
+    double e[KT];
+    tape_pack<M, CT>(a, P, e);
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // (only lane 0 owns bulk groups)
     __syncwarp();
-    const unsigned dst = slot0_s + par * BYTES + lane * 8u;
+    const unsigned dst = slot0_s + par * SLOT_BYTES + lane * 8u;
 #pragma unroll
-    for (int k = 0; k < M; ++k) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + k * 256u), "d"(a[k]) : "memory");
-#pragma unroll
-    for (int k = 0; k < Dim<M>::NS; ++k)
-      asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + (M + k) * 256u), "d"(P[k]) : "memory");
+    for (int k = 0; k < KT; ++k) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + k * 256u), "d"(e[k]) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tq), "r"(slot0_s + par * BYTES),
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tq), "r"(slot0_s + par * SLOT_BYTES),
                    "r"(BYTES)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -212,7 +217,7 @@ template <int M, bool SAVE, int ZU = 0, bool H0 = false>
 __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     kf_p1_forward_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = Dim<M>::KT;
+  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;  // doubles per tape entry
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     if (u0 >= A.U) return;
     BulkSink<M> sink;
     sink.slot0_s = (unsigned)__cvta_generic_to_shared(kf_dyn_smem + ((y_smem_doubles + 15) & ~15)) +
-                   (unsigned)((threadIdx.x >> 5) * 2 * KT * 32 * 8);
+                   (unsigned)((threadIdx.x >> 5) * 2 * Dim<M>::KT * 32 * 8);
     sink.lane = (unsigned)lane;
     sink.par = 0;
     double* tp = A.tape + (u >> 5) * (KT * 32) + lane;
@@ -264,6 +269,8 @@ static cudaError_t launch_fwd_one(const KfArgs& A, int ysm, int bulk_ok, cudaStr
 
 template <int M>
 static cudaError_t launch_fwd_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
+  if ((A.struct_flags & 15) == 15)
+    return A.tape ? launch_fwd_one<M, true, 3, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 3, true>(A, ysm, bulk_ok, s);
   if ((A.struct_flags & 7) == 7)
     return A.tape ? launch_fwd_one<M, true, 2, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 2, true>(A, ysm, bulk_ok, s);
   if (A.struct_flags & 1) {

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import (FILTER_KIND, KFB_FLAG_CORRECTED, KFB_FLAG_FORCE_COOP, KFB_FLAG_GENERIC_ADJOINT, KFB_FLAG_H_ZERO,
-                   KFB_FLAG_T_COMPANION, KFB_FLAG_Z_UNIT0, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
+                   KFB_FLAG_NO_MISSING, KFB_FLAG_T_COMPANION, KFB_FLAG_Z_UNIT0, KfbCotangents, KfbDesc, KfbGrads, KfbInputs,
                    KfbOutputs, check, load)
 
 MATRIX_NAMES = ("a0", "P0", "T", "Z", "R", "H", "Q", "c", "d")
@@ -49,7 +49,7 @@ class BatchedKalman:
     def __init__(self, kind: str, n: int, m: int, p: int, r: int, n_draws: int, n_series: int = 1,
                  strict_reference: bool = True, time_varying: Iterable[str] = (), device="cuda",
                  force_coop: bool = False, generic_adjoint: bool = False, z_unit0: bool = False, h_zero: bool = False,
-                 pad_odd: bool = True, t_companion: bool = False):
+                 pad_odd: bool = True, t_companion: bool = False, no_missing: bool = False):
         kind = kind.lower()
         if kind not in FILTER_KIND:
             raise NotImplementedError("The following are valid filter types: " + ", ".join(FILTER_KIND))
@@ -67,7 +67,9 @@ class BatchedKalman:
                       # structure promises (k_endog = 1): Z = [1, 0, ..], H = 0 - verified per unit by the forward kernel
                       | (KFB_FLAG_Z_UNIT0 if z_unit0 else 0) | (KFB_FLAG_H_ZERO if (h_zero and z_unit0) else 0)
                       # + T in companion form (only column 0 carries parameters): columns >= 1 of the T gradient come back 0
-                      | (KFB_FLAG_T_COMPANION if (t_companion and h_zero and z_unit0) else 0))
+                      | (KFB_FLAG_T_COMPANION if (t_companion and h_zero and z_unit0) else 0)
+                      # + no NaN in y: with all four the tape holds only what varies from step to step
+                      | (KFB_FLAG_NO_MISSING if (no_missing and t_companion and h_zero and z_unit0) else 0))
         self._base = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (p, m), "R": (m, r), "H": (p, p), "Q": (r, r),
                       "c": (m,), "d": (p,)}
         self._desc = None

@@ -202,7 +202,8 @@ class KalmanLogp:
                        and all(fi % mT == 0 for _, fi in spec.maps.get("T", [])))
         self.kalman = BatchedKalman(filter_type, self.n, spec.k_states, spec.k_endog, spec.k_posdef, n_draws=self.B,
                                     strict_reference=strict_reference, device=device, force_coop=force_coop,
-                                    z_unit0=z_unit0, h_zero=h_zero, pad_odd=pad_to_fused, t_companion=t_companion)
+                                    z_unit0=z_unit0, h_zero=h_zero, pad_odd=pad_to_fused, t_companion=t_companion,
+                                    no_missing=not bool(torch.isnan(self.y).any()))
         m, pp, r = spec.k_states, spec.k_endog, spec.k_posdef
         self._shape = {"a0": (m,), "P0": (m, m), "T": (m, m), "Z": (pp, m), "R": (m, r), "H": (pp, pp), "Q": (r, r),
                        "c": (m,), "d": (pp,)}

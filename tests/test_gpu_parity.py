@@ -861,3 +861,69 @@ def test_p1_companion_T_promise(m):
     out = bk.forward(_dev(y[..., 0]), stack(1)[..., 0], stack(2), _dev(Tb), _dev(Z), stack(5), _dev(H), stack(7))
     info = out["info"].cpu().numpy()
     assert info[5] == KFB_INFO_BAD_STRUCTURE and (np.delete(info, 5) == 0).all() and bool(torch.isnan(out["loglik"][5]))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_p1_compressed_tape(m):
+    """All four structure promises (Z = e0, H = 0, companion T, no missing observation: every BayesianARMA model on complete
+    data): P_t = C + blockdiag(B_t, 0), so the tape holds a_t and the leading (m-1) x (m-1) block of P_t only and the adjoint
+    re-inserts the last column of C.  Same loglik and gradients as the kernels with the full tape on every unit and as the
+    oracle; the full-output forward writes the same compressed tape; a NaN in y breaks the promise (reported per unit);
+    Z-bar / H-bar cannot be requested."""
+    from pymc_statespace_b200 import BatchedKalman
+    from pymc_statespace_b200._lib import KFB_INFO_BAD_STRUCTURE
+
+    rng = np.random.default_rng(270 + m)
+    B, n, r = 45, 33, 1
+    systems = [list(random_system(rng, m, 1, r, n)) for _ in range(B)]
+    Tc = np.zeros((B, m, m))
+    Tc[:, :, 1:] = np.eye(m)[:, :m - 1]
+    Tc[:, :, 0] = rng.uniform(-0.5, 0.5, size=(B, m)) / np.arange(1, m + 1)
+    y = random_system(rng, m, 1, r, n)[0]
+    for s in systems:
+        s[2] = s[2] + 0.05 * rng.normal(size=(m, m))  # non-symmetric P0
+    stack = lambda i: _dev(np.stack([s[i] for s in systems]))  # noqa: E731
+    Z, H = np.eye(m)[:1], np.zeros((1, 1))
+    cs, ds = rng.normal(size=(B, m)), rng.normal(size=(B, 1))
+    w = rng.normal(size=(B, n))
+    wrt = ("a0", "P0", "T", "R", "Q", "c", "d")
+    ins = lambda yy: (_dev(yy[..., 0]), stack(1)[..., 0], stack(2), _dev(Tc), _dev(Z), stack(5), _dev(H), stack(7))  # noqa: E731
+    for gobs in (None, w):
+        res = {}
+        for variant in ("plain", "compressed", "compressed_full_forward"):
+            bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True, h_zero=True, t_companion=True,
+                               no_missing=variant != "plain")
+            outs = ("loglik",) if variant != "compressed_full_forward" else ALL_OUT
+            out = bk.forward(*ins(y), c=_dev(cs), d=_dev(ds), outputs=outs, save_for_backward=True)
+            g = bk.backward(g_loglik=None if gobs is None else _dev(np.full(B, 0.5)),
+                            g_ll_obs=None if gobs is None else _dev(gobs), wrt=wrt)
+            assert int((out["info"] != 0).sum()) == 0
+            res[variant] = {k: v.cpu().numpy() for k, v in g.items()}
+            res[variant]["loglik"] = out["loglik"].cpu().numpy()
+        for variant in ("compressed", "compressed_full_forward"):
+            for k in res[variant]:
+                scale = np.abs(res["plain"][k]).max()
+                assert np.abs(res[variant][k] - res["plain"][k]).max() / scale < 1e-11, (variant, k, gobs is None)
+        for b in (0, 44):
+            args = (y, systems[b][1], systems[b][2], Tc[b], Z, systems[b][5], H, systems[b][7])
+            ll_ref, gref = kt.loglik_and_grads("standard", *args, c=cs[b][:, None], d=ds[b][:, None],
+                                               g_ll_obs=None if gobs is None else 0.5 + gobs[b])
+            if gobs is None:
+                assert abs(res["compressed"]["loglik"][b] - ll_ref) < RTOL * abs(ll_ref)
+            gref["T"][:, 1:] = 0.0
+            for k in wrt:
+                got = res["compressed"][k][b].reshape(gref[k].shape)
+                scale = max(np.abs(gref[k]).max(), 1e-12 * max(np.abs(v).max() for v in gref.values()))
+                assert np.abs(got - gref[k]).max() / scale < RTOL, (k, b)
+    # a missing observation breaks the promise: every unit is flagged (hot-path and full-output forward alike)
+    yb = y.copy()
+    yb[7] = np.nan
+    for outs in (("loglik",), ALL_OUT):
+        bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True, h_zero=True, t_companion=True, no_missing=True)
+        out = bk.forward(*ins(yb), outputs=outs, save_for_backward=True)
+        assert (out["info"].cpu().numpy() == KFB_INFO_BAD_STRUCTURE).all() and bool(torch.isnan(out["loglik"]).all())
+    # Z-bar with a design row that was promised constant: refused
+    bk = BatchedKalman("standard", n, m, 1, r, n_draws=B, z_unit0=True, h_zero=True, t_companion=True, no_missing=True)
+    bk.forward(*ins(y), outputs=("loglik",), save_for_backward=True)
+    with pytest.raises(Exception):
+        bk.backward(wrt=("Z",))

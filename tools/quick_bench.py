@@ -29,7 +29,7 @@ def main():
     print("fp64 peak TFLOP/s:", fp64_peak_tflops())
     for force, gen in ((False, False), (False, True)) + (((True, False),) if B <= 16384 else ()):
         st = os.environ.get('KFB_STRUCT', '1') == '1' and not gen and not force   # ARMA: Z = [1, 0], H = 0
-        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen, z_unit0=st, h_zero=st)
+        bk = BatchedKalman("standard", n, 2, 1, 1, n_draws=B, force_coop=force, generic_adjoint=gen, z_unit0=st, h_zero=st, t_companion=st, no_missing=st)
         # the CPU must run AHEAD of the GPU or the events also measure launch latency: enqueue several evaluations
         # back to back, time the later ones
         for it in range(3):
