@@ -35,7 +35,10 @@ sys.path.insert(0, ROOT)
 METRIC = "kalman_logp_grad_filter_steps_per_s"
 UNIT = "filter-steps/s"
 ALG_FLOPS_PER_STEP = 442.0      # logp+grad, m=2 p=1
-TAPE_BYTES_PER_STEP = 40.0      # 8 * (m + m(m+1)/2) written by the forward kernel and read by the adjoint kernel
+SURVEY_TAPE_BYTES_PER_STEP = 40.0  # 8 * (m + m(m+1)/2) per kernel and step for a store-all tape at m = 2
+TAPE_BYTES_PER_STEP = 24.0      # what the kernels move since the compressed tape: 8 * (m + (m-1)m/2) - with Z = e0, H = 0, a
+                                # companion T and complete data (every BayesianARMA model) the last row / column of every
+                                # predicted covariance is a constant of the draw and stays off the tape (kf_p1.cuh, ZU == 3)
 
 
 def parse():
@@ -324,7 +327,10 @@ def main():
         resident_path = f"GatherStepGraph ({how}): kernels + one NCCL all-gather of [B,{1 + spec.n_theta}] f64 per rank"
         step_resident = gsg
 
-    chunks = 4 if B % 4 == 0 else 1
+    # draw-chunk branches of the host-step graph: with the round-2 kernels (0.65 ms per evaluation) the ~10 helper launches
+    # per chunk cost more than the overlapped copies save - measured 0.795 / 0.840 / 0.848 / 0.849 / 1.13 ms for 1 / 2 / 4 / 8 /
+    # 16 chunks (tools/graph_e2e_chunks.py); round 1's 1.45 ms evaluation gained 7 % from 4 chunks
+    chunks = 1
     host_step = model.capture_host_step(theta_h, out_h, chunks=chunks) if use_graph else None
 
     def step_e2e():
@@ -394,20 +400,28 @@ def main():
         except Exception:
             pass
         tape_bytes = B * (n - 1) * TAPE_BYTES_PER_STEP
+        survey_bytes = B * (n - 1) * SURVEY_TAPE_BYTES_PER_STEP
         bwd_gbs = tape_bytes / (ms_bwd * 1e-3) / 1e9
         fwd_gbs = tape_bytes / (ms_fwd * 1e-3) / 1e9
+        rnote = ("achieved = ALGORITHMIC bytes (SURVEY 8(d): 40 B per step and kernel for a store-all tape at k_states 2) / "
+                 "CUDA-event time; frac > 1: the kernel beats the store-all HBM floor because it does not move what the "
+                 "model's structure makes constant - moved_*: the bytes it really moves (24 B/step, compressed tape, = "
+                 "traffic measured by ncu) against the same time and peak; ")
         roof = {
-            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false,2,true> (reverse sweep: TMA tape ring; Z = e0, H = 0, companion T promised by the model)",
-                        "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bwd_gbs / hbm_peak,
+            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false,3,true> (reverse sweep: TMA tape ring; Z = e0, H = 0, companion T, complete data promised by the model: compressed tape)",
+                        "achieved": survey_bytes / (ms_bwd * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": survey_bytes / (ms_bwd * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("adjoint"), "ms_per_launch": ms_bwd,
-                        "algorithmic_bytes_per_launch": tape_bytes,
-                        "note": "algorithmic bytes = 40 B/step tape read; ms_per_launch includes the ~8 us R Q R^T adjoint "
-                                "helper launched with it"},
-            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true,2,true> (loglik + tape; Z = e0, H = 0, companion T promised by the model)",
-                        "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak,
+                        "algorithmic_bytes_per_launch": survey_bytes, "moved_bytes_per_launch": tape_bytes,
+                        "moved_achieved": bwd_gbs, "moved_frac": bwd_gbs / hbm_peak,
+                        "note": rnote + "ms_per_launch includes the ~8 us R Q R^T adjoint helper launched with it"},
+            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true,3,true> (loglik + tape; Z = e0, H = 0, companion T, complete data promised by the model: compressed tape)",
+                        "achieved": survey_bytes / (ms_fwd * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": survey_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("forward"), "ms_per_launch": ms_fwd,
-                        "algorithmic_bytes_per_launch": tape_bytes,
-                        "note": "algorithmic bytes = 40 B/step tape write; ms_per_launch includes the ~6 us R Q R^T helper"},
+                        "algorithmic_bytes_per_launch": survey_bytes, "moved_bytes_per_launch": tape_bytes,
+                        "moved_achieved": fwd_gbs, "moved_frac": fwd_gbs / hbm_peak,
+                        "note": rnote + "ms_per_launch includes the ~6 us R Q R^T helper"},
         }
         dominant = "forward" if ms_fwd >= ms_bwd else "adjoint"
         other = "adjoint" if dominant == "forward" else "forward"
@@ -420,13 +434,14 @@ def main():
                        "gradient": "theta-level [B,5] (scatter + Lyapunov + Kalman adjoint)",
                        "l2": "no flush: each step streams a %.2f GB tape (write in forward, read in adjoint) >> 126 MB L2"
                              % (tape_bytes / 1e9),
+                       "tape": "compressed: a_t and the leading (m-1) x (m-1) block of P_t, 24 B per step and kernel (store-all: 40 B)",
                        "parallelism": f"draws sharded x{world}; resident leg: {resident_path}" if world > 1 else "1 GPU",
                        "resident_path": resident_path, "draws_with_info": bad},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(theta_h.numel() * 8 * world),
                     "d2h_bytes_per_step": int(out_h.numel() * 8 * world),
                     "path": (f"KalmanLogp.capture_host_step on every rank: pinned H2D + evaluation + pinned D2H of the rank's "
-                             f"shard replayed as one CUDA graph ({chunks} parallel draw-chunk branches: copies overlap kernels), "
+                             f"shard replayed as one CUDA graph ({chunks} draw-chunk branch(es)), "
                              "stream-synchronised every step; no collective") if use_graph else
                             "eager: pinned H2D, logp_and_grad, pinned D2H, stream-synchronised every step"},
             "gpu_launches": int(launches),

@@ -48,7 +48,7 @@ def timeit(fn, k=200):
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / k * 1e3
 
 res, ref = {}, None
-for C in (1, 2, 4):
+for C in (1, 2, 4, 8, 16):
     rp, out_h, keep = build(C)
     res[C] = timeit(rp)
     if ref is None: ref = out_h.clone()
