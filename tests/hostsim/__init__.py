@@ -36,7 +36,8 @@ def _p(a):
 
 
 def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_dims=False, do_bwd=True,
-        g_loglik=None, g_ll_obs=None, full=True, pred=False, skip=(), p1=False, z_unit0=False, h_zero=False):
+        g_loglik=None, g_ll_obs=None, full=True, pred=False, skip=(), p1=False, z_unit0=False, h_zero=False,
+        t_companion=False, no_missing=False):
     """Returns (outputs6, grads dict or None, info).  ``skip``: cotangents NOT requested (null pointers, left zero)."""
     lib = build()
     f8 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))  # noqa: E731
@@ -88,7 +89,7 @@ def run(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict=True, static_d
     glo = None if g_ll_obs is None else f8(g_ll_obs)
     rc = lib.hostsim_run(
         mk, m, p, n, _p(data), _p(a0), _p(P0), _p(T), _p(Z), _p(H), _p(C), _p(c), _p(d), _p(Pss), _p(Gss), _p(ts),
-        ctypes.c_double(ll_const), ctypes.c_double(d_sign), int(static_dims) | (2 if pred else 0) | (4 * int(p1)) | (16 if z_unit0 else 0) | (32 if h_zero else 0), _p(loglik), _p(ll_obs), _p(fs), _p(ps),
+        ctypes.c_double(ll_const), ctypes.c_double(d_sign), int(static_dims) | (2 if pred else 0) | (4 * int(p1)) | (16 if z_unit0 else 0) | (32 if h_zero else 0) | (64 if t_companion else 0) | (128 if no_missing else 0), _p(loglik), _p(ll_obs), _p(fs), _p(ps),
         _p(fc), _p(pc), _p(info), int(do_bwd), _p(gl), _p(glo),
         *([None if k in skip else _p(g[k]) for k in ("a0", "P0", "T", "Z", "H", "C", "c", "d", "Pss", "Gss")]
           if do_bwd else [None] * 10),

@@ -298,3 +298,58 @@ def test_p1_structure_flags_give_identical_values(m):
     _, _, info = hostsim.run("standard", *args, static_dims=True, full=False, pred=True, p1=True, z_unit0=True, h_zero=True,
                              do_bwd=False)
     assert info == 0x40000003
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_p1_companion_T_and_compressed_tape_on_host(m):
+    """The device math of the two ARMA-family promises of round 2, compiled for the host (kf_p1.cuh, ZU = 2 / 3):
+    KFB_FLAG_T_COMPANION (T = [t | e_0 .. e_{m-2}]: products with the unit columns not issued, only column 0 of T-bar) and,
+    on complete data, the compressed tape (P_t = C + blockdiag(B_t, 0): a_t and the leading block of P_t only).  Same
+    loglik and cotangents as the kernels with Z = e0 / H = 0 alone and as torch-autograd of the oracle; a T that is not a
+    companion matrix, or a missing observation under the no-missing promise, is reported."""
+    rng = np.random.default_rng(600 + m)
+    for n, n_missing in ((25, 0), (25, 3), (2, 0), (1, 0)):
+        args = list(random_system(rng, m, 1, 1, n, n_missing=n_missing))
+        args[4] = np.eye(m)[:1].copy()                       # Z = e_0
+        args[6] = np.zeros((1, 1))                           # H = 0
+        Tc = np.zeros((m, m))
+        Tc[:, 1:] = np.eye(m)[:, :m - 1]
+        Tc[:, 0] = rng.uniform(-0.5, 0.5, size=m) / np.arange(1, m + 1)
+        args[3] = Tc
+        args[2] = args[2] + 0.05 * rng.normal(size=(m, m))   # non-symmetric P0
+        c, d = rng.normal(size=(m, 1)), rng.normal(size=(1, 1))
+        for w in (None, rng.normal(size=n)):
+            kw = dict(c=c, d=d, static_dims=True, full=False, pred=True, p1=True, g_ll_obs=w,
+                      g_loglik=(0.0 if w is not None else None), skip=("Z", "H"), z_unit0=True, h_zero=True)
+            o0, g0, i0 = hostsim.run("standard", *args, **kw)
+            variants = [dict(t_companion=True)] + ([dict(t_companion=True, no_missing=True)] if n_missing == 0 else [])
+            _, gt = kt.loglik_and_grads("standard", *args, c=c, d=d, g_ll_obs=w)
+            for extra in variants:
+                o1, g1, i1 = hostsim.run("standard", *args, **kw, **extra)
+                assert i0 == 0 and i1 == 0 and abs(o1[4] - o0[4]) <= 1e-13 * abs(o0[4]), (extra, n)
+                for k in gt:
+                    if k in ("Z", "H"):
+                        continue
+                    a, b, t = g1[k], g0[k], gt[k]
+                    if k == "T":  # only the first column of a companion T carries parameters
+                        assert m == 1 or np.abs(np.asarray(a).reshape(m, m)[:, 1:]).max() == 0.0
+                        a, b, t = (np.asarray(v).reshape(m, m)[:, 0] for v in (a, b, t))
+                    assert rel_err(a, b) < 1e-11 or np.abs(a - b).max() < 1e-13, (k, n, extra)
+                    assert rel_err(a, t) < 1e-9 or np.abs(a - t).max() < 1e-13, (k, n, extra)
+    # false promises
+    args = list(random_system(rng, m, 1, 1, 6))
+    args[4], args[6] = np.eye(m)[:1].copy(), np.zeros((1, 1))
+    kw = dict(static_dims=True, full=False, pred=True, p1=True, z_unit0=True, h_zero=True, do_bwd=False)
+    if m >= 2:  # a random T is not a companion matrix
+        _, _, info = hostsim.run("standard", *args, t_companion=True, **kw)
+        assert info == 0x40000003
+    Tc = np.zeros((m, m))
+    Tc[:, 1:] = np.eye(m)[:, :m - 1]
+    Tc[:, 0] = 0.3 / np.arange(1, m + 1)
+    args[3] = Tc
+    args[0] = args[0].copy()
+    args[0][3] = np.nan
+    _, _, info = hostsim.run("standard", *args, t_companion=True, no_missing=True, **kw)
+    assert info == 0x40000003
+    _, _, info = hostsim.run("standard", *args, t_companion=True, **kw)
+    assert info == 0
