@@ -120,6 +120,7 @@ struct Plan {
   int mk;
   double ll_const, d_sign;
   bool tv_any, use_thread;
+  bool compressed;   // k_endog = 1 kernels with all four structure promises: tape entries hold a_t and the leading block of P_t
   long long U, nD;
   int nTC;           // time entries of C = R Q R^T (1 or n)
   long long C_bs;    // 0 if R and Q are shared by all draws
@@ -165,9 +166,14 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
     pl->off_Gss = take((size_t)pl->nD * d->p * d->p);
     pl->off_dinfo = take((size_t)(pl->nD + 1) / 2);
   }
+  // decided from the descriptor alone, so that workspace sizing, the forward pass and the adjoint always agree
+  constexpr uint32_t kPromises = KFB_FLAG_Z_UNIT0 | KFB_FLAG_H_ZERO | KFB_FLAG_T_COMPANION | KFB_FLAG_NO_MISSING;
+  pl->compressed = pl->use_thread && !pl->tv_any && d->y_bs == 0 && d->n_series == 1 && (d->flags & kPromises) == kPromises &&
+                   !(d->flags & KFB_FLAG_GENERIC_ADJOINT) && p1_adjoint_supported(d->m, d->p, pl->mk);
   pl->off_tape = pl->off_gC = 0;
   if (save) {
-    pl->off_tape = take((size_t)tape_units_padded(pl->U) * (d->n > 1 ? d->n - 1 : 0) * tape_width(d->m));
+    const size_t entry = pl->compressed ? (size_t)(d->m + ((d->m - 1) * d->m) / 2) : (size_t)tape_width(d->m);
+    pl->off_tape = take((size_t)tape_units_padded(pl->U) * (d->n > 1 ? d->n - 1 : 0) * entry);
     pl->off_gC = take((size_t)pl->U * pl->nTC * d->m * d->m);
     if (pl->mk == MK_STEADY) {
       pl->off_gPss = take((size_t)pl->U * d->m * d->m);
@@ -224,7 +230,7 @@ static kfb_status launch_main(const kfb_desc* d, const Plan& pl, const KfArgs& A
     // all four structure promises on the k_endog = 1 kernels: compressed tape entries (kf_p1.cuh, ZU == 3) - decided from
     // the descriptor alone, so that the forward pass and the adjoint always agree on the format
     KfArgs B = A;
-    if (p1_ok && (A.struct_flags & 7) == 7 && (d->flags & KFB_FLAG_NO_MISSING)) B.struct_flags |= 8;
+    if (pl.compressed && p1_ok && (A.struct_flags & 7) == 7) B.struct_flags |= 8;
     if ((B.struct_flags & 8) && bwd && (A.gZ || A.gH)) return KFB_ERR_UNSUPPORTED;  // Z, H were promised constant
     if (p1_ok && bwd)
       e = launch_p1_adjoint(B, ysm, bulk_ok, s);
