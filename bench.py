@@ -36,9 +36,10 @@ METRIC = "kalman_logp_grad_filter_steps_per_s"
 UNIT = "filter-steps/s"
 ALG_FLOPS_PER_STEP = 442.0      # logp+grad, m=2 p=1
 SURVEY_TAPE_BYTES_PER_STEP = 40.0  # 8 * (m + m(m+1)/2) per kernel and step for a store-all tape at m = 2
-TAPE_BYTES_PER_STEP = 24.0      # what the kernels move since the compressed tape: 8 * (m + (m-1)m/2) - with Z = e0, H = 0, a
-                                # companion T and complete data (every BayesianARMA model) the last row / column of every
-                                # predicted covariance is a constant of the draw and stays off the tape (kf_p1.cuh, ZU == 3)
+TAPE_BYTES_PER_STEP = 16.0      # what the kernels move: 8 * (1 + (m-1)m/2) - with Z = e0, H = 0, a companion T and complete
+                                # data (every BayesianARMA model) the recursion reduces to a_t and the leading block of P_t
+                                # (the last row / column of P_t is a constant of the draw), and the adjoint needs a_t only
+                                # through its first component (kf_p1.cuh, ZU == 4)
 
 
 def parse():
@@ -405,17 +406,17 @@ def main():
         fwd_gbs = tape_bytes / (ms_fwd * 1e-3) / 1e9
         rnote = ("achieved = ALGORITHMIC bytes (SURVEY 8(d): 40 B per step and kernel for a store-all tape at k_states 2) / "
                  "CUDA-event time; frac > 1: the kernel beats the store-all HBM floor because it does not move what the "
-                 "model's structure makes constant - moved_*: the bytes it really moves (24 B/step, compressed tape, = "
+                 "model's structure makes constant - moved_*: the bytes it really moves (16 B/step, reduced recursion, = "
                  "traffic measured by ncu) against the same time and peak; ")
         roof = {
-            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false,3,true> (reverse sweep: TMA tape ring; Z = e0, H = 0, companion T, complete data promised by the model: compressed tape)",
+            "adjoint": {"bound": "hbm", "kernel": "kf_p1_adjoint_kernel<2,false,false,false,4,true> (reverse sweep: TMA tape ring; Z = e0, H = 0, companion T, complete data promised by the model: reduced ARMA recursion, 16-byte tape entries)",
                         "achieved": survey_bytes / (ms_bwd * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": survey_bytes / (ms_bwd * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("adjoint"), "ms_per_launch": ms_bwd,
                         "algorithmic_bytes_per_launch": survey_bytes, "moved_bytes_per_launch": tape_bytes,
                         "moved_achieved": bwd_gbs, "moved_frac": bwd_gbs / hbm_peak,
                         "note": rnote + "ms_per_launch includes the ~8 us R Q R^T adjoint helper launched with it"},
-            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true,3,true> (loglik + tape; Z = e0, H = 0, companion T, complete data promised by the model: compressed tape)",
+            "forward": {"bound": "hbm", "kernel": "kf_p1_forward_kernel<2,true,4,true> (loglik + tape; Z = e0, H = 0, companion T, complete data promised by the model: reduced ARMA recursion, 16-byte tape entries)",
                         "achieved": survey_bytes / (ms_fwd * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": survey_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": peak_src, "traffic": traffic.get("forward"), "ms_per_launch": ms_fwd,
@@ -434,7 +435,7 @@ def main():
                        "gradient": "theta-level [B,5] (scatter + Lyapunov + Kalman adjoint)",
                        "l2": "no flush: each step streams a %.2f GB tape (write in forward, read in adjoint) >> 126 MB L2"
                              % (tape_bytes / 1e9),
-                       "tape": "compressed: a_t and the leading (m-1) x (m-1) block of P_t, 24 B per step and kernel (store-all: 40 B)",
+                       "tape": "reduced recursion: a_t[0] and the leading (m-1) x (m-1) block of P_t, 16 B per step and kernel (store-all: 40 B)",
                        "parallelism": f"draws sharded x{world}; resident leg: {resident_path}" if world > 1 else "1 GPU",
                        "resident_path": resident_path, "draws_with_info": bad},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
@@ -453,7 +454,7 @@ def main():
                      "flops_per_step": ALG_FLOPS_PER_STEP,
                      "note": "ALGORITHMIC throughput: the reference algorithm's flop count (BASELINE.md section 3: 442 per "
                              "logp+grad step at k_states=2) divided by time - the kernels execute fewer (predictor form, "
-                             "symmetric storage, structure promises: ~190 warp instructions per step pair), so this is not pipe utilisation"},
+                             "symmetric storage, reduced ARMA recursion), so this is not pipe utilisation"},
         }
         if c5 is not None:
             line["c5"] = c5

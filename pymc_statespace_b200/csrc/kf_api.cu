@@ -172,7 +172,7 @@ static kfb_status make_plan(const kfb_desc* d, bool save, Plan* pl) {
                    !(d->flags & KFB_FLAG_GENERIC_ADJOINT) && p1_adjoint_supported(d->m, d->p, pl->mk);
   pl->off_tape = pl->off_gC = 0;
   if (save) {
-    const size_t entry = pl->compressed ? (size_t)(d->m + ((d->m - 1) * d->m) / 2) : (size_t)tape_width(d->m);
+    const size_t entry = pl->compressed ? (size_t)(1 + ((d->m - 1) * d->m) / 2) : (size_t)tape_width(d->m);
     pl->off_tape = take((size_t)tape_units_padded(pl->U) * (d->n > 1 ? d->n - 1 : 0) * entry);
     pl->off_gC = take((size_t)pl->U * pl->nTC * d->m * d->m);
     if (pl->mk == MK_STEADY) {

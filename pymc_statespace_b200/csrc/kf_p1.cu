@@ -107,7 +107,7 @@ template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = 
 __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
     kf_p1_adjoint_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
 
 template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = false>
 static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
-  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
   const int block = 32 * P1_WPC;
   const unsigned grid = (unsigned)((A.U + block - 1) / block);
   const size_t smem = (size_t)((ysm + 15) & ~15) * 8 + (size_t)P1_WPC * P1_SLOTS * (KT * 32 * 8 + 8);
@@ -148,9 +148,9 @@ static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_
 template <int M>
 static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   const bool z = A.gZ != nullptr, h = A.gH != nullptr, g = A.g_ll_obs != nullptr;
-  if (!z && !h && (A.struct_flags & 15) == 15) {  // + no missing observation: compressed tape (a_t, leading block of P_t)
-    return g ? launch_one<M, false, false, true, 3, true>(A, ysm, bulk_ok, s)
-             : launch_one<M, false, false, false, 3, true>(A, ysm, bulk_ok, s);
+  if (!z && !h && (A.struct_flags & 15) == 15) {  // + no missing observation: reduced recursion, tape = (a_t[0], leading block of P_t)
+    return g ? launch_one<M, false, false, true, 4, true>(A, ysm, bulk_ok, s)
+             : launch_one<M, false, false, false, 4, true>(A, ysm, bulk_ok, s);
   }
   if (!z && !h && (A.struct_flags & 7) == 7) {  // + companion T (ARMA / SARIMAX): only column 0 of T-bar exists
     return g ? launch_one<M, false, false, true, 2, true>(A, ysm, bulk_ok, s)
@@ -217,7 +217,7 @@ template <int M, bool SAVE, int ZU = 0, bool H0 = false>
 __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     kf_p1_forward_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;  // doubles per tape entry
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;  // doubles per tape entry
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
@@ -270,7 +270,7 @@ static cudaError_t launch_fwd_one(const KfArgs& A, int ysm, int bulk_ok, cudaStr
 template <int M>
 static cudaError_t launch_fwd_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
   if ((A.struct_flags & 15) == 15)
-    return A.tape ? launch_fwd_one<M, true, 3, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 3, true>(A, ysm, bulk_ok, s);
+    return A.tape ? launch_fwd_one<M, true, 4, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 4, true>(A, ysm, bulk_ok, s);
   if ((A.struct_flags & 7) == 7)
     return A.tape ? launch_fwd_one<M, true, 2, true>(A, ysm, bulk_ok, s) : launch_fwd_one<M, false, 2, true>(A, ysm, bulk_ok, s);
   if (A.struct_flags & 1) {

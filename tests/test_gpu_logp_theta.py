@@ -145,7 +145,9 @@ def test_full_size_all_draws_match_c_port():
                                            mats["H"].cpu().numpy().reshape(1, 1), C, nthreads=os.cpu_count() or 1)
     assert bad == 0 and int((out["info"] != 0).sum()) == 0
     lg = out["loglik"].cpu().numpy()
-    assert np.abs(lg - ll).max() / np.abs(ll).max() < 1e-11 and (np.abs(lg / ll - 1) < 1e-9).all()
+    # (the kernels run the reduced ARMA recursion - Schur form, kf_p1.cuh ZU == 4 - the C port the general Joseph form: the two
+    #  agree to 2e-11 over all draws, tools/reduced_check.py)
+    assert np.abs(lg - ll).max() / np.abs(ll).max() < 1e-10 and (np.abs(lg / ll - 1) < 1e-9).all()
     for k in ("a0", "P0", "T"):
         got, ref = g[k].cpu().numpy().reshape(B, -1), gc[k].reshape(B, -1)
         if k == "T":  # companion T promised by the model (KFB_FLAG_T_COMPANION): only its first column has a gradient
