@@ -15,7 +15,7 @@ namespace p1 {
 
 template <int M, int SLOTS, int KTE = Dim<M>::KT>
 struct RingTape {
-  static constexpr int KT = KTE;  // doubles per entry (Dim<M>::KTC for the compressed tape)
+  static constexpr int KT = KTE;  // doubles per entry (Dim<M>::KTA for the reduced recursion)
   static constexpr unsigned BYTES = KT * 32 * 8;
   static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
   // warp-uniform state (derived from blockIdx and a shuffled warp index so that the compiler keeps it in uniform
@@ -107,7 +107,7 @@ template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = 
 __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
     kf_p1_adjoint_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : Dim<M>::KT;
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32 * P1_WPC, (M <= 2) ? KFB_P1_MINB : 4)
 
 template <int M, bool NEED_Z, bool NEED_H, bool HAS_GOBS, int ZU = 0, bool H0 = false>
 static cudaError_t launch_one(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t s) {
-  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : Dim<M>::KT;
   const int block = 32 * P1_WPC;
   const unsigned grid = (unsigned)((A.U + block - 1) / block);
   const size_t smem = (size_t)((ysm + 15) & ~15) * 8 + (size_t)P1_WPC * P1_SLOTS * (KT * 32 * 8 + 8);
@@ -183,24 +183,23 @@ static cudaError_t launch_m(const KfArgs& A, int ysm, int bulk_ok, cudaStream_t 
 #endif
 template <int M>
 struct BulkSink {
-  static constexpr unsigned SLOT_BYTES = Dim<M>::KT * 32 * 8;  // staging slot (sized for the full entry)
+  static constexpr int KT = Dim<M>::KT;
+  static constexpr unsigned BYTES = KT * 32 * 8;
   unsigned slot0_s;  // shared-window address of this warp's two staging slots
   unsigned lane, par;
-  template <bool CT>
   __device__ __forceinline__ void put(double* tq, const double (&a)[M], const double (&P)[Dim<M>::NS]) {
-    constexpr int KT = CT ? Dim<M>::KTC : Dim<M>::KT;
-    constexpr unsigned BYTES = KT * 32 * 8;
-    double e[KT];
-    tape_pack<M, CT>(a, P, e);
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // (only lane 0 owns bulk groups)
     __syncwarp();
-    const unsigned dst = slot0_s + par * SLOT_BYTES + lane * 8u;
+    const unsigned dst = slot0_s + par * BYTES + lane * 8u;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + k * 256u), "d"(e[k]) : "memory");
+    for (int k = 0; k < M; ++k) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + k * 256u), "d"(a[k]) : "memory");
+#pragma unroll
+    for (int k = 0; k < Dim<M>::NS; ++k)
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + (M + k) * 256u), "d"(P[k]) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tq), "r"(slot0_s + par * SLOT_BYTES),
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(tq), "r"(slot0_s + par * BYTES),
                    "r"(BYTES)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -217,7 +216,7 @@ template <int M, bool SAVE, int ZU = 0, bool H0 = false>
 __global__ void __launch_bounds__(64, (M <= 2) ? 8 : 4)
     kf_p1_forward_kernel(const __grid_constant__ KfArgs A, int y_smem_doubles, int bulk_ok) {
   extern __shared__ __align__(128) double kf_dyn_smem[];
-  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : (ZU == 3) ? Dim<M>::KTC : Dim<M>::KT;  // doubles per tape entry
+  constexpr int KT = (ZU == 4) ? Dim<M>::KTA : Dim<M>::KT;  // doubles per tape entry
   const double* yp = A.y.p;
   if (y_smem_doubles > 0) {
     stage_y(kf_dyn_smem, A.y.p, y_smem_doubles, bulk_ok != 0);

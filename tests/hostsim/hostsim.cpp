@@ -34,14 +34,14 @@ static void run_p1(ThreadCtx<M, 1>& x, KfArgs& A, int do_bwd) {
   const bool zu = (A.struct_flags & 1) != 0, h0 = (A.struct_flags & 2) != 0;
   if (g_p1 == 1 && (A.struct_flags & 7) == 7 && !A.gZ && !A.gH) {  // + companion T (+ complete data: compressed tape)
     const bool ct = (A.struct_flags & 8) != 0;
-    constexpr int KTC = p1::Dim<M>::KTA;  // reduced recursion: (a_t[0], leading block of P_t)
-    if (ct) p1::forward_unit_p1<M, true, 4, true>(A, 0, true, A.y.p, A.tape, (long long)KTC * 32);
+    constexpr int KTA_ = p1::Dim<M>::KTA;  // reduced recursion: (a_t[0], leading block of P_t)
+    if (ct) p1::forward_unit_p1<M, true, 4, true>(A, 0, true, A.y.p, A.tape, (long long)KTA_ * 32);
     else p1::forward_unit_p1<M, true, 2, true>(A, 0, true, A.y.p, x.tape_base(A, 0), x.tape_step(A));
     if (!do_bwd) return;
     if (ct) {
-      p1::DirectTape<M, KTC> tc{A.tape + (long long)(A.n - 2) * KTC * 32, (long long)KTC * 32, 32};
-      if (A.g_ll_obs) p1::backward_unit_p1<M, false, false, true, p1::DirectTape<M, KTC>, 4, true>(A, 0, true, A.y.p, tc);
-      else p1::backward_unit_p1<M, false, false, false, p1::DirectTape<M, KTC>, 4, true>(A, 0, true, A.y.p, tc);
+      p1::DirectTape<M, KTA_> tc{A.tape + (long long)(A.n - 2) * KTA_ * 32, (long long)KTA_ * 32, 32};
+      if (A.g_ll_obs) p1::backward_unit_p1<M, false, false, true, p1::DirectTape<M, KTA_>, 4, true>(A, 0, true, A.y.p, tc);
+      else p1::backward_unit_p1<M, false, false, false, p1::DirectTape<M, KTA_>, 4, true>(A, 0, true, A.y.p, tc);
     } else {
       p1::DirectTape<M> tc{x.tape_base(A, 0) + (long long)(A.n - 2) * x.tape_step(A), x.tape_step(A), x.tape_elem(A)};
       if (A.g_ll_obs) p1::backward_unit_p1<M, false, false, true, p1::DirectTape<M>, 2, true>(A, 0, true, A.y.p, tc);
