@@ -493,7 +493,10 @@ def bench_c5(a, world, rank, dev, timed, gather_graph, use_graph):
     # 2 waves: enough to hide the NCCL gather / PCIe copies of one wave under the kernels of the other, and large enough
     # (>= 2^19 draws = 27.7 warps per SM sub-partition) that the last, partially filled round of resident warps costs
     # < 10 % (4 waves of 2^18 draws measured 15.7 ms per 2^20 draws instead of ~14)
-    waves = 2 if B5 % 2 == 0 else 1
+    # Waves of 2^19 draws whatever the shard size (2 at 2^20 draws per GPU, 4 at 2^21): the gather of the LAST wave is the
+    # only exposed one, and with the round-2 kernels (2.3x faster, same bytes to gather) a 2^20-draw wave left ~9 % of an
+    # 8-GPU step to it.
+    waves = B5 >> 19 if (B5 >= (1 << 19) and B5 % (1 << 19) == 0) else (2 if B5 % 2 == 0 else 1)
     h = B5 // waves
     steps = a.c5_steps or max(2, min(a.steps, 8))
     spec, y, theta = arma21_workload(B5, a.n, seed=1 + rank)      # every rank draws its own shard
