@@ -236,3 +236,72 @@ def loglik_and_grads(kind, data, a0, P0, T, Z, R, H, Q, c=None, d=None, strict_r
     grads = torch.autograd.grad(target, list(ins.values()), allow_unused=True)
     gd = {k: (np.zeros_like(ins[k].detach().numpy()) if g is None else g.numpy()) for k, g in zip(GRAD_NAMES, grads)}
     return float(out[4].detach()), gd
+
+
+# ----------------------------------------------------------------------------
+# independent check used to pin the GRADIENT oracle: autograd of the dense multivariate-normal log density
+# ----------------------------------------------------------------------------
+def lyapunov_dense(T, RQR):
+    """Stationary P0 = T P0 T^T + R Q R^T as ONE dense linear solve, vec(P0) = (I - T (x) T)^{-1} vec(R Q R^T), written with
+    differentiable torch ops only - shares neither scipy's bilinear algorithm nor the hand-written adjoint of
+    ``_Lyapunov`` (the formula the reference uses, models/SARIMAX.py:106 + PyTensor's SolveDiscreteLyapunov grad)."""
+    m = T.shape[0]
+    A = torch.eye(m * m, dtype=DT) - torch.kron(T, T)
+    return torch.linalg.solve(A, RQR.reshape(m * m, 1)).reshape(m, m)
+
+
+def dense_gaussian_loglik(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
+    """torch twin of ``kalman_numpy.dense_gaussian_loglik``: log N(vec(y); mean, cov) of the stacked sample, no recursion
+    shared with the filter, every op differentiable - ``torch.autograd`` of this scalar is an algorithm-independent
+    known answer for d loglik / d (a0, P0, T, Z, R, H, Q, c, d).  Static matrices, missing entries marginalised by
+    deleting rows / columns.  The covariance blocks use P0, H, Q exactly as given: for a non-symmetric P0 / H / Q only
+    the symmetric part of the gradient is comparable with the filter's (DESIGN.md "gradient gauge")."""
+    data = torch.as_tensor(np.asarray(data), dtype=DT)
+    n, p = data.shape[0], data.shape[1]
+    m = T.shape[0]
+    c = torch.zeros((m, 1), dtype=DT) if c is None else c
+    d = torch.zeros((p, 1), dtype=DT) if d is None else d
+    RQR = R @ Q @ R.T
+    means, covs = [a0], [P0]
+    for _ in range(n - 1):
+        means.append(T @ means[-1] + c)
+        covs.append(T @ covs[-1] @ T.T + RQR)
+    Tpow = [torch.eye(m, dtype=DT)]
+    for _ in range(n):
+        Tpow.append(T @ Tpow[-1])
+    mu = torch.cat([Z @ mk + d for mk in means], dim=0).reshape(n * p)
+    rows = []
+    for t in range(n):
+        blks = []
+        for s in range(n):
+            if s <= t:
+                blk = Z @ (Tpow[t - s] @ covs[s]) @ Z.T  # Cov(y_t, y_s)
+                if s == t:
+                    blk = blk + H
+            else:
+                blk = (Z @ (Tpow[s - t] @ covs[t]) @ Z.T).T
+            blks.append(blk)
+        rows.append(torch.cat(blks, dim=1))
+    S = torch.cat(rows, dim=0)
+    yflat = data.reshape(n * p)
+    keep = ~torch.isnan(yflat)
+    idx = torch.nonzero(keep).reshape(-1)
+    yv = (torch.nan_to_num(yflat) - mu)[idx]
+    Sk = S[idx][:, idx]
+    Sk = 0.5 * (Sk + Sk.T)
+    L = torch.linalg.cholesky(Sk)
+    w = torch.linalg.solve_triangular(L, yv[:, None], upper=False)[:, 0]
+    return -0.5 * (idx.numel() * LOG_2PI + w @ w) - torch.log(torch.diagonal(L)).sum()
+
+
+def dense_loglik_and_grads(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
+    """(loglik, {name: gradient}) of the dense density; same signature / return as ``loglik_and_grads``."""
+    p, m = np.asarray(Z).shape[-2], np.asarray(Z).shape[-1]
+    c = np.zeros((m, 1)) if c is None else c
+    d = np.zeros((p, 1)) if d is None else d
+    ins = {k: torch.tensor(np.asarray(v, dtype=np.float64), dtype=DT, requires_grad=True)
+           for k, v in zip(GRAD_NAMES, (a0, P0, T, Z, R, H, Q, c, d))}
+    ll = dense_gaussian_loglik(data, *[ins[k] for k in GRAD_NAMES])
+    grads = torch.autograd.grad(ll, list(ins.values()), allow_unused=True)
+    gd = {k: (np.zeros_like(ins[k].detach().numpy()) if g is None else g.numpy()) for k, g in zip(GRAD_NAMES, grads)}
+    return float(ll.detach()), gd

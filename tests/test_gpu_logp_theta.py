@@ -58,6 +58,36 @@ def test_arma_theta_gradient(order, stationary):
     _compare(lambda t: om.arma_matrices(t, order, stationary), y[:, :, None], theta, logp, grad, (0, 1, 31, 63))
 
 
+@pytest.mark.parametrize("order", [(1, 1), (2, 1), (3, 2)])
+def test_arma_theta_gradient_equals_autograd_of_dense_density(order):
+    """A parity leg that does NOT route through the restated recursion nor through a hand-written adjoint: the CUDA
+    theta-level logp and gradient (scatter + Lyapunov doubling + reduced ARMA recursion + adjoints) against
+    torch-autograd of [theta -> matrices -> P0 by one dense Kronecker solve -> dense multivariate-normal log-density of
+    the stacked sample] (oracle.kalman_torch.dense_gaussian_loglik).  The reference's gradient is autodiff of the same
+    scalar, so this is the value it must produce.  BayesianARMA, stationary initialisation (models/SARIMAX.py:59-107):
+    the north-star model family, on the structure-promise kernels of kf_p1.cu."""
+    from oracle import kalman_torch as kt
+    from pymc_statespace_b200.models import arma_spec
+
+    spec = arma_spec(order, True)
+    rng = np.random.default_rng(70 + 10 * order[0] + order[1])
+    B, n, m = 40, 40, spec.k_states
+    y = rng.normal(size=(n, 1))
+    theta = np.zeros((B, spec.n_theta))
+    theta[:, spec.param_slices["x0"]] = rng.normal(size=(B, m)) * 0.3
+    theta[:, spec.param_slices["sigma_state"]] = np.exp(rng.normal(0, 0.3, (B, 1)))
+    theta[:, spec.param_slices["rho"]] = rng.uniform(-0.4, 0.4, (B, order[0])) / np.arange(1, order[0] + 1)
+    theta[:, spec.param_slices["theta"]] = rng.uniform(-0.5, 0.5, (B, order[1]))
+    logp, grad, _ = _run(spec, y, theta)
+    for b in (0, 1, 17, 39):
+        th = torch.tensor(theta[b], dtype=torch.float64, requires_grad=True)
+        a0, _, T, Z, R, H, Q = om.arma_matrices(th, order)
+        ll = kt.dense_gaussian_loglik(y[:, :, None], a0, kt.lyapunov_dense(T, R @ Q @ R.T), T, Z, R, H, Q)
+        (g,) = torch.autograd.grad(ll, [th])
+        assert abs(logp[b] - float(ll.detach())) <= RTOL * abs(float(ll.detach())), (b, logp[b], ll)
+        assert np.abs(grad[b] - g.numpy()).max() <= RTOL * np.abs(g.numpy()).max(), (b, grad[b], g)
+
+
 @pytest.mark.parametrize("kind", ["standard", "univariate", "cholesky"])
 def test_varmax_theta_gradient_with_missing_rows(kind):
     from pymc_statespace_b200.synthetic import varmax20_workload

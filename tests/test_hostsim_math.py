@@ -353,3 +353,38 @@ def test_p1_companion_T_and_compressed_tape_on_host(m):
     assert info == 0x40000003
     _, _, info = hostsim.run("standard", *args, t_companion=True, **kw)
     assert info == 0
+
+
+@pytest.mark.parametrize("m", [1, 2, 3])
+def test_device_math_gradient_equals_autograd_of_dense_density(m):
+    """The device step programs against an answer that shares nothing with them: torch-autograd of the dense
+    multivariate-normal log-density of the stacked sample (oracle.kalman_torch.dense_gaussian_loglik) - not the restated
+    recursion, not a hand-written adjoint.  Generic thread-per-unit math (all nine cotangents, missing rows, k_endog 1 and
+    2) and the ARMA-family reduced recursion of kf_p1.cuh (Z = e0, H = 0, companion T, complete data)."""
+    rng = np.random.default_rng(800 + m)
+    sym = lambda k, g: 0.5 * (g + g.T) if k in ("P0", "H", "Q") else g  # noqa: E731
+    for p in (1, 2)[:m]:  # thread-per-unit instantiations exist for k_endog <= k_states
+        args = random_system(rng, m, p, min(m, 2), 16, n_missing=2)
+        c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+        ll, gd = kt.dense_loglik_and_grads(*args, c=c, d=d)
+        outs, g, info = hostsim.run("standard", *args, c=c, d=d, strict=False, static_dims=True)
+        assert info == 0 and abs(outs[4] - ll) < 1e-11 * abs(ll)
+        for k in gd:
+            a, b = sym(k, np.asarray(g[k]).reshape(gd[k].shape)), sym(k, gd[k])
+            assert rel_err(a, b) < 1e-9 or np.abs(a - b).max() < 1e-13, (p, k)
+    # ARMA family: the four structure promises -> reduced recursion, 16-byte tape entries at k_states 2
+    args = list(random_system(rng, m, 1, 1, 20))
+    args[4], args[6] = np.eye(m)[:1].copy(), np.zeros((1, 1))
+    Tc = np.zeros((m, m))
+    Tc[:, 1:] = np.eye(m)[:, :m - 1]
+    Tc[:, 0] = rng.uniform(-0.5, 0.5, size=m) / np.arange(1, m + 1)
+    args[3] = Tc
+    ll, gd = kt.dense_loglik_and_grads(*args)
+    outs, g, info = hostsim.run("standard", *args, static_dims=True, full=False, pred=True, p1=True, skip=("Z", "H"),
+                                z_unit0=True, h_zero=True, t_companion=True, no_missing=True)
+    assert info == 0 and abs(outs[4] - ll) < 1e-11 * abs(ll)
+    for k in ("a0", "P0", "T", "R", "Q"):
+        a, b = sym(k, np.asarray(g[k]).reshape(gd[k].shape)), sym(k, gd[k])
+        if k == "T":
+            a, b = a[:, 0], b[:, 0]
+        assert rel_err(a, b) < 1e-9 or np.abs(a - b).max() < 1e-13, ("reduced", k)

@@ -9,7 +9,9 @@ golden vectors (they call statsmodels live), so the oracle is pinned on:
   * the documented quirk offsets (SURVEY A.2-Q1);
   * committed golden vectors of the oracle itself (tests/golden/*.npz, made by tests/golden/make_golden.py) so that
     any later change of the oracle is caught.
-Gradient values and multivariate values remain "parity unpinned" against the real reference.
+  * GRADIENTS: torch-autograd of the dense density (oracle.kalman_torch.dense_gaussian_loglik) - an algorithm-independent
+    known answer for all nine matrix cotangents and for d logp / d theta of BayesianARMA.
+Everything remains "parity unpinned" against the real reference itself (it has never run next to this code).
 """
 import os
 
@@ -229,3 +231,84 @@ def test_golden_vectors_of_the_oracle():
         np.testing.assert_allclose(out[0], z[key + "_fs"], rtol=1e-10, atol=1e-12)
         _, g = kt.loglik_and_grads(kind, *args)
         np.testing.assert_allclose(g["T"], z[key + "_gT"], rtol=1e-9, atol=1e-12)
+
+
+def _sym_if_square_sym_input(name, g):
+    # P0, H, Q are mathematically symmetric inputs: the entry-wise split of their gradient depends on how a graph uses
+    # each entry (DESIGN.md "gradient gauge"); the symmetric part is graph-independent
+    return 0.5 * (g + g.T) if name in ("P0", "H", "Q") else g
+
+
+@pytest.mark.parametrize("n_missing", [0, 3])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (3, 2, 2), (4, 3, 2)])
+def test_gradient_oracle_equals_autograd_of_dense_density(dims, n_missing):
+    """Pins the GRADIENT oracle on an algorithm-independent known answer: torch-autograd of the dense multivariate-normal
+    log-density of the stacked sample (oracle.kalman_torch.dense_gaussian_loglik - no recursion, no filter) against
+    torch-autograd of the restated filters, for all nine inputs (a0, P0, T, Z, R, H, Q, c, d), with all-missing rows.
+    The reference's gradient is autodiff of the same scalar, so this is the value it must have."""
+    m, p, r = dims
+    rng = np.random.default_rng(900 + 10 * m + p + n_missing)
+    args = random_system(rng, m, p, r, 14, n_missing=n_missing)
+    c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+    ll, gd = kt.dense_loglik_and_grads(*args, c=c, d=d)
+    assert abs(ll - kn.dense_gaussian_loglik(*args, c=c, d=d)) < 1e-11 * abs(ll)
+    kinds = ("standard", "cholesky", "single", "univariate") if p == 1 else ("standard", "cholesky")
+    for kind in kinds:
+        l2, g2 = kt.loglik_and_grads(kind, *args, c=c, d=d, strict_reference=False)
+        assert abs(l2 - ll) < 1e-11 * abs(ll), kind
+        for k in gd:
+            a, b = _sym_if_square_sym_input(k, g2[k]), _sym_if_square_sym_input(k, gd[k])
+            assert rel_err(a, b) < 1e-9, (kind, k)
+    if p > 1:  # the univariate filter needs a diagonal H to be the same model
+        args = random_system(rng, m, p, r, 14, n_missing=n_missing, diag_H=True)
+        ll, gd = kt.dense_loglik_and_grads(*args, c=c, d=d)
+        l2, g2 = kt.loglik_and_grads("univariate", *args, c=c, d=d)
+        assert abs(l2 - ll) < 1e-11 * abs(ll)
+        for k in gd:
+            a, b = _sym_if_square_sym_input(k, g2[k]), _sym_if_square_sym_input(k, gd[k])
+            if k == "H":  # the univariate filter reads diag(H) only
+                a, b = np.diag(a), np.diag(b)
+            assert rel_err(a, b) < 1e-9, ("univariate", k)
+
+
+@pytest.mark.parametrize("order", [(1, 1), (2, 1), (3, 2)])
+def test_theta_gradient_of_arma_equals_dense_density(order):
+    """theta-level pin for the north-star models (BayesianARMA, stationary initialisation, models/SARIMAX.py:59-107):
+    d logp / d theta from the restated model + filter + Lyapunov adjoint (the formula the reference uses) against
+    autograd of [theta -> matrices -> P0 by ONE dense Kronecker solve -> dense log-density]; and the plain-C port
+    (the timed CPU arm) against the same number."""
+    import torch
+
+    from oracle import kalman_c, models as om
+
+    p_, q_ = order
+    k_states = max(p_, q_ + 1)
+    rng = np.random.default_rng(40 + 10 * p_ + q_)
+    n = 40
+    y = rng.normal(size=(n, 1, 1))
+    theta = np.r_[rng.normal(size=k_states) * 0.3, 0.7, rng.uniform(-0.4, 0.4, size=p_) / np.arange(1, p_ + 1),
+                  rng.uniform(-0.5, 0.5, size=q_)]
+    fn = lambda th: om.arma_matrices(th, order)  # noqa: E731
+    lp, g = om.logp_and_grad_theta(fn, theta, y)
+
+    th = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    a0, _, T, Z, R, H, Q = om.arma_matrices(th, order)
+    P0 = kt.lyapunov_dense(T, R @ Q @ R.T)
+    ll = kt.dense_gaussian_loglik(y, a0, P0, T, Z, R, H, Q)
+    (gd,) = torch.autograd.grad(ll, [th])
+    assert abs(lp - float(ll.detach())) < 1e-11 * abs(lp)
+    assert rel_err(g, gd.numpy()) < 1e-9
+
+    # the C port evaluates matrices -> (loglik, matrix cotangents); chain them to theta with the dense map
+    th2 = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    a0, _, T, Z, R, H, Q = om.arma_matrices(th2, order)
+    RQR = R @ Q @ R.T
+    P0 = kt.lyapunov_dense(T, RQR)
+    npy = lambda v: v.detach().numpy()  # noqa: E731
+    ll_c, gm, bad = kalman_c.logp_grad_batch(y[:, :, 0], npy(a0)[None, :, 0], npy(P0)[None], npy(T)[None], npy(Z), npy(H),
+                                             npy(RQR)[None], nthreads=1)
+    assert bad == 0 and abs(ll_c[0] - float(ll.detach())) < 1e-11 * abs(lp)
+    surrogate = sum((torch.as_tensor(gm[k][0]).reshape(v.shape) * v).sum()
+                    for k, v in (("a0", a0), ("P0", P0), ("T", T), ("Z", Z), ("H", H), ("C", RQR)))
+    (gc,) = torch.autograd.grad(surrogate, [th2])
+    assert rel_err(gc.numpy(), gd.numpy()) < 1e-9
