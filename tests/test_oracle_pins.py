@@ -312,3 +312,36 @@ def test_theta_gradient_of_arma_equals_dense_density(order):
                     for k, v in (("a0", a0), ("P0", P0), ("T", T), ("Z", Z), ("H", H), ("C", RQR)))
     (gc,) = torch.autograd.grad(surrogate, [th2])
     assert rel_err(gc.numpy(), gd.numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate", "cholesky"])
+def test_theta_gradient_of_varmax_equals_dense_density(kind):
+    """BASELINE configs[2] at theta level (BayesianVARMAX(2,0), k_endog 3, measurement error, stationary initialisation,
+    whole rows missing; models/VARMAX.py:95-150): the oracle the CUDA kernels are compared with in
+    tests/test_gpu_logp_theta.py::test_varmax_theta_gradient_with_missing_rows, against autograd of
+    [theta -> matrices -> P0 by one dense Kronecker solve -> dense log-density with the missing rows deleted].
+    state_cov enters as theta.reshape(3, 3): entry-wise gauge, so its block is compared after symmetrisation."""
+    import torch
+
+    from oracle import models as om
+    from pymc_statespace_b200.synthetic import varmax20_workload
+
+    spec, y, theta = varmax20_workload(n_draws=3, n=30)
+    assert np.isnan(y).any()
+    sl = spec.param_slices["state_cov"]
+    for b in range(3):
+        lp, g = om.logp_and_grad_theta(lambda t: om.varmax_matrices(t, 3, (2, 0), True, True), theta[b], y[:, :, None], kind,
+                                       kind != "cholesky")
+        th = torch.tensor(theta[b], dtype=torch.float64, requires_grad=True)
+        a0, _, T, Z, R, H, Q = om.varmax_matrices(th, 3, (2, 0), True, True)
+        ll = kt.dense_gaussian_loglik(y[:, :, None], a0, kt.lyapunov_dense(T, R @ Q @ R.T), T, Z, R, H, Q)
+        (gd,) = torch.autograd.grad(ll, [th])
+        gd = gd.numpy().copy()
+        ll = float(ll.detach())
+        if kind == "standard":  # as-coded constant: log(2 pi) x 1 instead of x k_endog per observed row (SURVEY A.2-Q1)
+            ll += 0.5 * (3 - 1) * np.log(2 * np.pi) * int((~np.isnan(y).any(axis=1)).sum())
+        assert abs(lp - ll) < 1e-10 * abs(ll), (kind, lp, ll)
+        for arr in (g, gd):
+            blk = arr[sl].reshape(3, 3)
+            arr[sl] = (0.5 * (blk + blk.T)).reshape(-1)
+        assert rel_err(g, gd) < 1e-8, kind
