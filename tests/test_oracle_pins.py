@@ -21,7 +21,7 @@ import scipy.linalg
 
 from oracle import kalman_numpy as kn
 from oracle import kalman_torch as kt
-from tests.helpers import GOLDEN, make_test_inputs, nile_inputs, random_system, rel_err
+from tests.helpers import GOLDEN, make_test_inputs, nile_data, nile_inputs, random_system, rel_err
 
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (3, 2, 2), (4, 3, 2)])
@@ -345,3 +345,18 @@ def test_theta_gradient_of_varmax_equals_dense_density(kind):
             blk = arr[sl].reshape(3, 3)
             arr[sl] = (0.5 * (blk + blk.T)).reshape(-1)
         assert rel_err(g, gd) < 1e-8, kind
+
+
+def test_nile_local_level_soft_known_answer_from_the_literature():
+    """SOFT pin (3 decimals), BASELINE configs[0] (true local level, k_states 1): the Nile local-level model at its
+    maximum-likelihood variances is a textbook example (Durbin & Koopman 2012, ch. 2: sigma2_eps = 15,099,
+    sigma2_eta = 1,469.1); statsmodels' UnobservedComponents("local level") documentation prints llf = -632.538 for it
+    (sigma2.irregular 1.508e+04, sigma2.level 1478.81; approximate diffuse start P0 = 1e6, first observation burned).
+    The value is QUOTED FROM MEMORY of public documentation - there is no network here and it is not in /root/reference -
+    hence soft: 1e-3 absolute, both parameter sets (the likelihood is flat at its maximum)."""
+    y = np.asarray(nile_data(), dtype=float).reshape(-1, 1, 1)
+    one = np.eye(1)
+    for H, Q in ((15080.0, 1478.81), (15099.0, 1469.1)):
+        for kind in ("standard", "cholesky", "single", "univariate"):
+            out = kn.kalman_filter(kind, y, np.zeros((1, 1)), 1e6 * one, one, one, one, H * one, Q * one)
+            assert abs(out[5][1:].sum() - (-632.538)) < 1e-3, (kind, H, Q, out[5][1:].sum())
