@@ -363,6 +363,44 @@ def _dense_gaussian_loglik_mp(data, a0, P0, T, Z, R, H, Q, c, d, digits):
         return float(-(len(keep) * mp.log(2 * mp.pi) + quad) / 2 - logdet)
 
 
+def dense_gaussian_state_moments(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
+    """Conditional moments of the states from the joint Gaussian of (x_0..x_n, y_0..y_{n-1}), by dense linear algebra
+    only (no recursion shared with the filter or the smoother): returns a function ``cond(t, s)`` giving
+    (E[x_t | y_0..y_s], Cov[x_t | y_0..y_s]); s = t: filtered, t = s + 1: predicted, s = n - 1: smoothed.  x_0 ~ N(a0, P0) is
+    the predicted state of the first step (kalman_filter.py:235-252).  Static matrices; missing entries are dropped from
+    the conditioning set.  Small cases only."""
+    data = np.asarray(data, dtype=np.float64)
+    n, p = data.shape[0], data.shape[1]
+    m = T.shape[0]
+    c = np.zeros((m, 1)) if c is None else c
+    d = np.zeros((p, 1)) if d is None else d
+    RQR = R @ Q @ R.T
+    means, covs = [a0], [P0]
+    for _ in range(n):
+        means.append(T @ means[-1] + c)
+        covs.append(T @ covs[-1] @ T.T + RQR)
+    Tpow = [np.eye(m)]
+    for _ in range(n + 1):
+        Tpow.append(T @ Tpow[-1])
+
+    def cov_xx(t, s):  # Cov(x_t, x_s)
+        return Tpow[t - s] @ covs[s] if t >= s else (Tpow[s - t] @ covs[t]).T
+
+    def cond(t, s):
+        idx = [(k, i) for k in range(s + 1) for i in range(p) if not np.isnan(data[k, i, 0])]
+        if not idx:
+            return means[t], covs[t]
+        Zr = lambda i: Z[i : i + 1, :]  # noqa: E731
+        Syy = np.array([[(Zr(i) @ cov_xx(k, l) @ Zr(j).T)[0, 0] + (H[i, j] if k == l else 0.0) for (l, j) in idx]
+                        for (k, i) in idx])
+        Sxy = np.concatenate([cov_xx(t, k) @ Zr(i).T for (k, i) in idx], axis=1)
+        resid = np.array([[data[k, i, 0] - (Zr(i) @ means[k])[0, 0] - d[i, 0]] for (k, i) in idx])
+        W = np.linalg.solve(Syy, Sxy.T).T
+        return means[t] + W @ resid, covs[t] - W @ Sxy.T
+
+    return cond
+
+
 # ----------------------------------------------------------------------------
 # RTS smoother (SURVEY.md section 8(f) row f2 - not on the logp/grad path)
 # ----------------------------------------------------------------------------

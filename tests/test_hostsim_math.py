@@ -388,3 +388,32 @@ def test_device_math_gradient_equals_autograd_of_dense_density(m):
         if k == "T":
             a, b = a[:, 0], b[:, 0]
         assert rel_err(a, b) < 1e-9 or np.abs(a - b).max() < 1e-13, ("reduced", k)
+
+
+def test_device_math_moments_and_smoother_equal_dense_conditional_moments():
+    """Full-output device math (filtered / predicted moments) and the device RTS smoother, compiled for the host, against
+    the dense conditional moments of the joint Gaussian (oracle.kalman_numpy.dense_gaussian_state_moments) - a known answer
+    that shares no recursion with them."""
+    import ctypes
+
+    lib = hostsim.build()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rng = np.random.default_rng(77)
+    for (m, p, r), static in (((2, 1, 1), True), ((3, 2, 2), True), ((4, 3, 2), False)):
+        n = 10
+        args = random_system(rng, m, p, r, n, n_missing=2)
+        d = rng.normal(size=(p, 1))
+        cond = kn.dense_gaussian_state_moments(*args, d=d)
+        outs, _, info = hostsim.run("standard", *args, d=d, strict=False, static_dims=static, do_bwd=False)
+        assert info == 0
+        fs, ps, fc, pc = outs[:4]
+        for t in range(n):
+            for (got_a, got_P), (a, P) in (((fs[t], fc[t]), cond(t, t)), ((ps[t + 1], pc[t + 1]), cond(t + 1, t))):
+                assert rel_err(got_a, a) < 1e-10 and rel_err(got_P, P) < 1e-10, (m, t)
+        T, R, Q = (np.ascontiguousarray(args[i]) for i in (3, 5, 7))
+        f1, f2 = np.ascontiguousarray(fs[..., 0]), np.ascontiguousarray(fc)
+        ss, sc = np.zeros_like(f1), np.zeros_like(f2)
+        assert lib.hostsim_smoother(n, m, vp(T), vp(np.ascontiguousarray(R @ Q @ R.T)), vp(f1), vp(f2), vp(ss), vp(sc)) == 0
+        for t in range(n):
+            a, P = cond(t, n - 1)
+            assert rel_err(ss[t], a[:, 0]) < 1e-10 and rel_err(sc[t], P) < 1e-10, (m, t)

@@ -360,3 +360,33 @@ def test_nile_local_level_soft_known_answer_from_the_literature():
         for kind in ("standard", "cholesky", "single", "univariate"):
             out = kn.kalman_filter(kind, y, np.zeros((1, 1)), 1e6 * one, one, one, one, H * one, Q * one)
             assert abs(out[5][1:].sum() - (-632.538)) < 1e-3, (kind, H, Q, out[5][1:].sum())
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (3, 2, 2), (4, 3, 2)])
+def test_filtered_predicted_and_smoothed_moments_equal_dense_conditional_moments(dims):
+    """Pins the per-step outputs (rows a1 / f2) on an algorithm-independent known answer: the conditional moments of the
+    joint Gaussian of states and observations by dense linear algebra (oracle.kalman_numpy.dense_gaussian_state_moments):
+    filtered = E / Cov[x_t | y_0..t], predicted = [x_{t+1} | y_0..t], RTS-smoothed = [x_t | y_0..n-1]; whole rows missing,
+    intercepts c and d (the reference's smoother has no intercept in its predict step, kalman_smoother.py:99-104: c = 0
+    there).  All exact filters; univariate with a diagonal H."""
+    m, p, r = dims
+    n = 10
+    rng = np.random.default_rng(60 + m)
+    for diag_H in (False, True):
+        args = random_system(rng, m, p, r, n, n_missing=2, diag_H=diag_H)
+        c, d = rng.normal(size=(m, 1)), rng.normal(size=(p, 1))
+        kinds = ("standard", "cholesky") + (("univariate",) if diag_H or p == 1 else ()) + (("single",) if p == 1 else ())
+        cond = kn.dense_gaussian_state_moments(*args, c=c, d=d)
+        for kind in kinds:
+            fs, ps, fc, pc = kn.kalman_filter(kind, *args, c=c, d=d, strict_reference=False)[:4]
+            np.testing.assert_allclose(ps[0], args[1])
+            np.testing.assert_allclose(pc[0], args[2])
+            for t in range(n):
+                for (got_a, got_P), (a, P) in (((fs[t], fc[t]), cond(t, t)), ((ps[t + 1], pc[t + 1]), cond(t + 1, t))):
+                    assert rel_err(got_a, a) < 1e-10 and rel_err(got_P, P) < 1e-10, (kind, t)
+        cond = kn.dense_gaussian_state_moments(*args, d=d)
+        out = kn.kalman_filter("standard", *args, d=d, strict_reference=False)
+        ss, sc = kn.kalman_smoother(args[3], args[5], args[7], out[0], out[2])
+        for t in range(n):
+            a, P = cond(t, n - 1)
+            assert rel_err(ss[t], a) < 1e-10 and rel_err(sc[t], P) < 1e-10, t
