@@ -363,6 +363,41 @@ def _dense_gaussian_loglik_mp(data, a0, P0, T, Z, R, H, Q, c, d, digits):
         return float(-(len(keep) * mp.log(2 * mp.pi) + quad) / 2 - logdet)
 
 
+def dense_gaussian_loglik_time_varying(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
+    """``dense_gaussian_loglik`` for time-varying matrices (any of T, Z, R, H, Q, c, d may be 3-D, time first, as
+    filters/utilities.py:9-14 slices them): x_{t+1} = T_t x_t + c_t + R_t eta_t (Q_t), y_t = Z_t x_t + d_t + eps_t (H_t).
+    Dense algebra only; whole-row / single-entry missing values are deleted."""
+    data = np.asarray(data, dtype=np.float64)
+    n, p = data.shape[0], data.shape[1]
+    at = lambda M, t: None if M is None else (M[t] if np.ndim(M) == 3 else M)  # noqa: E731
+    m = at(T, 0).shape[0]
+    zc, zd = np.zeros((m, 1)), np.zeros((p, 1))
+    ct = lambda t: zc if c is None else at(c, t)  # noqa: E731
+    dt = lambda t: zd if d is None else at(d, t)  # noqa: E731
+    means, covs = [a0], [P0]
+    for t in range(n - 1):
+        Tt, Rt = at(T, t), at(R, t)
+        means.append(Tt @ means[-1] + ct(t))
+        covs.append(Tt @ covs[-1] @ Tt.T + Rt @ at(Q, t) @ Rt.T)
+    mu = np.concatenate([at(Z, t) @ means[t] + dt(t) for t in range(n)], axis=0).ravel()
+    S = np.zeros((n * p, n * p))
+    for s in range(n):
+        Phi = np.eye(m)  # T_{t-1} ... T_s
+        for t in range(s, n):
+            blk = at(Z, t) @ (Phi @ covs[s]) @ at(Z, s).T  # Cov(y_t, y_s)
+            if s == t:
+                blk = blk + at(H, t)
+            S[t * p : (t + 1) * p, s * p : (s + 1) * p] = blk
+            S[s * p : (s + 1) * p, t * p : (t + 1) * p] = blk.T
+            Phi = at(T, t) @ Phi
+    yflat = data.reshape(n * p)
+    keep = ~np.isnan(yflat)
+    yv = (yflat - mu)[keep]
+    L = np.linalg.cholesky(S[np.ix_(keep, keep)])
+    w = scipy.linalg.solve_triangular(L, yv, lower=True)
+    return float(-0.5 * (int(keep.sum()) * LOG_2PI + w @ w) - np.log(np.diag(L)).sum())
+
+
 def dense_gaussian_state_moments(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
     """Conditional moments of the states from the joint Gaussian of (x_0..x_n, y_0..y_{n-1}), by dense linear algebra
     only (no recursion shared with the filter or the smoother): returns a function ``cond(t, s)`` giving

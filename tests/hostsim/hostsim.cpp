@@ -126,9 +126,16 @@ extern "C" int hostsim_run(int mk, int m, int p, int n, const double* y, const d
 #undef KFB_P1CASE
     return 2;
   }
+  const bool tv_any = ts[0] || ts[1] || ts[2] || ts[3] || ts[4] || ts[5];
   if (static_dims) {
 #define KFB_CASE(MM, PP)                                   \
   if (m == MM && p == PP) {                                \
+    if (tv_any) { /* the time-varying instantiation (standard filter only, kf_thread_inst.inc pick_kind) */ \
+      if (mk != MK_STD) return 7;                          \
+      ThreadCtx<MM, PP, true> x{nullptr, nullptr, 0, 1};   \
+      run_both<MK_STD>(x, A, do_bwd);                      \
+      return 0;                                            \
+    }                                                      \
     ThreadCtx<MM, PP> x{nullptr, nullptr, 0, 1};                         \
     run_kind(x, A, do_bwd);                                \
     return 0;                                              \

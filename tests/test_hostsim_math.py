@@ -417,3 +417,20 @@ def test_device_math_moments_and_smoother_equal_dense_conditional_moments():
         for t in range(n):
             a, P = cond(t, n - 1)
             assert rel_err(ss[t], a[:, 0]) < 1e-10 and rel_err(sc[t], P) < 1e-10, (m, t)
+
+
+@pytest.mark.parametrize("static", [True, False], ids=["ThreadCtx", "CoopCtx"])
+def test_device_math_time_varying_loglik_equals_dense_density(static):
+    """Row f3 on the device math: time-varying T, Z, R, H, Q, c, d against the dense density of the stacked sample."""
+    rng = np.random.default_rng(11)
+    n, m, p, r = 12, 3, 2, 2
+    systems = [random_system(rng, m, p, r, n, n_missing=2) for _ in range(n)]
+    y, a0, P0 = systems[0][:3]
+    T, Z, R, H, Q = (np.stack([s[i] for s in systems]) for i in range(3, 8))
+    c, d = rng.normal(size=(n, m, 1)), rng.normal(size=(n, p, 1))
+    dense = kn.dense_gaussian_loglik_time_varying(y, a0, P0, T, Z, R, H, Q, c, d)
+    outs, _, info = hostsim.run("standard", y, a0, P0, T, Z, R, H, Q, c=c, d=d, strict=False, static_dims=static, do_bwd=False)
+    assert info == 0 and abs(outs[4] - dense) < 1e-10 * abs(dense)
+    # all six outputs and every cotangent of the time-varying instantiation against the oracle (strict and corrected)
+    _check("standard", (y, a0, P0, T, Z, R, H, Q), c, d, True, static)
+    _check("standard", (y, a0, P0, T, Z, R, H, Q), c, d, False, static, w=rng.normal(size=n))

@@ -390,3 +390,26 @@ def test_filtered_predicted_and_smoothed_moments_equal_dense_conditional_moments
         for t in range(n):
             a, P = cond(t, n - 1)
             assert rel_err(ss[t], a) < 1e-10 and rel_err(sc[t], P) < 1e-10, t
+
+
+def test_time_varying_loglik_equals_dense_gaussian_density():
+    """Row f3: the reference tests time-varying inputs for shapes only (tests/test_kalman_filter.py:102-156).  Values are
+    pinned here on the dense density with time-varying T, Z, R, H, Q, c, d (time first, filters/utilities.py:9-14:
+    matrices of step t in the update AND the predict of step t), all varying / only T varying / single series."""
+    rng = np.random.default_rng(1)
+    n, m, p, r = 12, 3, 2, 2
+    systems = [random_system(rng, m, p, r, n, n_missing=2) for _ in range(n)]
+    y, a0, P0 = systems[0][:3]
+    T, Z, R, H, Q = (np.stack([s[i] for s in systems]) for i in range(3, 8))
+    c, d = rng.normal(size=(n, m, 1)), rng.normal(size=(n, p, 1))
+    dense = kn.dense_gaussian_loglik_time_varying(y, a0, P0, T, Z, R, H, Q, c, d)
+    for kind in ("standard", "cholesky"):
+        assert abs(kn.kalman_filter(kind, y, a0, P0, T, Z, R, H, Q, c=c, d=d, strict_reference=False)[4] - dense) < 1e-10 * abs(dense)
+    dense = kn.dense_gaussian_loglik_time_varying(y, a0, P0, T, Z[0], R[0], H[0], Q[0])
+    assert abs(kn.kalman_filter("standard", y, a0, P0, T, Z[0], R[0], H[0], Q[0], strict_reference=False)[4] - dense) < 1e-10 * abs(dense)
+    assert abs(kn.dense_gaussian_loglik_time_varying(*systems[0]) - kn.dense_gaussian_loglik(*systems[0])) < 1e-12
+    y1 = y[:, :1]
+    dense = kn.dense_gaussian_loglik_time_varying(y1, a0, P0, T, Z[:, :1], R, H[:, :1, :1], Q, c, d[:, :1])
+    for kind in ("standard", "cholesky", "single"):
+        got = kn.kalman_filter(kind, y1, a0, P0, T, Z[:, :1], R, H[:, :1, :1], Q, c=c, d=d[:, :1], strict_reference=False)[4]
+        assert abs(got - dense) < 1e-10 * abs(dense), kind
