@@ -305,3 +305,15 @@ def dense_loglik_and_grads(data, a0, P0, T, Z, R, H, Q, c=None, d=None):
     grads = torch.autograd.grad(ll, list(ins.values()), allow_unused=True)
     gd = {k: (np.zeros_like(ins[k].detach().numpy()) if g is None else g.numpy()) for k, g in zip(GRAD_NAMES, grads)}
     return float(ll.detach()), gd
+
+
+def dare_by_riccati_iteration(T, Z, RQR, H, iters=300):
+    """Stabilising solution of the filter DARE by plain fixed-point iteration of the Riccati recursion, differentiable
+    torch ops only: ``torch.autograd`` through the unrolled iteration is a gradient that shares nothing with the adjoint
+    formula of ``_DARE`` (utils/pytensor_scipy.py:39-60).  For contracting systems (the tests' scale of T)."""
+    P = RQR.clone()
+    for _ in range(iters):
+        M = P @ Z.T
+        P = T @ (P - M @ torch.linalg.solve(Z @ M + H, M.T)) @ T.T + RQR
+        P = 0.5 * (P + P.T)
+    return P

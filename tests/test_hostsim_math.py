@@ -434,3 +434,24 @@ def test_device_math_time_varying_loglik_equals_dense_density(static):
     # all six outputs and every cotangent of the time-varying instantiation against the oracle (strict and corrected)
     _check("standard", (y, a0, P0, T, Z, R, H, Q), c, d, True, static)
     _check("standard", (y, a0, P0, T, Z, R, H, Q), c, d, False, static, w=rng.normal(size=n))
+
+
+def test_device_math_steady_state_gradient_equals_dense_density_at_the_riccati_fixed_point():
+    """Steady-state device math (forward + adjoint incl. the P_ss / F^-1 cotangents chained through the DARE adjoint)
+    against autograd of [unrolled Riccati iteration -> dense density started at P_ss] - no shared recursion or adjoint."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    sym = lambda k, a: 0.5 * (a + a.T) if k in ("H", "Q") else a  # noqa: E731
+    for (m, p, r), static in (((2, 1, 1), True), ((4, 2, 2), True), ((4, 3, 2), False)):
+        args = list(random_system(rng, m, p, r, 14))
+        names = ("a0", "P0", "T", "Z", "R", "H", "Q")
+        ins = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in zip(names, args[1:])}
+        T, Z, R, H, Q = (ins[k] for k in ("T", "Z", "R", "H", "Q"))
+        lld = kt.dense_gaussian_loglik(args[0], ins["a0"], kt.dare_by_riccati_iteration(T, Z, R @ Q @ R.T, H), T, Z, R, H, Q)
+        gs = dict(zip(names, torch.autograd.grad(lld, [ins[k] for k in names], allow_unused=True)))
+        outs, g, info = hostsim.run("steady_state", *args, strict=False, static_dims=static)
+        assert info == 0 and abs(outs[4] - float(lld.detach())) < 1e-10 * abs(outs[4])
+        for k in ("a0", "T", "Z", "R", "H", "Q"):
+            a, b = sym(k, np.asarray(g[k]).reshape(gs[k].shape)), sym(k, gs[k].numpy())
+            assert rel_err(a, b) < 1e-7, (m, k)  # 1e-7: the tolerance of every steady-state gradient test (DESIGN section 2)

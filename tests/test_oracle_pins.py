@@ -413,3 +413,28 @@ def test_time_varying_loglik_equals_dense_gaussian_density():
     for kind in ("standard", "cholesky", "single"):
         got = kn.kalman_filter(kind, y1, a0, P0, T, Z[:, :1], R, H[:, :1, :1], Q, c=c, d=d[:, :1], strict_reference=False)[4]
         assert abs(got - dense) < 1e-10 * abs(dense), kind
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 1), (4, 2, 2), (4, 3, 2)])
+def test_steady_state_filter_equals_dense_density_started_at_the_riccati_fixed_point(dims):
+    """Row a8: on complete data the steady-state filter (kalman_filter.py:354-441) IS the exact filter started at
+    P0 = P_ss (P_t = P_ss for every t), so its loglik equals the dense density with that P0 and its gradient equals
+    autograd of [matrices -> P_ss by unrolled Riccati iteration -> dense density]: pins the filter, scipy's DARE and
+    the DARE adjoint formula (utils/pytensor_scipy.py:39-60) on an answer that shares nothing with them; P0 gets zero
+    gradient.  Corrected constants (strict_reference=False: log 2 pi x k_endog)."""
+    import torch
+
+    m, p, r = dims
+    args = list(random_system(np.random.default_rng(9 + m + p), m, p, r, 14))
+    ll, g = kt.loglik_and_grads("steady_state", *args, strict_reference=False)
+    names = ("a0", "P0", "T", "Z", "R", "H", "Q")
+    ins = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in zip(names, args[1:])}
+    T, Z, R, H, Q = (ins[k] for k in ("T", "Z", "R", "H", "Q"))
+    Pss = kt.dare_by_riccati_iteration(T, Z, R @ Q @ R.T, H)
+    lld = kt.dense_gaussian_loglik(args[0], ins["a0"], Pss, T, Z, R, H, Q)
+    gs = torch.autograd.grad(lld, [ins[k] for k in names], allow_unused=True)
+    assert abs(ll - float(lld.detach())) < 1e-11 * abs(ll)
+    assert np.abs(g["P0"]).max() == 0.0 and gs[1] is None
+    for k, gd in zip(names, gs):
+        if gd is not None:
+            assert rel_err(_sym_if_square_sym_input(k, g[k]), _sym_if_square_sym_input(k, gd.numpy())) < 1e-9, k
