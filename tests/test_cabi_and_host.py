@@ -250,3 +250,29 @@ def test_pytensor_adapter_is_import_guarded():
     if not pytensor_op.HAVE_PYTENSOR:
         with pytest.raises(ImportError, match="pytensor is not installed"):
             pytensor_op.build_symbolic_graph(None, *[None] * 8)
+
+
+def test_reference_arm_uses_every_core_under_torchrun_env_and_only_rank0_prints():
+    """torchrun exports OMP_NUM_THREADS=1 and round 1's N >= 2 CPU arm ran on one core.  `bench.py --impl
+    reference` must use every host core regardless, print ONE JSON line with the contract's keys on rank 0, and exit 0
+    silently on the other ranks (no GPU involved: the arm times oracle/kalman_c.c here)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--cpu-sample-draws", "256", "--n", "200"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "kalman_logp_grad_filter_steps_per_s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["c5"]["cores"] == line["cpu_baseline"]["cores"]
+    out = subprocess.run(cmd, env=dict(env, RANK="1"), capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
